@@ -1,0 +1,417 @@
+"""ctypes binding of the C ABI (include/gkr_msm_b200.h) plus thin python mirrors of the reference's
+host-side objects.  There is NO CPU fallback here: if the shared library is missing or no CUDA device
+is present, construction fails loudly.
+
+Field elements at this level are numpy uint64 arrays of shape (..., 4): canonical Montgomery limbs,
+the reference's own `Vec<Fr>` memory layout.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgkr_msm_b200.so")
+
+GATE_AFF_L1, GATE_AFF_L2, GATE_AFF_L3 = 0, 1, 2
+GATE_PRJ_L1, GATE_PRJ_L2, GATE_PRJ_L3 = 3, 4, 5
+GATE_TRI_L1, GATE_BITCHECK, GATE_LOGUP_LAYER, GATE_ADD_INVERSES = 6, 7, 8, 9
+GATE_PROD3, GATE_FOLDED_PROD, GATE_ID, GATE_AFF_L1_BITCHECK2 = 10, 11, 12, 13
+SO_PLAIN, SO_EQ_GAMMA = 0, 1
+
+GKR_OK, GKR_ERR_CUDA, GKR_ERR_ARG, GKR_ERR_PROTOCOL, GKR_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+
+
+class GkrError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"gkr_msm_b200 status {code}: {msg}")
+        self.code = code
+
+
+def build_library(force: bool = False) -> str:
+    """Compile every CUDA source for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", _HERE, "-j8"]
+    if force:
+        subprocess.check_call(["make", "-C", _HERE, "clean"])
+    subprocess.check_call(args)
+    return LIB_PATH
+
+
+_lib = None
+
+_u64p = C.POINTER(C.c_uint64)
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+
+
+def _sig(lib):
+    def f(name, res, *args):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+    f("gkr_version", C.c_int)
+    f("gkr_ctx_create", C.c_int, C.c_int, C.POINTER(_vp))
+    f("gkr_ctx_destroy", None, _vp)
+    f("gkr_last_error", C.c_char_p, _vp)
+    f("gkr_ctx_sync", C.c_int, _vp)
+    f("gkr_ctx_launch_count", C.c_uint64, _vp)
+    f("gkr_ctx_stream", _vp, _vp)
+    f("gkr_ctx_timing_enable", C.c_int, _vp, C.c_int)
+    f("gkr_ctx_timing_read", C.c_int, _vp, _vp, _vp, _vp, C.c_int)
+    f("gkr_bench_modmul", C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
+    f("gkr_table_upload", C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp))
+    f("gkr_table_download", C.c_int, _vp, _vp, _vp)
+    f("gkr_table_alloc", C.c_int, _vp, C.c_uint64, C.POINTER(_vp))
+    f("gkr_table_synth", C.c_int, _vp, C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(_vp))
+    f("gkr_table_len", C.c_uint64, _vp)
+    f("gkr_table_device_ptr", _vp, _vp)
+    f("gkr_table_free", None, _vp)
+    f("gkr_eq_table", C.c_int, _vp, _vp, C.c_uint32, _vp, C.POINTER(_vp))
+    f("gkr_dense_gate_sum", C.c_int, _vp, C.c_int, C.c_int, C.c_uint32, _vp, C.c_uint32, C.POINTER(_vp), C.c_uint32, _vp)
+    f("gkr_so_create_dense", C.c_int, _vp, C.c_int, C.c_int, C.c_uint32, _vp, C.c_uint32, C.POINTER(_vp), C.c_uint32,
+      C.c_uint32, _vp, C.POINTER(_vp))
+    f("gkr_so_unipoly", C.c_int, _vp, _vp, C.POINTER(C.c_uint32))
+    f("gkr_so_bind", C.c_int, _vp, _vp)
+    f("gkr_so_final_evals", C.c_int, _vp, _vp)
+    f("gkr_so_claim", C.c_int, _vp, _vp)
+    f("gkr_so_degree", C.c_uint32, _vp)
+    f("gkr_so_num_polys", C.c_uint32, _vp)
+    f("gkr_so_round", C.c_uint32, _vp)
+    f("gkr_so_destroy", None, _vp)
+    f("gkr_transcript_new", C.c_int, _vp, C.c_size_t, C.POINTER(_vp))
+    f("gkr_transcript_free", None, _vp)
+    f("gkr_transcript_write_scalars", C.c_int, _vp, _vp, C.c_uint32)
+    f("gkr_transcript_write_raw", C.c_int, _vp, _vp, C.c_size_t)
+    f("gkr_transcript_challenge", C.c_int, _vp, C.c_uint32, _vp)
+    f("gkr_transcript_raw_challenge", C.c_int, _vp, _vp, C.c_size_t)
+    f("gkr_transcript_proof_len", C.c_size_t, _vp)
+    f("gkr_transcript_proof", C.c_int, _vp, _vp)
+    f("gkr_sumcheck_prove", C.c_int, _vp, _vp, C.c_uint32, _vp, _vp, _vp)
+    f("gkr_exchange_open", C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_vp))
+    f("gkr_exchange_close", None, _vp)
+    f("gkr_exchange_allgather", C.c_int, _vp, _vp, C.c_uint32, _vp)
+    f("gkr_sumcheck_prove_sharded", C.c_int, _vp, _vp, _vp, C.c_uint32, C.c_int, C.c_int, C.c_uint32, _vp, C.c_uint32, _vp, _vp, _vp, _vp)
+
+
+def load_library():
+    """dlopen the in-tree shared library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GkrError(GKR_ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                         "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _sig(_lib)
+    return _lib
+
+
+def _limbs(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    return a
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+class Context:
+    """gkr_ctx: one per GPU / per calling thread."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.gkr_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise GkrError(rc, "gkr_ctx_create failed: no usable CUDA device (this backend has no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gkr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc):
+        if rc != 0:
+            raise GkrError(rc, self.lib.gkr_last_error(self.h).decode())
+
+    def sync(self):
+        self.check(self.lib.gkr_ctx_sync(self.h))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.gkr_ctx_launch_count(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.gkr_ctx_stream(self.h) or 0)
+
+    def timing_enable(self, on: bool = True):
+        self.check(self.lib.gkr_ctx_timing_enable(self.h, 1 if on else 0))
+
+    def timing_read(self, max_n: int = 4096):
+        """[(kernel_id, n_items, ms)] of every launch recorded since the last read."""
+        kid = np.zeros(max_n, np.int32)
+        items = np.zeros(max_n, np.uint64)
+        ms = np.zeros(max_n, np.float32)
+        n = self.lib.gkr_ctx_timing_read(self.h, _ptr(kid), _ptr(items), _ptr(ms), max_n)
+        return [(int(kid[i]), int(items[i]), float(ms[i])) for i in range(n)]
+
+    def bench_modmul(self, ilp=2, threads=128, blocks_per_sm=8, iters=2000) -> float:
+        out = C.c_double(0)
+        self.check(self.lib.gkr_bench_modmul(self.h, ilp, threads, blocks_per_sm, iters, C.byref(out)))
+        return out.value
+
+    # -- tables ------------------------------------------------------------------------------
+    def upload(self, limbs) -> "Table":
+        a = _limbs(limbs).reshape(-1, 4)
+        return self.upload_ptr(a.ctypes.data, a.shape[0], keep=a)
+
+    def upload_ptr(self, host_ptr: int, n: int, keep=None) -> "Table":
+        h = _vp()
+        self.check(self.lib.gkr_table_upload(self.h, _vp(host_ptr), n, C.byref(h)))
+        t = Table(self, h)
+        t._keep = keep
+        return t
+
+    def synth(self, seed: int, n: int, first_index: int = 0) -> "Table":
+        h = _vp()
+        self.check(self.lib.gkr_table_synth(self.h, seed & 0xFFFFFFFFFFFFFFFF, first_index, n, C.byref(h)))
+        return Table(self, h)
+
+    def eq_table(self, point, mult=None) -> "Table":
+        p = _limbs(point).reshape(-1, 4)
+        if mult is None:
+            mult = MONT_ONE
+        m = _limbs(mult).reshape(4)
+        h = _vp()
+        self.check(self.lib.gkr_eq_table(self.h, _ptr(p), p.shape[0], _ptr(m), C.byref(h)))
+        return Table(self, h)
+
+    def gate_sum(self, so_kind, gate, tables, gate_param=0, consts=None) -> np.ndarray:
+        c = _limbs(consts).reshape(-1, 4) if consts is not None else np.zeros((0, 4), np.uint64)
+        arr = (_vp * len(tables))(*[t.h for t in tables])
+        out = np.zeros(4, np.uint64)
+        self.check(self.lib.gkr_dense_gate_sum(self.h, so_kind, gate, gate_param, _ptr(c), c.shape[0], arr, len(tables), _ptr(out)))
+        return out
+
+    def dense_so(self, so_kind, gate, tables, num_vars, claim, gate_param=0, consts=None) -> "SumcheckObject":
+        c = _limbs(consts).reshape(-1, 4) if consts is not None else np.zeros((0, 4), np.uint64)
+        arr = (_vp * len(tables))(*[t.h for t in tables])
+        cl = _limbs(claim).reshape(4)
+        h = _vp()
+        self.check(self.lib.gkr_so_create_dense(self.h, so_kind, gate, gate_param, _ptr(c), c.shape[0], arr, len(tables),
+                                                num_vars, _ptr(cl), C.byref(h)))
+        return SumcheckObject(self, h, list(tables))
+
+
+MONT_ONE = np.array([0x00000001FFFFFFFE, 0x5884B7FA00034802, 0x998C4FEFECBC4FF5, 0x1824B159ACC5056F], dtype=np.uint64)
+
+
+class Table:
+    """gkr_table: a `Vec<Fr>` resident in HBM."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+        self._keep = None
+
+    def __len__(self):
+        return int(self.ctx.lib.gkr_table_len(self.h))
+
+    @property
+    def device_ptr(self) -> int:
+        return int(self.ctx.lib.gkr_table_device_ptr(self.h) or 0)
+
+    def download(self) -> np.ndarray:
+        out = np.empty((len(self), 4), np.uint64)
+        self.ctx.check(self.ctx.lib.gkr_table_download(self.ctx.h, self.h, _ptr(out)))
+        return out
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.gkr_table_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+class SumcheckObject:
+    """gkr_so: `trait Sumcheckable` (src/cleanup/protocols/sumchecks/vecvec_eq.rs:218-225)."""
+
+    def __init__(self, ctx: Context, h, keep):
+        self.ctx, self.h, self._keep = ctx, h, keep
+
+    def unipoly(self) -> np.ndarray:
+        """evaluations of the round polynomial at 0..deg, shape (deg+1, 4)."""
+        out = np.zeros((8, 4), np.uint64)
+        n = C.c_uint32(0)
+        self.ctx.check(self.ctx.lib.gkr_so_unipoly(self.h, _ptr(out), C.byref(n)))
+        return out[: n.value].copy()
+
+    def bind(self, t):
+        tt = _limbs(t).reshape(4)
+        self.ctx.check(self.ctx.lib.gkr_so_bind(self.h, _ptr(tt)))
+
+    def final_evals(self) -> np.ndarray:
+        out = np.zeros((self.num_polys, 4), np.uint64)
+        self.ctx.check(self.ctx.lib.gkr_so_final_evals(self.h, _ptr(out)))
+        return out
+
+    @property
+    def claim(self) -> np.ndarray:
+        out = np.zeros(4, np.uint64)
+        self.ctx.lib.gkr_so_claim(self.h, _ptr(out))
+        return out
+
+    @property
+    def degree(self) -> int:
+        return int(self.ctx.lib.gkr_so_degree(self.h))
+
+    @property
+    def num_polys(self) -> int:
+        return int(self.ctx.lib.gkr_so_num_polys(self.h))
+
+    @property
+    def round(self) -> int:
+        return int(self.ctx.lib.gkr_so_round(self.h))
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.gkr_so_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.destroy()
+        except Exception:
+            pass
+
+
+class Transcript:
+    """gkr_transcript: ProofTranscript2 in prover mode (src/cleanup/proof_transcript.rs:76-147)."""
+
+    def __init__(self, label: bytes):
+        self.lib = load_library()
+        h = _vp()
+        buf = (C.c_uint8 * len(label)).from_buffer_copy(label) if label else None
+        rc = self.lib.gkr_transcript_new(buf, len(label), C.byref(h))
+        if rc:
+            raise GkrError(rc, "gkr_transcript_new")
+        self.h = h
+
+    def write_scalars(self, limbs):
+        a = _limbs(limbs).reshape(-1, 4)
+        rc = self.lib.gkr_transcript_write_scalars(self.h, _ptr(a), a.shape[0])
+        if rc:
+            raise GkrError(rc, "write_scalars: non-canonical element")
+
+    def write_raw(self, msg: bytes):
+        buf = (C.c_uint8 * len(msg)).from_buffer_copy(msg) if msg else None
+        rc = self.lib.gkr_transcript_write_raw(self.h, buf, len(msg))
+        if rc:
+            raise GkrError(rc, "write_raw")
+
+    def challenge(self, bitsize: int = 128) -> np.ndarray:
+        out = np.zeros(4, np.uint64)
+        rc = self.lib.gkr_transcript_challenge(self.h, bitsize, _ptr(out))
+        if rc:
+            raise GkrError(rc, "challenge")
+        return out
+
+    def raw_challenge(self, n: int) -> bytes:
+        buf = (C.c_uint8 * n)()
+        rc = self.lib.gkr_transcript_raw_challenge(self.h, buf, n)
+        if rc:
+            raise GkrError(rc, "raw_challenge")
+        return bytes(buf)
+
+    def proof(self) -> bytes:
+        n = int(self.lib.gkr_transcript_proof_len(self.h))
+        buf = (C.c_uint8 * max(n, 1))()
+        self.lib.gkr_transcript_proof(self.h, buf)
+        return bytes(buf[:n])
+
+    def free(self):
+        if self.h:
+            self.lib.gkr_transcript_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def sumcheck_prove(transcript: Transcript, so: SumcheckObject, num_rounds: int):
+    """GenericSumcheckProtocol::prove (src/cleanup/protocols/sumcheck.rs:101-123).
+    Returns (claim, point[num_rounds] (reversed like the reference), final_evals)."""
+    claim = np.zeros(4, np.uint64)
+    point = np.zeros((max(num_rounds, 1), 4), np.uint64)
+    fe = np.zeros((so.num_polys, 4), np.uint64)
+    rc = so.ctx.lib.gkr_sumcheck_prove(transcript.h, so.h, num_rounds, _ptr(claim), _ptr(point), _ptr(fe))
+    so.ctx.check(rc)
+    return claim, point[:num_rounds], fe
+
+
+class Exchange:
+    """gkr_exchange: shared-memory all-gather between the ranks (one process per GPU) of one box."""
+
+    def __init__(self, name: str, rank: int, world: int, create: bool):
+        self.lib = load_library()
+        h = _vp()
+        rc = self.lib.gkr_exchange_open(name.encode(), rank, world, 1 if create else 0, C.byref(h))
+        if rc:
+            raise GkrError(rc, f"gkr_exchange_open({name})")
+        self.h, self.rank, self.world = h, rank, world
+
+    def allgather(self, mine) -> np.ndarray:
+        a = _limbs(mine).reshape(-1, 4)
+        out = np.zeros((self.world, a.shape[0], 4), np.uint64)
+        rc = self.lib.gkr_exchange_allgather(self.h, _ptr(a), a.shape[0], _ptr(out))
+        if rc:
+            raise GkrError(rc, "gkr_exchange_allgather")
+        return out
+
+    def close(self):
+        if self.h:
+            self.lib.gkr_exchange_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sumcheck_prove_sharded(transcript: Transcript, so: SumcheckObject, exchange, local_rounds: int, so_kind: int, gate: int,
+                           global_claim, gate_param: int = 0, consts=None):
+    """GenericSumcheckProtocol::prove over a hypercube sharded by its top index bits (exchange=None: 1 GPU).
+    Returns (claim, point, final_evals) -- identical on every rank."""
+    world = exchange.world if exchange is not None else 1
+    g_ = world.bit_length() - 1
+    c = _limbs(consts).reshape(-1, 4) if consts is not None else np.zeros((0, 4), np.uint64)
+    claim = np.zeros(4, np.uint64)
+    point = np.zeros((max(local_rounds + g_, 1), 4), np.uint64)
+    fe = np.zeros((so.num_polys, 4), np.uint64)
+    gc = _limbs(global_claim).reshape(4)
+    rc = so.ctx.lib.gkr_sumcheck_prove_sharded(transcript.h, so.h, exchange.h if exchange is not None else None, local_rounds,
+                                               so_kind, gate, gate_param, _ptr(c), c.shape[0], _ptr(gc), _ptr(claim), _ptr(point), _ptr(fe))
+    so.ctx.check(rc)
+    return claim, point[: local_rounds + g_], fe

@@ -1,0 +1,151 @@
+// extern "C" surface declared in include/gkr_msm_b200.h: thin argument checking + dispatch.
+#include "common.cuh"
+#include "so.hpp"
+#include "transcript.hpp"
+
+int gkr_dense_gate_sum_impl(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const gkr::FrH* consts, uint32_t n_consts,
+                            gkr_table* const* tables, uint32_t n_polys, gkr::FrH* out);
+
+static std::vector<gkr::FrH> load_frs(const uint64_t* p, uint32_t n) {
+    std::vector<gkr::FrH> v(n);
+    for (uint32_t i = 0; i < n; i++) v[i] = frh_from_limbs(p + 4 * i);
+    return v;
+}
+
+extern "C" int gkr_so_create_dense(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const uint64_t* gate_consts,
+                                   uint32_t n_consts, gkr_table* const* tables, uint32_t n_polys, uint32_t num_vars,
+                                   const uint64_t claim[4], gkr_so** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!out || !tables || !claim || (!gate_consts && n_consts)) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (n_polys == 0 || n_polys > GKR_MAX_POLYS) return ctx->fail(GKR_ERR_ARG, "bad number of tables");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    std::vector<gkr::FrH> c = load_frs(gate_consts, n_consts);
+    return gkr_make_dense_so(ctx, so_kind, gate, gate_param, c.data(), n_consts, tables, n_polys, num_vars, frh_from_limbs(claim), out);
+}
+
+extern "C" int gkr_dense_gate_sum(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const uint64_t* gate_consts,
+                                  uint32_t n_consts, gkr_table* const* tables, uint32_t n_polys, uint64_t out[4]) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!out || !tables || (!gate_consts && n_consts)) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (n_polys == 0 || n_polys > GKR_MAX_POLYS) return ctx->fail(GKR_ERR_ARG, "bad number of tables");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    std::vector<gkr::FrH> c = load_frs(gate_consts, n_consts);
+    gkr::FrH r;
+    int rc = gkr_dense_gate_sum_impl(ctx, so_kind, gate, gate_param, c.data(), n_consts, tables, n_polys, &r);
+    if (rc == GKR_OK) frh_to_limbs(r, out);
+    return rc;
+}
+
+extern "C" int gkr_so_unipoly(gkr_so* so, uint64_t* evals_out, uint32_t* n_evals) {
+    if (!so || !evals_out) return GKR_ERR_ARG;
+    gkr::FrH ev[GKR_MAX_DEG + 1];
+    uint32_t n = 0;
+    int rc = so->unipoly(ev, &n);
+    if (rc) return rc;
+    for (uint32_t i = 0; i < n; i++) frh_to_limbs(ev[i], evals_out + 4 * i);
+    if (n_evals) *n_evals = n;
+    return GKR_OK;
+}
+
+extern "C" int gkr_so_bind(gkr_so* so, const uint64_t t[4]) {
+    if (!so || !t) return GKR_ERR_ARG;
+    return so->bind(frh_from_limbs(t));
+}
+
+extern "C" int gkr_so_final_evals(gkr_so* so, uint64_t* out) {
+    if (!so || !out) return GKR_ERR_ARG;
+    std::vector<gkr::FrH> v(so->num_polys());
+    int rc = so->final_evals(v.data());
+    if (rc) return rc;
+    for (size_t i = 0; i < v.size(); i++) frh_to_limbs(v[i], out + 4 * i);
+    return GKR_OK;
+}
+
+extern "C" int gkr_so_claim(const gkr_so* so, uint64_t out[4]) {
+    if (!so || !out) return GKR_ERR_ARG;
+    frh_to_limbs(so->claim(), out);
+    return GKR_OK;
+}
+
+extern "C" uint32_t gkr_so_degree(const gkr_so* so) { return so ? so->degree() : 0; }
+extern "C" uint32_t gkr_so_num_polys(const gkr_so* so) { return so ? so->num_polys() : 0; }
+extern "C" uint32_t gkr_so_round(const gkr_so* so) { return so ? so->round() : 0; }
+extern "C" void gkr_so_destroy(gkr_so* so) { delete so; }
+
+// ---- transcript ----------------------------------------------------------------------------------------
+extern "C" int gkr_transcript_new(const uint8_t* label, size_t label_len, gkr_transcript** out) {
+    if (!out || (!label && label_len)) return GKR_ERR_ARG;
+    *out = new gkr_transcript(label, label_len);
+    return GKR_OK;
+}
+extern "C" void gkr_transcript_free(gkr_transcript* t) { delete t; }
+
+extern "C" int gkr_transcript_write_scalars(gkr_transcript* t, const uint64_t* limbs, uint32_t n) {
+    if (!t || (!limbs && n)) return GKR_ERR_ARG;
+    std::vector<gkr::FrH> v = load_frs(limbs, n);
+    for (auto& x : v)
+        if (!frh_canonical(x)) return GKR_ERR_ARG;
+    t->t.write_scalars(v.data(), v.size());
+    return GKR_OK;
+}
+
+extern "C" int gkr_transcript_write_raw(gkr_transcript* t, const uint8_t* msg, size_t len) {
+    if (!t || (!msg && len)) return GKR_ERR_ARG;
+    t->t.write_raw_msg(msg, len);
+    return GKR_OK;
+}
+
+extern "C" int gkr_transcript_challenge(gkr_transcript* t, uint32_t bitsize, uint64_t out[4]) {
+    if (!t || !out || bitsize == 0 || bitsize > 512) return GKR_ERR_ARG;
+    frh_to_limbs(t->t.challenge(bitsize), out);
+    return GKR_OK;
+}
+
+extern "C" int gkr_transcript_raw_challenge(gkr_transcript* t, uint8_t* out, size_t len) {
+    if (!t || (!out && len)) return GKR_ERR_ARG;
+    t->t.raw_challenge(out, len);
+    return GKR_OK;
+}
+
+extern "C" size_t gkr_transcript_proof_len(const gkr_transcript* t) { return t ? t->t.proof.size() : 0; }
+
+extern "C" int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out) {
+    if (!t || !out) return GKR_ERR_ARG;
+    std::memcpy(out, t->t.proof.data(), t->t.proof.size());
+    return GKR_OK;
+}
+
+// GenericSumcheckProtocol::prove  (src/cleanup/protocols/sumcheck.rs:101-123)
+extern "C" int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_rounds, uint64_t out_claim[4],
+                                  uint64_t* out_point, uint64_t* out_final_evals) {
+    if (!t || !so) return GKR_ERR_ARG;
+    gkr::FrH claim = so->claim();
+    std::vector<gkr::FrH> r;
+    r.reserve(num_rounds);
+    for (uint32_t k = 0; k < num_rounds; k++) {
+        gkr::FrH ev[GKR_MAX_DEG + 1];
+        uint32_t n = 0;
+        int rc = so->unipoly(ev, &n);
+        if (rc) return rc;
+        std::vector<gkr::FrH> poly = gkr::frh::interpolate_coeffs(ev, (int)n);  // unipoly().as_vec()
+        std::vector<gkr::FrH> msg;                                               // compress_coefficients: drop the linear term
+        msg.push_back(poly[0]);
+        for (size_t i = 2; i < poly.size(); i++) msg.push_back(poly[i]);
+        t->t.write_scalars(msg.data(), msg.size());
+        gkr::FrH x = t->t.challenge(128);
+        r.push_back(x);
+        rc = so->bind(x);
+        if (rc) return rc;
+        claim = gkr::frh::evaluate_univar(poly, x);
+    }
+    if (out_claim) frh_to_limbs(claim, out_claim);
+    if (out_point)
+        for (uint32_t k = 0; k < num_rounds; k++) frh_to_limbs(r[num_rounds - 1 - k], out_point + 4 * k);  // r.reverse()
+    if (out_final_evals) {
+        std::vector<gkr::FrH> fe(so->num_polys());
+        int rc = so->final_evals(fe.data());
+        if (rc) return rc;
+        for (size_t i = 0; i < fe.size(); i++) frh_to_limbs(fe[i], out_final_evals + 4 * i);
+    }
+    return GKR_OK;
+}

@@ -1,0 +1,183 @@
+// Shared host/device plumbing for the C-ABI implementation: context, tables, error handling and the
+// block / grid reduction of per-thread field accumulators (warp shuffles -> shared memory -> last block).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/gkr_msm_b200.h"
+#include "field.cuh"
+#include "host_field.hpp"
+
+#define GKR_MAX_POLYS 16        // max tables per sumcheck object (triangle L1 has 12 inputs + eq)
+#define GKR_MAX_DEG 4           // max number of accumulated evaluation points per round
+#define GKR_REDUCE_THREADS 128  // block size of the sumcheck round kernels
+#define GKR_MAX_BLOCKS 4096     // upper bound on the grid of a round kernel (partials scratch)
+
+struct gkr_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    Fr* partials = nullptr;         // [GKR_MAX_BLOCKS * GKR_MAX_DEG] device scratch
+    unsigned int* ticket = nullptr; // device counter for the last-block pattern
+    Fr* result_host = nullptr;      // pinned + mapped: round sums land here without a memcpy launch
+    Fr* result_dev = nullptr;       // device alias of result_host
+    // optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream
+    bool timing = false;
+    struct TimedLaunch {
+        int kernel_id;
+        uint64_t n_items;
+        cudaEvent_t start, stop;
+    };
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;  // recycled events so a timed launch costs two cudaEventRecord only
+    cudaEvent_t take_event() {
+        if (event_pool.empty()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            return e;
+        }
+        cudaEvent_t e = event_pool.back();
+        event_pool.pop_back();
+        return e;
+    }
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+};
+
+struct gkr_table {
+    gkr_ctx* ctx = nullptr;
+    Fr* d = nullptr;
+    uint64_t n = 0;
+    bool owned = true;
+};
+
+// kernel ids reported by gkr_ctx_timing_read
+enum GkrKernelId { GKR_K_DENSE_EVAL = 0, GKR_K_DENSE_FOLD_EVAL = 1, GKR_K_DENSE_SUM = 2, GKR_K_DENSE_FOLD = 3 };
+
+struct GkrLaunchTimer {
+    gkr_ctx* ctx;
+    bool on;
+    gkr_ctx::TimedLaunch t;
+    GkrLaunchTimer(gkr_ctx* c, int kernel_id, uint64_t n_items) : ctx(c), on(c->timing) {
+        if (!on) return;
+        t.kernel_id = kernel_id;
+        t.n_items = n_items;
+        t.start = ctx->take_event();
+        t.stop = ctx->take_event();
+        cudaEventRecord(t.start, ctx->stream);
+    }
+    ~GkrLaunchTimer() {
+        if (!on) return;
+        cudaEventRecord(t.stop, ctx->stream);
+        ctx->timed.push_back(t);
+    }
+};
+
+#define GKR_CUDA_OK(ctx, call)                                                                          \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            return (ctx)->fail(GKR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));      \
+        }                                                                                               \
+    } while (0)
+
+static inline gkr::FrH frh_from_limbs(const uint64_t* p) {
+    gkr::FrH r;
+    for (int i = 0; i < 4; i++) r.v[i] = p[i];
+    return r;
+}
+static inline void frh_to_limbs(const gkr::FrH& a, uint64_t* p) {
+    for (int i = 0; i < 4; i++) p[i] = a.v[i];
+}
+static inline bool frh_canonical(const gkr::FrH& a) { return !gkr::frh::geq_mod(a.v); }
+
+static inline Fr fr_from_host(const gkr::FrH& a) {
+    Fr r;
+    for (int i = 0; i < 4; i++) {
+        r.l[2 * i] = (uint32_t)a.v[i];
+        r.l[2 * i + 1] = (uint32_t)(a.v[i] >> 32);
+    }
+    return r;
+}
+static inline gkr::FrH fr_to_host(const Fr& a) {
+    gkr::FrH r;
+    for (int i = 0; i < 4; i++) r.v[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
+    return r;
+}
+
+#ifdef __CUDACC__
+// Sum `acc[0..N)` over all threads of the grid.  Field addition is associative and commutative and every
+// partial is canonical, so the result is bit-identical to the reference's sequential / rayon sum whatever
+// the order.  Block: shuffle tree inside each warp, one shared-memory hop, warp 0 finishes.  Grid: every
+// block publishes its partial, the last block to take a ticket folds them (threadfence reduction) and
+// writes the N results to `result` (pinned host memory mapped into the device address space).
+template <int N>
+__device__ __forceinline__ void block_reduce_fr(Fr* acc, Fr* smem /* [N * warps] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+    for (int s = 0; s < N; s++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[s] = fr_add(acc[s], fr_shfl_down(acc[s], off));
+        if (lane == 0) smem[s * nwarps + warp] = acc[s];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            Fr v = lane < nwarps ? smem[s * nwarps + lane] : fr_zero();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v = fr_add(v, fr_shfl_down(v, off));
+            acc[s] = v;
+        }
+    }
+    __syncthreads();
+}
+
+template <int N>
+__device__ __forceinline__ void grid_reduce_fr(Fr* acc, Fr* smem, Fr* partials, unsigned int* ticket, Fr* result) {
+    block_reduce_fr<N>(acc, smem);
+    if (gridDim.x == 1) {
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < N; s++) result[s] = acc[s];
+        }
+        return;
+    }
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < N; s++) partials[(size_t)blockIdx.x * N + s] = acc[s];
+        __threadfence();
+        unsigned int tk = atomicAdd(ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int s = 0; s < N; s++) acc[s] = fr_zero();
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            const Fr* p = &partials[(size_t)b * N + s];
+            Fr v;
+            asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v.l[0]), "=r"(v.l[1]), "=r"(v.l[2]), "=r"(v.l[3]), "=r"(v.l[4]), "=r"(v.l[5]), "=r"(v.l[6]), "=r"(v.l[7])
+                         : "l"(p));
+            acc[s] = fr_add(acc[s], v);
+        }
+    }
+    block_reduce_fr<N>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < N; s++) result[s] = acc[s];
+        *ticket = 0;
+    }
+}
+#endif

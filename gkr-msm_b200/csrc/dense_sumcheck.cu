@@ -1,0 +1,345 @@
+// DenseSumcheckObjectSO on the device  (reference: src/cleanup/protocols/sumcheck.rs:241-347).
+//
+// One kernel per sumcheck round.  `bind(t)` of round k and `unipoly()` of round k+1 are FUSED: the kernel
+// reads every table once (4 consecutive elements per thread and table), folds them with the challenge
+// (bind_dense_poly, sumcheck.rs:160-163: p'[i] = p[2i] + t (p[2i+1] - p[2i])), writes the half-size table
+// and, from the two fresh elements still in registers, accumulates the next round's evaluations at
+// 1..deg exactly like sumcheck.rs:295-313 (args = p[2i+1]; difs = p[2i+1]-p[2i]; args += difs per node).
+// Algorithmic traffic: 32 B read + 16 B written per table element per round (the reference's separate
+// unipoly + bind passes move 64 + 16).  The per-round result (deg field elements) is written by the last
+// block straight into pinned host memory; the challenge travels as a kernel argument, so a round costs
+// one launch and one stream synchronisation and nothing table-sized ever crosses PCIe.
+#include <algorithm>
+#include "common.cuh"
+#include "gates.cuh"
+#include "so.hpp"
+
+struct DenseRoundArgs {
+    const Fr* in[GKR_MAX_POLYS];
+    Fr* out[GKR_MAX_POLYS];
+    uint64_t n_items;  // MODE 0/1: number of pairs evaluated; MODE 2: number of elements
+    Fr t;
+    GateConsts consts;
+    Fr* partials;
+    unsigned int* ticket;
+    Fr* result;
+};
+
+// MODE 0: evaluate pairs (2i, 2i+1) of `in`                      (first round: nothing to fold yet)
+// MODE 1: fold quads (4i..4i+3) of `in` into `out` (2i, 2i+1), then evaluate that fresh pair
+// MODE 2: plain sum of f over all elements (claim_hint computation), one accumulator
+template <class SO, int MODE>
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const __grid_constant__ DenseRoundArgs A) {
+    constexpr int P = SO::P;
+    constexpr int NACC = (MODE == 2) ? 1 : SO::DEG;
+    __shared__ Fr smem[NACC * (GKR_REDUCE_THREADS / 32)];
+    Fr acc[NACC];
+#pragma unroll
+    for (int s = 0; s < NACC; s++) acc[s] = fr_zero();
+
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_items; i += stride) {
+        Fr a[P];
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < P; j++) a[j] = A.in[j][i];
+            acc[0] = fr_add(acc[0], SO::eval(a, A.consts));
+        } else {
+            Fr d[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                Fr lo, hi;
+                if (MODE == 1) {
+                    const Fr* src = A.in[j] + 4 * i;
+                    Fr e0 = src[0], e1 = src[1], e2 = src[2], e3 = src[3];
+                    lo = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+                    hi = fr_add(e2, fr_mul(A.t, fr_sub(e3, e2)));
+                    Fr* dst = A.out[j] + 2 * i;
+                    dst[0] = lo;
+                    dst[1] = hi;
+                } else {
+                    const Fr* src = A.in[j] + 2 * i;
+                    lo = src[0];
+                    hi = src[1];
+                }
+                a[j] = hi;
+                d[j] = fr_sub(hi, lo);
+            }
+            acc[0] = fr_add(acc[0], SO::eval(a, A.consts));
+#pragma unroll
+            for (int s = 1; s < SO::DEG; s++) {
+#pragma unroll
+                for (int j = 0; j < P; j++) a[j] = fr_add(a[j], d[j]);
+                acc[s] = fr_add(acc[s], SO::eval(a, A.consts));
+            }
+        }
+    }
+    grid_reduce_fr<NACC>(acc, smem, A.partials, A.ticket, A.result);
+}
+
+// out[j][i] = in[j][2i] + t (in[j][2i+1] - in[j][2i])   -- used for the last round (one pair -> one value)
+__global__ void dense_fold_kernel(const __grid_constant__ DenseRoundArgs A, int n_polys) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_items; i += stride) {
+        for (int j = 0; j < n_polys; j++) {
+            Fr e0 = A.in[j][2 * i], e1 = A.in[j][2 * i + 1];
+            A.out[j][i] = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+        }
+    }
+}
+
+// ---- gate dispatch --------------------------------------------------------------------------------
+template <class F>
+static int dispatch_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t param, F&& f) {
+    if (so_kind == GKR_SO_PLAIN) {
+        if (gate == GKR_GATE_PROD3) return f(SoProd3{});
+        if (gate == GKR_GATE_FOLDED_PROD) {
+            switch (param) {
+                case 1: return f(SoFoldedProd<1>{});
+                case 2: return f(SoFoldedProd<2>{});
+                case 3: return f(SoFoldedProd<3>{});
+                case 4: return f(SoFoldedProd<4>{});
+                default: return ctx->fail(GKR_ERR_UNSUPPORTED, "FOLDED_PROD: nargs must be 1..4");
+            }
+        }
+        return ctx->fail(GKR_ERR_UNSUPPORTED, "GKR_SO_PLAIN supports PROD3 and FOLDED_PROD");
+    }
+    if (so_kind == GKR_SO_EQ_GAMMA) {
+        switch (gate) {
+            case GKR_GATE_AFF_L1: return f(SoEqGamma<GATE_AFF_L1>{});
+            case GKR_GATE_AFF_L2: return f(SoEqGamma<GATE_AFF_L2>{});
+            case GKR_GATE_AFF_L3: return f(SoEqGamma<GATE_AFF_L3>{});
+            case GKR_GATE_PRJ_L1: return f(SoEqGamma<GATE_PRJ_L1>{});
+            case GKR_GATE_PRJ_L2: return f(SoEqGamma<GATE_PRJ_L2>{});
+            case GKR_GATE_PRJ_L3: return f(SoEqGamma<GATE_PRJ_L3>{});
+            case GKR_GATE_AFF_L1_BITCHECK2: return f(SoEqGamma<GATE_AFF_L1_BITCHECK2>{});
+            case GKR_GATE_LOGUP_LAYER: return f(SoEqGamma<GATE_LOGUP_LAYER>{});
+            case GKR_GATE_ADD_INVERSES: return f(SoEqGamma<GATE_ADD_INVERSES>{});
+            default: return ctx->fail(GKR_ERR_UNSUPPORTED, "GKR_SO_EQ_GAMMA: unsupported gate");
+        }
+    }
+    return ctx->fail(GKR_ERR_ARG, "unknown so_kind");
+}
+
+template <class SO, int MODE>
+static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int b = 0;
+        GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_kernel<SO, MODE>, GKR_REDUCE_THREADS, 0));
+        blocks_per_sm = std::max(b, 1);
+    }
+    uint64_t want = (args.n_items + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
+    uint64_t cap = std::min<uint64_t>((uint64_t)ctx->num_sms * blocks_per_sm, GKR_MAX_BLOCKS);
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+    {
+        GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : (MODE == 1 ? GKR_K_DENSE_FOLD_EVAL : GKR_K_DENSE_SUM), args.n_items);
+        dense_round_kernel<SO, MODE><<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(args);
+    }
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    return GKR_OK;
+}
+
+struct DenseSoInfo {
+    int P, DEG;
+};
+
+static int dense_so_info(gkr_ctx* ctx, int so_kind, int gate, uint32_t param, DenseSoInfo* info) {
+    return dispatch_dense_so(ctx, so_kind, gate, param, [&](auto so) {
+        using SO = decltype(so);
+        info->P = SO::P;
+        info->DEG = SO::DEG;
+        return (int)GKR_OK;
+    });
+}
+
+int gkr_result_slot_acquire(gkr_ctx* ctx);
+void gkr_result_slot_release(gkr_ctx* ctx, int slot);
+
+class DenseSO : public gkr_so {
+   public:
+    int so_kind, gate;
+    uint32_t gate_param;
+    GateConsts consts;
+    int P = 0, DEG = 0;
+    uint32_t num_vars = 0, round_idx = 0;
+    gkr::FrH claim_;
+    const Fr* cur[GKR_MAX_POLYS];  // current tables (round 0: the caller's tables, untouched)
+    Fr* slab = nullptr;            // P * (n/2 + n/4) ping-pong storage
+    Fr* buf[2][GKR_MAX_POLYS];
+    int next_buf = 0;
+    bool sums_pending = false;  // a launched kernel will deliver the sums of the current round
+    bool cached = false;
+    gkr::FrH evals[GKR_MAX_DEG + 1];
+    int slot = -1;
+
+    ~DenseSO() override {
+        if (slab) cudaFree(slab);
+        if (slot >= 0) gkr_result_slot_release(ctx, slot);
+    }
+
+    Fr* result_dev() const { return ctx->result_dev + (size_t)slot * GKR_MAX_DEG; }
+    Fr* result_host() const { return ctx->result_host + (size_t)slot * GKR_MAX_DEG; }
+
+    void fill_common(DenseRoundArgs& a) {
+        a.consts = consts;
+        a.partials = ctx->partials;
+        a.ticket = ctx->ticket;
+        a.result = result_dev();
+    }
+
+    int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
+        if (round_idx >= num_vars) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly: the protocol has already ended");
+        if (!cached) {
+            if (!sums_pending) {
+                DenseRoundArgs a;
+                for (int j = 0; j < P; j++) { a.in[j] = cur[j]; a.out[j] = nullptr; }
+                a.n_items = (uint64_t)1 << (num_vars - round_idx - 1);
+                fill_common(a);
+                int rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
+                    return launch_dense_round<decltype(so), 0>(ctx, a);
+                });
+                if (rc) return rc;
+            }
+            GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            sums_pending = false;
+            const Fr* r = result_host();
+            for (int s = 0; s < DEG; s++) evals[s + 1] = fr_to_host(r[s]);
+            evals[0] = gkr::frh::sub(claim_, evals[1]);  // sumcheck.rs:325
+            cached = true;
+        }
+        for (int s = 0; s <= DEG; s++) out[s] = evals[s];
+        if (n_evals) *n_evals = DEG + 1;
+        return GKR_OK;
+    }
+
+    int bind(const gkr::FrH& t) override {
+        if (round_idx >= num_vars) return ctx->fail(GKR_ERR_PROTOCOL, "bind: the protocol has already ended");
+        if (!cached) return ctx->fail(GKR_ERR_PROTOCOL, "bind: should evaluate unipoly before binding");
+        if (!frh_canonical(t)) return ctx->fail(GKR_ERR_ARG, "bind: challenge is not a canonical field element");
+        const uint64_t cur_len = (uint64_t)1 << (num_vars - round_idx);
+        const uint64_t new_len = cur_len >> 1;
+        if (!slab) {
+            uint64_t per = new_len + (new_len >> 1);
+            GKR_CUDA_OK(ctx, cudaMalloc(&slab, sizeof(Fr) * per * P));
+            for (int j = 0; j < P; j++) {
+                buf[0][j] = slab + (size_t)j * per;
+                buf[1][j] = slab + (size_t)j * per + new_len;
+            }
+        }
+        DenseRoundArgs a;
+        for (int j = 0; j < P; j++) { a.in[j] = cur[j]; a.out[j] = buf[next_buf][j]; }
+        a.t = fr_from_host(t);
+        fill_common(a);
+        if (new_len >= 2) {
+            a.n_items = new_len >> 1;
+            int rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
+                return launch_dense_round<decltype(so), 1>(ctx, a);
+            });
+            if (rc) return rc;
+            sums_pending = true;
+        } else {
+            a.n_items = new_len;
+            dense_fold_kernel<<<1, 32, 0, ctx->stream>>>(a, P);
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+        }
+        for (int j = 0; j < P; j++) cur[j] = buf[next_buf][j];
+        next_buf ^= 1;
+        claim_ = gkr::frh::interpolate_eval(evals, DEG + 1, t);  // u.evaluate(&t), sumcheck.rs:273
+        cached = false;
+        round_idx++;
+        return GKR_OK;
+    }
+
+    int final_evals(gkr::FrH* out) override {
+        if (round_idx != num_vars) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: can only be called after the last round");
+        for (int j = 0; j < P; j++) {
+            Fr v;
+            GKR_CUDA_OK(ctx, cudaMemcpyAsync(&v, cur[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+            GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            out[j] = fr_to_host(v);
+        }
+        return GKR_OK;
+    }
+
+    gkr::FrH claim() const override { return claim_; }
+    uint32_t degree() const override { return DEG; }
+    uint32_t num_polys() const override { return P; }
+    uint32_t round() const override { return round_idx; }
+};
+
+static int fill_consts(gkr_ctx* ctx, const gkr::FrH* consts, uint32_t n_consts, GateConsts* out) {
+    if (n_consts > GKR_MAX_GATE_CONSTS) return ctx->fail(GKR_ERR_ARG, "too many gate constants");
+    for (uint32_t i = 0; i < GKR_MAX_GATE_CONSTS; i++) {
+        if (i < n_consts) {
+            if (!frh_canonical(consts[i])) return ctx->fail(GKR_ERR_ARG, "gate constant is not canonical");
+            out->g[i] = fr_from_host(consts[i]);
+        } else {
+            for (int k = 0; k < 8; k++) out->g[i].l[k] = 0;
+        }
+    }
+    return GKR_OK;
+}
+
+int gkr_make_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const gkr::FrH* consts, uint32_t n_consts,
+                      gkr_table* const* tables, uint32_t n_polys, uint32_t num_vars, const gkr::FrH& claim, gkr_so** out) {
+    DenseSoInfo info;
+    int rc = dense_so_info(ctx, so_kind, gate, gate_param, &info);
+    if (rc) return rc;
+    if ((int)n_polys != info.P) return ctx->fail(GKR_ERR_ARG, "number of tables != f.n_ins()");  // sumcheck.rs:255
+    if (num_vars >= 40) return ctx->fail(GKR_ERR_ARG, "num_vars too large");
+    for (uint32_t j = 0; j < n_polys; j++) {
+        if (!tables[j] || tables[j]->n != ((uint64_t)1 << num_vars))
+            return ctx->fail(GKR_ERR_ARG, "table length != 1 << num_vars");  // sumcheck.rs:257
+    }
+    if (!frh_canonical(claim)) return ctx->fail(GKR_ERR_ARG, "claim is not canonical");
+    DenseSO* so = new DenseSO();
+    so->ctx = ctx;
+    so->so_kind = so_kind;
+    so->gate = gate;
+    so->gate_param = gate_param;
+    rc = fill_consts(ctx, consts, n_consts, &so->consts);
+    if (rc) { delete so; return rc; }
+    so->P = info.P;
+    so->DEG = info.DEG;
+    so->num_vars = num_vars;
+    so->claim_ = claim;
+    for (uint32_t j = 0; j < n_polys; j++) so->cur[j] = tables[j]->d;
+    so->slot = gkr_result_slot_acquire(ctx);
+    if (so->slot < 0) { delete so; return ctx->fail(GKR_ERR_UNSUPPORTED, "too many live sumcheck objects"); }
+    *out = so;
+    return GKR_OK;
+}
+
+// sum_i f(tables[.][i])
+int gkr_dense_gate_sum_impl(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const gkr::FrH* consts, uint32_t n_consts,
+                            gkr_table* const* tables, uint32_t n_polys, gkr::FrH* out) {
+    DenseSoInfo info;
+    int rc = dense_so_info(ctx, so_kind, gate, gate_param, &info);
+    if (rc) return rc;
+    if ((int)n_polys != info.P) return ctx->fail(GKR_ERR_ARG, "number of tables != f.n_ins()");
+    DenseRoundArgs a;
+    rc = fill_consts(ctx, consts, n_consts, &a.consts);
+    if (rc) return rc;
+    for (uint32_t j = 0; j < n_polys; j++) {
+        if (!tables[j] || tables[j]->n != tables[0]->n) return ctx->fail(GKR_ERR_ARG, "tables must have equal length");
+        a.in[j] = tables[j]->d;
+        a.out[j] = nullptr;
+    }
+    a.n_items = tables[0]->n;
+    int slot = gkr_result_slot_acquire(ctx);
+    if (slot < 0) return ctx->fail(GKR_ERR_UNSUPPORTED, "no free result slot");
+    a.partials = ctx->partials;
+    a.ticket = ctx->ticket;
+    a.result = ctx->result_dev + (size_t)slot * GKR_MAX_DEG;
+    rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) { return launch_dense_round<decltype(so), 2>(ctx, a); });
+    if (rc == GKR_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+        else *out = fr_to_host(ctx->result_host[(size_t)slot * GKR_MAX_DEG]);
+    }
+    gkr_result_slot_release(ctx, slot);
+    return rc;
+}

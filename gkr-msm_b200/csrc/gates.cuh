@@ -1,0 +1,194 @@
+// The closed set of polynomial gates the reference instantiates on the hot path, as device functors.
+// `AlgFn` is an open Rust generic (src/cleanup/utils/algfn.rs:20-34); a C ABI needs a closed enum, so the
+// ids below are the ones exported in include/gkr_msm_b200.h (enum gkr_gate_id).
+//
+//   twisted-Edwards addition gates      src/cleanup/utils/twisted_edwards_ops.rs:10-81
+//   BitCheckFn, Stacked, Repeated       src/cleanup/utils/algfn.rs:187-291
+//   LogupLayerFn                        src/cleanup/protocols/pushforward/logup_mainphase.rs:42-61
+//   AddInversesFn, Prod3Fn              src/cleanup/protocols/pushforward/pushforward.rs:38-50, 266-281
+//   FoldedProdAlgFn                     src/cleanup/protocols/multiopen_reduction.rs:13-41
+//   GammaWrapper, EqWrapper             src/cleanup/protocols/sumcheck.rs:706-741, 802-829
+#pragma once
+#include "field.cuh"
+
+enum GateId : int {
+    GATE_AFF_L1 = 0,
+    GATE_AFF_L2 = 1,
+    GATE_AFF_L3 = 2,
+    GATE_PRJ_L1 = 3,
+    GATE_PRJ_L2 = 4,
+    GATE_PRJ_L3 = 5,
+    GATE_TRI_L1 = 6,
+    GATE_BITCHECK = 7,
+    GATE_LOGUP_LAYER = 8,
+    GATE_ADD_INVERSES = 9,
+    GATE_PROD3 = 10,
+    GATE_FOLDED_PROD = 11,
+    GATE_ID = 12,
+    GATE_AFF_L1_BITCHECK2 = 13,
+};
+
+#define GKR_MAX_GATE_CONSTS 16
+// gamma powers: g[i] multiplies output i (g[0] is never read: output 0 has coefficient one).
+struct GateConsts {
+    Fr g[GKR_MAX_GATE_CONSTS];
+};
+
+template <int G>
+struct MoGate;
+
+template <>
+struct MoGate<GATE_AFF_L1> {
+    static constexpr int N_INS = 4, N_OUTS = 3;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        o[0] = fr_mul(a[0], a[3]);
+        o[1] = fr_mul(a[2], a[1]);
+        o[2] = fr_add_5x(fr_mul(a[1], a[3]), fr_mul(a[0], a[2]));
+    }
+};
+
+template <>
+struct MoGate<GATE_AFF_L2> {
+    static constexpr int N_INS = 3, N_OUTS = 3;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        o[0] = fr_add(a[0], a[1]);
+        o[1] = a[2];
+        o[2] = fr_mul(a[0], a[1]);
+    }
+};
+
+template <>
+struct MoGate<GATE_AFF_L3> {
+    static constexpr int N_INS = 3, N_OUTS = 3;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        Fr dxy = fr_mul(a[2], fr_te_d());
+        Fr m = fr_sub(fr_one(), dxy);
+        Fr p = fr_add(fr_one(), dxy);
+        o[0] = fr_mul(m, a[0]);
+        o[1] = fr_mul(p, a[1]);
+        o[2] = fr_mul(m, p);
+    }
+};
+
+template <>
+struct MoGate<GATE_PRJ_L1> {
+    static constexpr int N_INS = 6, N_OUTS = 4;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        o[0] = fr_mul(a[0], a[4]);
+        o[1] = fr_mul(a[3], a[1]);
+        o[2] = fr_add_5x(fr_mul(a[1], a[4]), fr_mul(a[0], a[3]));
+        o[3] = fr_mul(a[2], a[5]);
+    }
+};
+
+template <>
+struct MoGate<GATE_PRJ_L2> {
+    static constexpr int N_INS = 4, N_OUTS = 4;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        o[0] = fr_mul(fr_add(a[0], a[1]), a[3]);
+        o[1] = fr_mul(a[2], a[3]);
+        o[2] = fr_sqr(a[3]);
+        o[3] = fr_mul(a[0], a[1]);
+    }
+};
+
+template <>
+struct MoGate<GATE_PRJ_L3> {
+    static constexpr int N_INS = 4, N_OUTS = 3;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        Fr dxy = fr_mul(a[3], fr_te_d());
+        Fr m = fr_sub(a[2], dxy);
+        Fr p = fr_add(a[2], dxy);
+        o[0] = fr_mul(m, a[0]);
+        o[1] = fr_mul(p, a[1]);
+        o[2] = fr_mul(m, p);
+    }
+};
+
+// three projective L1 on (a,c), (b,d), (c,d); inputs a,b,c,d = 4 points x (x,y,z)
+template <>
+struct MoGate<GATE_TRI_L1> {
+    static constexpr int N_INS = 12, N_OUTS = 12;
+    __device__ __forceinline__ static void eval(const Fr* p, Fr* o) {
+        Fr t[6];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { t[i] = p[i]; t[3 + i] = p[6 + i]; }
+        MoGate<GATE_PRJ_L1>::eval(t, o);
+#pragma unroll
+        for (int i = 0; i < 3; i++) { t[i] = p[3 + i]; t[3 + i] = p[9 + i]; }
+        MoGate<GATE_PRJ_L1>::eval(t, o + 4);
+        MoGate<GATE_PRJ_L1>::eval(p + 6, o + 8);
+    }
+};
+
+template <>
+struct MoGate<GATE_BITCHECK> {
+    static constexpr int N_INS = 1, N_OUTS = 1;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) { o[0] = fr_sub(fr_sqr(a[0]), a[0]); }
+};
+
+// Stacked(affine_l1, Repeated(BitCheck, 2))   (src/cleanup/protocols/gkrs/bintree_add.rs:259-273)
+template <>
+struct MoGate<GATE_AFF_L1_BITCHECK2> {
+    static constexpr int N_INS = 6, N_OUTS = 5;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        MoGate<GATE_AFF_L1>::eval(a, o);
+        o[3] = fr_sub(fr_sqr(a[4]), a[4]);
+        o[4] = fr_sub(fr_sqr(a[5]), a[5]);
+    }
+};
+
+template <>
+struct MoGate<GATE_LOGUP_LAYER> {
+    static constexpr int N_INS = 4, N_OUTS = 2;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        o[0] = fr_add(fr_mul(a[0], a[3]), fr_mul(a[1], a[2]));
+        o[1] = fr_mul(a[1], a[3]);
+    }
+};
+
+template <>
+struct MoGate<GATE_ADD_INVERSES> {
+    static constexpr int N_INS = 2, N_OUTS = 2;
+    __device__ __forceinline__ static void eval(const Fr* a, Fr* o) {
+        o[0] = fr_add(a[0], a[1]);
+        o[1] = fr_mul(a[0], a[1]);
+    }
+};
+
+// sum_i gamma^i * out_i  (GammaWrapper::exec / the gamma_pows fold of the Deg2 objects)
+template <int G>
+__device__ __forceinline__ Fr gamma_eval(const Fr* a, const GateConsts& c) {
+    Fr o[MoGate<G>::N_OUTS];
+    MoGate<G>::eval(a, o);
+    Fr ret = o[0];
+#pragma unroll
+    for (int i = 1; i < MoGate<G>::N_OUTS; i++) ret = fr_add(ret, fr_mul(o[i], c.g[i]));
+    return ret;
+}
+
+// ---- single-output gates for DenseSumcheckObjectSO --------------------------------------------
+struct SoProd3 {
+    static constexpr int P = 3, DEG = 3;
+    __device__ __forceinline__ static Fr eval(const Fr* a, const GateConsts&) { return fr_mul(fr_mul(a[0], a[1]), a[2]); }
+};
+
+template <int NARGS>
+struct SoFoldedProd {
+    static constexpr int P = 2 * NARGS, DEG = 2;
+    __device__ __forceinline__ static Fr eval(const Fr* a, const GateConsts& c) {
+        Fr ret = fr_mul(a[0], a[NARGS]);  // gammas[0] == 1
+#pragma unroll
+        for (int i = 1; i < NARGS; i++) ret = fr_add(ret, fr_mul(fr_mul(a[i], a[i + NARGS]), c.g[i]));
+        return ret;
+    }
+};
+
+// EqWrapper(GammaWrapper(G, gamma)): last input is the eq table
+template <int G>
+struct SoEqGamma {
+    static constexpr int P = MoGate<G>::N_INS + 1, DEG = 3;
+    __device__ __forceinline__ static Fr eval(const Fr* a, const GateConsts& c) {
+        return fr_mul(gamma_eval<G>(a, c), a[MoGate<G>::N_INS]);
+    }
+};

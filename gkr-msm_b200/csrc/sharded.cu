@@ -1,0 +1,177 @@
+// Multi-GPU sharding of the dense sumcheck.
+//
+// Folding binds the LEAST significant index bit first (pairs 2i, 2i+1 -- sumcheck.rs:160-163), so splitting
+// the hypercube by its TOP log2(G) index bits gives every GPU a contiguous slice that stays independent for
+// the first n - log2(G) rounds: one process per GPU, each runs the same fused fold+eval kernel on its slice.
+// The only exchange is the per-round partial sums (deg field elements per rank).  They have to reach the
+// HOST anyway -- Fiat-Shamir stays on the host -- so the ranks of one box exchange them through a small
+// POSIX shared-memory segment (sequence-numbered slots, ~1 us) instead of a device collective: no kernel,
+// no NVLink traffic and no extra launch sits on the per-round critical path.  Every rank then runs the
+// identical transcript and derives the identical challenge.  After the local rounds each rank holds one
+// value per table; these G x P values are all-gathered the same way and the last log2(G) rounds run
+// replicated on every rank.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
+#include <cstring>
+#include "common.cuh"
+#include "so.hpp"
+#include "transcript.hpp"
+
+#define GKR_EX_MAX_RANKS 16
+#define GKR_EX_MAX_ELEMS 32
+
+struct ExShared {
+    std::atomic<uint64_t> seq[GKR_EX_MAX_RANKS];
+    uint64_t pad[8];
+    uint64_t data[2][GKR_EX_MAX_RANKS][GKR_EX_MAX_ELEMS * 4];
+};
+
+struct gkr_exchange {
+    ExShared* sh = nullptr;
+    int rank = 0, world = 1;
+    uint64_t counter = 0;
+    std::string name;
+    bool creator = false;
+};
+
+extern "C" int gkr_exchange_open(const char* name, int rank, int world, int create, gkr_exchange** out) {
+    if (!name || !out || world < 1 || world > GKR_EX_MAX_RANKS || rank < 0 || rank >= world) return GKR_ERR_ARG;
+    int fd = shm_open(name, create ? (O_CREAT | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return GKR_ERR_ARG;
+    if (create && ftruncate(fd, sizeof(ExShared)) != 0) {
+        close(fd);
+        return GKR_ERR_ARG;
+    }
+    void* p = mmap(nullptr, sizeof(ExShared), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return GKR_ERR_ARG;
+    gkr_exchange* ex = new gkr_exchange();
+    ex->sh = (ExShared*)p;
+    ex->rank = rank;
+    ex->world = world;
+    ex->name = name;
+    ex->creator = create != 0;
+    if (create) std::memset(p, 0, sizeof(ExShared));
+    *out = ex;
+    return GKR_OK;
+}
+
+extern "C" void gkr_exchange_close(gkr_exchange* ex) {
+    if (!ex) return;
+    munmap(ex->sh, sizeof(ExShared));
+    if (ex->creator) shm_unlink(ex->name.c_str());
+    delete ex;
+}
+
+// all-gather of n_elems field elements per rank; `all` receives world * n_elems elements ordered by rank
+extern "C" int gkr_exchange_allgather(gkr_exchange* ex, const uint64_t* mine, uint32_t n_elems, uint64_t* all) {
+    if (!ex || !mine || !all || n_elems > GKR_EX_MAX_ELEMS) return GKR_ERR_ARG;
+    const uint64_t c = ++ex->counter;
+    const int par = (int)(c & 1);
+    std::memcpy(ex->sh->data[par][ex->rank], mine, sizeof(uint64_t) * 4 * n_elems);
+    ex->sh->seq[ex->rank].store(c, std::memory_order_release);
+    for (int r = 0; r < ex->world; r++) {
+        uint64_t spins = 0;
+        while (ex->sh->seq[r].load(std::memory_order_acquire) < c) {
+            if (++spins > (1ull << 34)) return GKR_ERR_PROTOCOL;  // a peer died
+        }
+        std::memcpy(all + (size_t)r * 4 * n_elems, ex->sh->data[par][r], sizeof(uint64_t) * 4 * n_elems);
+    }
+    return GKR_OK;
+}
+
+// GenericSumcheckProtocol::prove (sumcheck.rs:101-123) over a hypercube sharded by its top index bits.
+//   so: this rank's DenseSumcheckObjectSO over its slice (local_rounds variables)
+//   global_claim: claim of the whole sum.  out_point: local_rounds + log2(world) challenges, reversed (:120).
+//   out_final_evals: n_polys elements (identical on every rank).
+extern "C" int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exchange* ex, uint32_t local_rounds,
+                                          int so_kind, int gate, uint32_t gate_param, const uint64_t* gate_consts, uint32_t n_consts,
+                                          const uint64_t global_claim[4], uint64_t out_claim[4], uint64_t* out_point,
+                                          uint64_t* out_final_evals) {
+    if (!t || !so || !global_claim) return GKR_ERR_ARG;
+    gkr_ctx* ctx = so->ctx;
+    const int world = ex ? ex->world : 1;
+    int g = 0;
+    while ((1 << g) < world) g++;
+    if ((1 << g) != world) return ctx->fail(GKR_ERR_ARG, "world size must be a power of two");
+    const uint32_t deg = so->degree(), P = so->num_polys();
+    gkr::FrH claim = frh_from_limbs(global_claim);
+    std::vector<gkr::FrH> r;
+    auto round_io = [&](const gkr::FrH* sums_total) {  // sums at nodes 1..deg of the WHOLE hypercube
+        gkr::FrH ev[GKR_MAX_DEG + 1];
+        for (uint32_t s = 0; s < deg; s++) ev[s + 1] = sums_total[s];
+        ev[0] = gkr::frh::sub(claim, ev[1]);
+        std::vector<gkr::FrH> poly = gkr::frh::interpolate_coeffs(ev, (int)deg + 1);
+        std::vector<gkr::FrH> msg;
+        msg.push_back(poly[0]);
+        for (size_t i = 2; i < poly.size(); i++) msg.push_back(poly[i]);
+        t->t.write_scalars(msg.data(), msg.size());
+        gkr::FrH x = t->t.challenge(128);
+        r.push_back(x);
+        claim = gkr::frh::evaluate_univar(poly, x);
+        return x;
+    };
+    std::vector<uint64_t> mine(4 * GKR_EX_MAX_ELEMS), all((size_t)4 * GKR_EX_MAX_ELEMS * GKR_EX_MAX_RANKS);
+    for (uint32_t k = 0; k < local_rounds; k++) {
+        gkr::FrH ev[GKR_MAX_DEG + 1];
+        uint32_t n = 0;
+        int rc = so->unipoly(ev, &n);  // ev[1..deg] are this shard's partial sums (ev[0] is not used here)
+        if (rc) return rc;
+        gkr::FrH tot[GKR_MAX_DEG];
+        if (world > 1) {
+            for (uint32_t s = 0; s < deg; s++) frh_to_limbs(ev[s + 1], mine.data() + 4 * s);
+            rc = gkr_exchange_allgather(ex, mine.data(), deg, all.data());
+            if (rc) return ctx->fail(rc, "partial-sum exchange failed");
+            for (uint32_t s = 0; s < deg; s++) {
+                tot[s] = gkr::frh::ZERO;
+                for (int q = 0; q < world; q++) tot[s] = gkr::frh::add(tot[s], frh_from_limbs(all.data() + ((size_t)q * deg + s) * 4));
+            }
+        } else {
+            for (uint32_t s = 0; s < deg; s++) tot[s] = ev[s + 1];
+        }
+        gkr::FrH x = round_io(tot);
+        rc = so->bind(x);
+        if (rc) return rc;
+    }
+    std::vector<gkr::FrH> fe(P);
+    int rc = so->final_evals(fe.data());
+    if (rc) return rc;
+    if (world > 1) {
+        // gather the G x P surviving values; table j over the remaining g variables is [rank 0, rank 1, ...]
+        for (uint32_t j = 0; j < P; j++) frh_to_limbs(fe[j], mine.data() + 4 * j);
+        rc = gkr_exchange_allgather(ex, mine.data(), P, all.data());
+        if (rc) return ctx->fail(rc, "final gather failed");
+        std::vector<gkr_table*> tabs(P, nullptr);
+        std::vector<uint64_t> col((size_t)4 * world);
+        for (uint32_t j = 0; j < P && rc == GKR_OK; j++) {
+            for (int q = 0; q < world; q++) std::memcpy(col.data() + 4 * q, all.data() + ((size_t)q * P + j) * 4, 32);
+            rc = gkr_table_upload(ctx, col.data(), (uint64_t)world, &tabs[j]);
+            if (rc == GKR_OK) rc = gkr_ctx_sync(ctx);  // `col` is reused
+        }
+        gkr_so* tail = nullptr;
+        uint64_t cl[4];
+        frh_to_limbs(claim, cl);
+        if (rc == GKR_OK) rc = gkr_so_create_dense(ctx, so_kind, gate, gate_param, gate_consts, n_consts, tabs.data(), P, (uint32_t)g, cl, &tail);
+        for (int k = 0; k < g && rc == GKR_OK; k++) {
+            gkr::FrH ev[GKR_MAX_DEG + 1];
+            uint32_t n = 0;
+            rc = tail->unipoly(ev, &n);
+            if (rc) break;
+            gkr::FrH x = round_io(ev + 1);
+            rc = tail->bind(x);
+        }
+        if (rc == GKR_OK) rc = tail->final_evals(fe.data());
+        delete tail;
+        for (auto* tb : tabs) gkr_table_free(tb);
+        if (rc) return rc;
+    }
+    if (out_claim) frh_to_limbs(claim, out_claim);
+    if (out_point)
+        for (size_t k = 0; k < r.size(); k++) frh_to_limbs(r[r.size() - 1 - k], out_point + 4 * k);
+    if (out_final_evals)
+        for (uint32_t j = 0; j < P; j++) frh_to_limbs(fe[j], out_final_evals + 4 * j);
+    return GKR_OK;
+}

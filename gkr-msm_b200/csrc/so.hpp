@@ -1,0 +1,21 @@
+// Base class behind the opaque `gkr_so` handle: the device-side counterpart of
+// `trait Sumcheckable<F>` (src/cleanup/protocols/sumchecks/vecvec_eq.rs:218-225).
+#pragma once
+#include "common.cuh"
+
+struct gkr_so {
+    gkr_ctx* ctx = nullptr;
+    virtual ~gkr_so() {}
+    // evals at nodes 0..deg (deg+1 values); the reference's UniPoly::from_evals is applied by the caller
+    virtual int unipoly(gkr::FrH* evals, uint32_t* n_evals) = 0;
+    virtual int bind(const gkr::FrH& t) = 0;
+    virtual int final_evals(gkr::FrH* out) = 0;
+    virtual gkr::FrH claim() const = 0;
+    virtual uint32_t degree() const = 0;
+    virtual uint32_t num_polys() const = 0;
+    virtual uint32_t round() const = 0;
+};
+
+// factories implemented in the .cu files
+int gkr_make_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const gkr::FrH* consts, uint32_t n_consts,
+                      gkr_table* const* tables, uint32_t n_polys, uint32_t num_vars, const gkr::FrH& claim, gkr_so** out);

@@ -1,0 +1,363 @@
+// Context, device tables and table builders (eq tables, synthetic inputs).
+//   eq tables: eq_poly_sequence_from_multiplier / eq_poly_sequence_last  src/utils.rs:222-262,
+//              EqPoly::evals src/cleanup/protocols/verifier_polys.rs:31-33
+#include <algorithm>
+#include <mutex>
+#include "common.cuh"
+
+#define GKR_RESULT_SLOTS 256
+
+static std::mutex g_slot_mutex;
+struct SlotPool {
+    std::vector<int> free_list;
+};
+static std::vector<std::pair<gkr_ctx*, SlotPool*>> g_pools;
+
+static SlotPool* pool_of(gkr_ctx* ctx) {
+    for (auto& p : g_pools)
+        if (p.first == ctx) return p.second;
+    return nullptr;
+}
+
+int gkr_result_slot_acquire(gkr_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    SlotPool* p = pool_of(ctx);
+    if (!p || p->free_list.empty()) return -1;
+    int s = p->free_list.back();
+    p->free_list.pop_back();
+    return s;
+}
+
+void gkr_result_slot_release(gkr_ctx* ctx, int slot) {
+    std::lock_guard<std::mutex> lk(g_slot_mutex);
+    SlotPool* p = pool_of(ctx);
+    if (p) p->free_list.push_back(slot);
+}
+
+extern "C" int gkr_version(void) { return 1; }
+
+extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
+    if (!out) return GKR_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return GKR_ERR_CUDA;  // no CPU fallback
+    gkr_ctx* ctx = new gkr_ctx();
+    ctx->device = device;
+    auto bail = [&](cudaError_t err) {
+        fprintf(stderr, "gkr_ctx_create: %s\n", cudaGetErrorString(err));
+        delete ctx;
+        return (int)GKR_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e);
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->partials, sizeof(Fr) * GKR_MAX_BLOCKS * GKR_MAX_DEG)) != cudaSuccess) return bail(e);
+    if ((e = cudaMalloc(&ctx->ticket, sizeof(unsigned int))) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->ticket, 0, sizeof(unsigned int))) != cudaSuccess) return bail(e);
+    if ((e = cudaHostAlloc(&ctx->result_host, sizeof(Fr) * GKR_RESULT_SLOTS * GKR_MAX_DEG, cudaHostAllocMapped)) != cudaSuccess) return bail(e);
+    if ((e = cudaHostGetDevicePointer(&ctx->result_dev, ctx->result_host, 0)) != cudaSuccess) return bail(e);
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mutex);
+        SlotPool* p = new SlotPool();
+        for (int i = GKR_RESULT_SLOTS - 1; i >= 0; i--) p->free_list.push_back(i);
+        g_pools.push_back({ctx, p});
+    }
+    *out = ctx;
+    return GKR_OK;
+}
+
+extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_slot_mutex);
+        for (size_t i = 0; i < g_pools.size(); i++)
+            if (g_pools[i].first == ctx) {
+                delete g_pools[i].second;
+                g_pools.erase(g_pools.begin() + i);
+                break;
+            }
+    }
+    if (ctx->partials) cudaFree(ctx->partials);
+    if (ctx->ticket) cudaFree(ctx->ticket);
+    if (ctx->result_host) cudaFreeHost(ctx->result_host);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* gkr_last_error(const gkr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int gkr_ctx_sync(gkr_ctx* ctx) {
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GKR_OK;
+}
+
+extern "C" uint64_t gkr_ctx_launch_count(const gkr_ctx* ctx) { return ctx->launches; }
+extern "C" void* gkr_ctx_stream(gkr_ctx* ctx) { return (void*)ctx->stream; }
+
+// ---- tables ----------------------------------------------------------------------------------------
+extern "C" int gkr_table_alloc(gkr_ctx* ctx, uint64_t n, gkr_table** out) {
+    if (!ctx || !out) return GKR_ERR_ARG;
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    gkr_table* t = new gkr_table();
+    t->ctx = ctx;
+    t->n = n;
+    cudaError_t e = cudaMalloc(&t->d, sizeof(Fr) * std::max<uint64_t>(n, 1));
+    if (e != cudaSuccess) {
+        delete t;
+        return ctx->fail(GKR_ERR_CUDA, std::string("cudaMalloc(table): ") + cudaGetErrorString(e));
+    }
+    *out = t;
+    return GKR_OK;
+}
+
+extern "C" int gkr_table_upload(gkr_ctx* ctx, const uint64_t* limbs, uint64_t n, gkr_table** out) {
+    if (!limbs && n) return ctx->fail(GKR_ERR_ARG, "null host buffer");
+    int rc = gkr_table_alloc(ctx, n, out);
+    if (rc) return rc;
+    if (n) GKR_CUDA_OK(ctx, cudaMemcpyAsync((*out)->d, limbs, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return GKR_OK;
+}
+
+extern "C" int gkr_table_download(gkr_ctx* ctx, const gkr_table* t, uint64_t* limbs_out) {
+    if (!t || !limbs_out) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (t->n) GKR_CUDA_OK(ctx, cudaMemcpyAsync(limbs_out, t->d, sizeof(Fr) * t->n, cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    return GKR_OK;
+}
+
+extern "C" uint64_t gkr_table_len(const gkr_table* t) { return t ? t->n : 0; }
+extern "C" void* gkr_table_device_ptr(gkr_table* t) { return t ? (void*)t->d : nullptr; }
+
+extern "C" void gkr_table_free(gkr_table* t) {
+    if (!t) return;
+    if (t->owned && t->d) {
+        cudaStreamSynchronize(t->ctx->stream);
+        cudaFree(t->d);
+    }
+    delete t;
+}
+
+// ---- synthetic input generator ------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64_at(uint64_t seed, uint64_t k) {
+    uint64_t z = seed + k * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ bool fr_geq_p(const Fr& a) {
+    const uint32_t p[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        if (a.l[i] > p[i]) return true;
+        if (a.l[i] < p[i]) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ Fr fr_sub_p_raw(const Fr& a) {
+    const uint32_t p[8] = {FR_P0, FR_P1, FR_P2, FR_P3, FR_P4, FR_P5, FR_P6, FR_P7};
+    Fr r;
+    uint64_t br = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint64_t d = (uint64_t)a.l[i] - p[i] - br;
+        r.l[i] = (uint32_t)d;
+        br = (d >> 63) & 1;
+    }
+    return r;
+}
+
+__global__ void synth_kernel(Fr* out, uint64_t n, uint64_t seed, uint64_t first) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        Fr v;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint64_t z = splitmix64_at(seed, 4 * (first + i) + j + 1);
+            v.l[2 * j] = (uint32_t)z;
+            v.l[2 * j + 1] = (uint32_t)(z >> 32);
+        }
+        if (fr_geq_p(v)) v = fr_sub_p_raw(v);
+        if (fr_geq_p(v)) v = fr_sub_p_raw(v);
+        out[i] = v;
+    }
+}
+
+extern "C" int gkr_table_synth(gkr_ctx* ctx, uint64_t seed, uint64_t first_index, uint64_t n, gkr_table** out) {
+    int rc = gkr_table_alloc(ctx, n, out);
+    if (rc) return rc;
+    if (n) {
+        unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
+        synth_kernel<<<grid, 256, 0, ctx->stream>>>((*out)->d, n, seed, first_index);
+        ctx->launches++;
+        GKR_CUDA_OK(ctx, cudaGetLastError());
+    }
+    return GKR_OK;
+}
+
+// ---- eq tables -------------------------------------------------------------------------------------------
+// Small table (n <= 10): one block runs the reference's doubling construction level by level
+// ([w - w r_i, w r_i], src/utils.rs:239-244) in shared memory.
+__global__ void eq_small_kernel(Fr* out, const Fr* point, int n, Fr mult) {
+    extern __shared__ Fr sh[];  // 2 * 2^n
+    Fr* a = sh;
+    Fr* b = sh + ((size_t)1 << n);
+    if (threadIdx.x == 0) a[0] = mult;
+    __syncthreads();
+    for (int lvl = 1; lvl <= n; lvl++) {
+        Fr r = point[lvl - 1];
+        int half = 1 << (lvl - 1);
+        for (int j = threadIdx.x; j < half; j += blockDim.x) {
+            Fr w = a[j];
+            Fr m = fr_mul(r, w);
+            b[2 * j] = fr_sub(w, m);
+            b[2 * j + 1] = m;
+        }
+        __syncthreads();
+        Fr* tmp = a;
+        a = b;
+        b = tmp;
+    }
+    for (int j = threadIdx.x; j < (1 << n); j += blockDim.x) out[j] = a[j];
+}
+
+// out[i] = hi[i >> k] * lo[i & (2^k - 1)]: eq over the concatenated point factors into the two halves.
+__global__ void eq_outer_kernel(Fr* out, const Fr* hi, const Fr* lo, int k, uint64_t n) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t mask = ((uint64_t)1 << k) - 1;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        out[i] = fr_mul(hi[i >> k], lo[i & mask]);
+    }
+}
+
+static int eq_build(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out) {
+    if (n <= 10) {
+        size_t sh = sizeof(Fr) * 2 * ((size_t)1 << n);
+        if (sh > 48 * 1024) GKR_CUDA_OK(ctx, cudaFuncSetAttribute(eq_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh));
+        eq_small_kernel<<<1, 256, sh, ctx->stream>>>(d_out, d_point, (int)n, mult);
+        ctx->launches++;
+        GKR_CUDA_OK(ctx, cudaGetLastError());
+        return GKR_OK;
+    }
+    uint32_t h = n / 2, k = n - h;
+    Fr *hi = nullptr, *lo = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&hi, sizeof(Fr) << h, ctx->stream));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&lo, sizeof(Fr) << k, ctx->stream));
+    int rc = eq_build(ctx, d_point, h, mult, hi);
+    if (rc == GKR_OK) rc = eq_build(ctx, d_point + h, k, fr_from_host(gkr::frh::ONE), lo);
+    if (rc == GKR_OK) {
+        uint64_t total = (uint64_t)1 << n;
+        unsigned grid = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 8);
+        eq_outer_kernel<<<grid, 256, 0, ctx->stream>>>(d_out, hi, lo, (int)k, total);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFreeAsync(hi, ctx->stream);
+    cudaFreeAsync(lo, ctx->stream);
+    return rc;
+}
+
+extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, const uint64_t mult[4], gkr_table** out) {
+    if (!ctx || !out || (!point && n) || !mult) return GKR_ERR_ARG;
+    if (n >= 40) return ctx->fail(GKR_ERR_ARG, "eq table: too many variables");
+    gkr::FrH m = frh_from_limbs(mult);
+    if (!frh_canonical(m)) return ctx->fail(GKR_ERR_ARG, "eq table: multiplier not canonical");
+    for (uint32_t i = 0; i < n; i++)
+        if (!frh_canonical(frh_from_limbs(point + 4 * i))) return ctx->fail(GKR_ERR_ARG, "eq table: point not canonical");
+    int rc = gkr_table_alloc(ctx, (uint64_t)1 << n, out);
+    if (rc) return rc;
+    Fr* d_point = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_point, sizeof(Fr) * std::max<uint32_t>(n, 1), ctx->stream));
+    if (n) GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_point, point, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    rc = eq_build(ctx, d_point, n, fr_from_host(m), (*out)->d);
+    cudaFreeAsync(d_point, ctx->stream);
+    if (rc) {
+        gkr_table_free(*out);
+        *out = nullptr;
+    }
+    return rc;
+}
+
+// ---- per-launch timing (used only by bench.py's roofline leg) ----------------------------------------------
+extern "C" int gkr_ctx_timing_enable(gkr_ctx* ctx, int on) {
+    if (!ctx) return GKR_ERR_ARG;
+    ctx->timing = on != 0;
+    return GKR_OK;
+}
+
+// Drains the recorded launches: kernel_id[i], n_items[i], ms[i].  Returns the number written (<= max_n).
+extern "C" int gkr_ctx_timing_read(gkr_ctx* ctx, int* kernel_id, uint64_t* n_items, float* ms, int max_n) {
+    if (!ctx) return GKR_ERR_ARG;
+    cudaStreamSynchronize(ctx->stream);
+    int n = 0;
+    for (auto& t : ctx->timed) {
+        if (n < max_n) {
+            float v = 0.f;
+            cudaEventElapsedTime(&v, t.start, t.stop);
+            kernel_id[n] = t.kernel_id;
+            n_items[n] = t.n_items;
+            ms[n] = v;
+            n++;
+        }
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
+    }
+    ctx->timed.clear();
+    return n;
+}
+
+// ---- integer-pipe microbenchmark: ILP independent chains of dependent Montgomery multiplications -----------
+template <int ILP>
+__global__ void modmul_bench_kernel(Fr* out, int iters) {
+    Fr x[ILP], y;
+    for (int k = 0; k < ILP; k++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[k].l[i] = (threadIdx.x + 1) * (i + 3 + k) + blockIdx.x;
+        x[k].l[7] &= 0x3fffffffu;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) y.l[i] = 0x9e3779b9u * (i + 1) + threadIdx.x;
+    y.l[7] &= 0x3fffffffu;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) x[k] = fr_mul(x[k], y);
+    }
+    Fr acc = x[0];
+    for (int k = 1; k < ILP; k++) acc = fr_add(acc, x[k]);
+    if (acc.l[0] == 0x12345678u && acc.l[5] == 77u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;  // keep the work alive
+}
+
+// Runs `iters` x ILP multiplications per thread on a grid filling the device; returns modmul/s.
+extern "C" int gkr_bench_modmul(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* modmul_per_s) {
+    if (!ctx || !modmul_per_s) return GKR_ERR_ARG;
+    Fr* out = nullptr;
+    int grid = ctx->num_sms * blocks_per_sm;
+    GKR_CUDA_OK(ctx, cudaMalloc(&out, sizeof(Fr) * (size_t)grid * threads));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    for (int rep = 0; rep < 2; rep++) {
+        cudaEventRecord(a, ctx->stream);
+        if (ilp == 1) modmul_bench_kernel<1><<<grid, threads, 0, ctx->stream>>>(out, iters);
+        else if (ilp == 2) modmul_bench_kernel<2><<<grid, threads, 0, ctx->stream>>>(out, iters);
+        else modmul_bench_kernel<4><<<grid, threads, 0, ctx->stream>>>(out, iters);
+        cudaEventRecord(b, ctx->stream);
+        ctx->launches++;
+    }
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    int eff_ilp = ilp == 1 ? 1 : (ilp == 2 ? 2 : 4);
+    *modmul_per_s = (double)grid * threads * (double)iters * eff_ilp / (ms * 1e-3);
+    return GKR_OK;
+}

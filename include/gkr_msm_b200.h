@@ -1,0 +1,168 @@
+/* gkr_msm_b200.h -- C ABI of the B200-native prover backend for the GKR-MSM hot path.
+ *
+ * The reference (morgana-proofs/GKR-MSM) is a pure-Rust crate with NO FFI; the narrowest waist every hot
+ * loop sits behind is a set of Rust traits.  Each entry point below replaces one trait method / free
+ * function of the reference (cited as file:line relative to the reference root) and is what a
+ * `#[cfg(feature = "gpu")]` shim in the crate would bind with `extern "C"`.
+ *
+ * Conventions
+ *   - Field elements cross the boundary exactly as the reference stores them: `Fr` =
+ *     ark_ff::Fp256<MontBackend<FrConfig,4>> = 4 little-endian u64 limbs in Montgomery form (R = 2^256),
+ *     canonical (< r).  A `Vec<Fr>` of n elements is n*4 contiguous u64.  No torch / C++ types here.
+ *   - Every function returns 0 on success and a negative gkr_status otherwise; `gkr_last_error` gives
+ *     the message.  The reference never returns Result on this path -- it panics (e.g.
+ *     src/cleanup/protocols/sumcheck.rs:271-274); the Rust shim turns a non-zero status into panic!().
+ *   - One calling thread per context (the reference's protocol code is single-threaded: the transcript
+ *     is `&mut`).  Kernels are enqueued on the context's stream; `unipoly`/`final_evals` synchronise.
+ *   - There is no CPU fallback: without a CUDA device `gkr_ctx_create` fails with GKR_ERR_CUDA.
+ */
+#ifndef GKR_MSM_B200_H
+#define GKR_MSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gkr_ctx gkr_ctx;               /* device context: stream, scratch, pinned result slots  */
+typedef struct gkr_table gkr_table;           /* device-resident dense table (`Vec<Fr>`)                */
+typedef struct gkr_so gkr_so;                 /* a `Sumcheckable` object                                */
+typedef struct gkr_transcript gkr_transcript; /* host-side ProofTranscript2 (merlin)                    */
+
+typedef enum gkr_status {
+    GKR_OK = 0,
+    GKR_ERR_CUDA = -1,      /* CUDA runtime error / no device                                          */
+    GKR_ERR_ARG = -2,       /* invalid argument (reference: assert!/assert_eq! on construction)        */
+    GKR_ERR_PROTOCOL = -3,  /* call-order violation (reference: panic in bind()/unipoly())             */
+    GKR_ERR_UNSUPPORTED = -4
+} gkr_status;
+
+/* Closed gate enum (the reference's `AlgFn` is an open generic, src/cleanup/utils/algfn.rs:20-34). */
+typedef enum gkr_gate_id {
+    GKR_GATE_AFF_L1 = 0,        /* affine_twisted_edwards_add_l1    4->3  twisted_edwards_ops.rs:10-14  */
+    GKR_GATE_AFF_L2 = 1,        /* affine_twisted_edwards_add_l2    3->3  :16-20                        */
+    GKR_GATE_AFF_L3 = 2,        /* affine_twisted_edwards_add_l3    3->3  :22-29                        */
+    GKR_GATE_PRJ_L1 = 3,        /* twisted_edwards_add_l1           6->4  :31-40                        */
+    GKR_GATE_PRJ_L2 = 4,        /* twisted_edwards_add_l2           4->4  :43-52                        */
+    GKR_GATE_PRJ_L3 = 5,        /* twisted_edwards_add_l3           4->3  :54-65                        */
+    GKR_GATE_TRI_L1 = 6,        /* triangle_twisted_edwards_add_l1 12->12 :67-80                        */
+    GKR_GATE_BITCHECK = 7,      /* BitCheckFn                       1->1  algfn.rs:262-291              */
+    GKR_GATE_LOGUP_LAYER = 8,   /* LogupLayerFn                     4->2  logup_mainphase.rs:42-61      */
+    GKR_GATE_ADD_INVERSES = 9,  /* AddInversesFn                    2->2  pushforward.rs:266-281        */
+    GKR_GATE_PROD3 = 10,        /* Prod3Fn (single output, deg 3)   3->1  pushforward.rs:38-50          */
+    GKR_GATE_FOLDED_PROD = 11,  /* FoldedProdAlgFn(gamma, nargs)  2n->1  multiopen_reduction.rs:13-41   */
+    GKR_GATE_ID = 12,           /* IdAlgFn(n)                       n->n  algfn.rs:130-164              */
+    GKR_GATE_AFF_L1_BITCHECK2 = 13 /* Stacked(aff_l1, Repeated(BitCheck,2)) 6->5 bintree_add.rs:259-273 */
+} gkr_gate_id;
+
+/* ---- context ------------------------------------------------------------------------------- */
+int gkr_ctx_create(int device, gkr_ctx** out);
+void gkr_ctx_destroy(gkr_ctx* ctx);
+const char* gkr_last_error(const gkr_ctx* ctx);
+int gkr_ctx_sync(gkr_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's `gpu_launches`) */
+uint64_t gkr_ctx_launch_count(const gkr_ctx* ctx);
+/* raw cudaStream_t of the context (so callers can record CUDA events on the launching stream) */
+void* gkr_ctx_stream(gkr_ctx* ctx);
+int gkr_version(void);
+/* measurement hooks (bench.py only): per-launch CUDA-event timing on the context stream, and an
+ * integer-pipe probe (chains of dependent Montgomery multiplications) giving the modmul/s ceiling. */
+int gkr_ctx_timing_enable(gkr_ctx* ctx, int on);
+int gkr_ctx_timing_read(gkr_ctx* ctx, int* kernel_id, uint64_t* n_items, float* ms, int max_n);
+int gkr_bench_modmul(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* modmul_per_s);
+
+/* ---- dense tables: `Vec<Fr>` resident in HBM ---------------------------------------------------
+ * Ownership mirrors the reference: sumcheck objects take their tables by value
+ * (`ProverInput = Vec<Vec<F>>`, dense_eq.rs:193) but the dense objects never modify the originals on
+ * the device (the first fold writes a fresh half-size buffer), so a table stays valid and resident
+ * after an object was created from it ("clone before prove", pushforward.rs:682-685, costs nothing). */
+int gkr_table_upload(gkr_ctx* ctx, const uint64_t* limbs, uint64_t n, gkr_table** out);
+int gkr_table_download(gkr_ctx* ctx, const gkr_table* t, uint64_t* limbs_out);
+int gkr_table_alloc(gkr_ctx* ctx, uint64_t n, gkr_table** out);
+/* synthetic table: element i = (SplitMix64 stream `seed`, 4 outputs starting at 4*(first_index+i)) mod r,
+ * taken as Montgomery limbs.  Used by bench.py so device-resident runs need no PCIe traffic; first_index
+ * lets each GPU generate its own shard of one global table. */
+int gkr_table_synth(gkr_ctx* ctx, uint64_t seed, uint64_t first_index, uint64_t n, gkr_table** out);
+uint64_t gkr_table_len(const gkr_table* t);
+void* gkr_table_device_ptr(gkr_table* t);
+void gkr_table_free(gkr_table* t);
+
+/* eq_poly_sequence_from_multiplier(mult, point).last()   src/utils.rs:222-262
+ * (== EqPoly::evals, src/cleanup/protocols/verifier_polys.rs:31-33, with mult = 1).
+ * point: n elements; last coordinate <-> least-significant index bit.  out has 2^n entries. */
+int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, const uint64_t mult[4], gkr_table** out);
+
+/* sum_i f(tables[0][i], .., tables[P-1][i])  for a single-output gate -- the `claim_hint` the callers of
+ * DenseSumcheckObjectSO::new compute on the CPU (e.g. sumcheck.rs:951, pushforward.rs:765-776). */
+int gkr_dense_gate_sum(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const uint64_t* gate_consts,
+                       uint32_t n_consts, gkr_table* const* tables, uint32_t n_polys, uint64_t out[4]);
+
+/* ---- trait Sumcheckable  (src/cleanup/protocols/sumchecks/vecvec_eq.rs:218-225) -----------------
+ * so_kind selects how the gate is wrapped into a single-output function:                           */
+typedef enum gkr_so_kind {
+    GKR_SO_PLAIN = 0,    /* gate is already single-output: PROD3, FOLDED_PROD(gate_param = nargs)     */
+    GKR_SO_EQ_GAMMA = 1  /* EqWrapper(GammaWrapper(gate, gamma)): last table is the eq table          */
+} gkr_so_kind;
+
+/* DenseSumcheckObjectSO::new(polys, f, num_vars, claim_hint)   src/cleanup/protocols/sumcheck.rs:252-261
+ *   gate_consts: n_consts field elements; for GKR_SO_EQ_GAMMA element i is gamma^i (i = 0..n_outs-1,
+ *   element 0 ignored); for FOLDED_PROD element i is gammas[i] (make_gamma_pows(gamma, nargs)).
+ *   tables: n_polys device tables of 2^num_vars entries each (reference asserts both, :255-258). */
+int gkr_so_create_dense(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const uint64_t* gate_consts,
+                        uint32_t n_consts, gkr_table* const* tables, uint32_t n_polys, uint32_t num_vars,
+                        const uint64_t claim[4], gkr_so** out);
+
+/* Sumcheckable::unipoly: writes the round polynomial as its evaluations at 0..deg ((deg+1)*4 limbs);
+ * the shim applies liblasso UniPoly::from_evals.  Dense object: a second call returns the cached
+ * value (sumcheck.rs:280-281).  Calling after the last round -> GKR_ERR_PROTOCOL (:278). */
+int gkr_so_unipoly(gkr_so* so, uint64_t* evals_out, uint32_t* n_evals);
+/* Sumcheckable::bind(t): requires a preceding unipoly() (sumcheck.rs:271-274) else GKR_ERR_PROTOCOL. */
+int gkr_so_bind(gkr_so* so, const uint64_t t[4]);
+/* Sumcheckable::final_evals: n_polys*4 limbs; only after the last round (sumcheck.rs:336). */
+int gkr_so_final_evals(gkr_so* so, uint64_t* out);
+/* current running claim (DenseSumcheckObjectSO::claim) */
+int gkr_so_claim(const gkr_so* so, uint64_t out[4]);
+uint32_t gkr_so_degree(const gkr_so* so);
+uint32_t gkr_so_num_polys(const gkr_so* so);
+uint32_t gkr_so_round(const gkr_so* so);
+void gkr_so_destroy(gkr_so* so);
+
+/* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
+ * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */
+int gkr_transcript_new(const uint8_t* label, size_t label_len, gkr_transcript** out);
+void gkr_transcript_free(gkr_transcript* t);
+int gkr_transcript_write_scalars(gkr_transcript* t, const uint64_t* limbs, uint32_t n);
+int gkr_transcript_write_raw(gkr_transcript* t, const uint8_t* msg, size_t len);
+int gkr_transcript_challenge(gkr_transcript* t, uint32_t bitsize, uint64_t out[4]);
+int gkr_transcript_raw_challenge(gkr_transcript* t, uint8_t* out, size_t len);
+size_t gkr_transcript_proof_len(const gkr_transcript* t);
+int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out);
+
+/* GenericSumcheckProtocol::prove   src/cleanup/protocols/sumcheck.rs:101-123
+ * Runs `num_rounds` rounds of (unipoly -> compress -> write_scalars -> challenge(128) -> bind).
+ * out_claim: final claim; out_point: num_rounds elements, already reversed (:120);
+ * out_final_evals: n_polys elements. */
+int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_rounds, uint64_t out_claim[4],
+                       uint64_t* out_point, uint64_t* out_final_evals);
+
+/* ---- multi-GPU: hypercube sharded by its top index bits, one process per GPU ----------
+ * gkr_exchange: all-gather of a few field elements between the ranks of one box through POSIX shared
+ * memory (the per-round partial sums must reach the host-side transcript anyway).                      */
+typedef struct gkr_exchange gkr_exchange;
+int gkr_exchange_open(const char* name, int rank, int world, int create, gkr_exchange** out);
+void gkr_exchange_close(gkr_exchange* ex);
+int gkr_exchange_allgather(gkr_exchange* ex, const uint64_t* mine, uint32_t n_elems, uint64_t* all);
+/* GenericSumcheckProtocol::prove over a sharded DenseSumcheckObjectSO: `so` covers this rank's slice
+ * (local_rounds variables); ex == NULL means a single GPU.  The gate description is repeated because the
+ * last log2(world) rounds run on a small replicated object built from the gathered survivors. */
+int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exchange* ex, uint32_t local_rounds, int so_kind, int gate,
+                               uint32_t gate_param, const uint64_t* gate_consts, uint32_t n_consts,
+                               const uint64_t global_claim[4], uint64_t out_claim[4], uint64_t* out_point,
+                               uint64_t* out_final_evals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKR_MSM_B200_H */
