@@ -81,6 +81,13 @@ def _sig(lib):
     f("gkr_so_num_polys", C.c_uint32, _vp)
     f("gkr_so_round", C.c_uint32, _vp)
     f("gkr_so_destroy", None, _vp)
+    f("gkr_vecvec_upload", C.c_int, _vp, _vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp))
+    f("gkr_vecvec_num_rows", C.c_uint32, _vp)
+    f("gkr_vecvec_total_len", C.c_uint64, _vp)
+    f("gkr_vecvec_download", C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32))
+    f("gkr_vecvec_free", None, _vp)
+    f("gkr_so_create_deg2_dense", C.c_int, _vp, _vp, _vp, C.c_uint32, C.POINTER(_vp), C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.POINTER(_vp))
+    f("gkr_so_create_deg2_vecvec", C.c_int, _vp, C.c_int, C.POINTER(_vp), C.c_uint32, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp))
     f("gkr_transcript_new", C.c_int, _vp, C.c_size_t, C.POINTER(_vp))
     f("gkr_transcript_free", None, _vp)
     f("gkr_transcript_write_scalars", C.c_int, _vp, _vp, C.c_uint32)
@@ -212,6 +219,86 @@ class Context:
         self.check(self.lib.gkr_so_create_dense(self.h, so_kind, gate, gate_param, _ptr(c), c.shape[0], arr, len(tables),
                                                 num_vars, _ptr(cl), C.byref(h)))
         return SumcheckObject(self, h, list(tables))
+
+
+    # appended methods are attached below (deg2 objects, vecvec upload)
+
+
+def _ctx_upload_vecvec(self, rows, row_pad, col_pad, row_logsize, col_logsize) -> "VecVec":
+    """VecVecPolynomial::new: rows = list of (len_r, 4) uint64 arrays (Montgomery limbs)."""
+    lens = np.array([len(r) for r in rows], dtype=np.uint32)
+    flat = np.concatenate([_limbs(r).reshape(-1, 4) for r in rows] + [np.zeros((0, 4), np.uint64)]) if len(rows) else np.zeros((0, 4), np.uint64)
+    flat = np.ascontiguousarray(flat)
+    rp, cp = _limbs(row_pad).reshape(4), _limbs(col_pad).reshape(4)
+    h = _vp()
+    self.check(self.lib.gkr_vecvec_upload(self.h, _ptr(flat), _ptr(lens), len(rows), _ptr(rp), _ptr(cp), row_logsize, col_logsize, C.byref(h)))
+    return VecVec(self, h)
+
+
+def _ctx_deg2_dense_so(self, parts, tables, gamma_pows, claim, point) -> "SumcheckObject":
+    """parts: list of (gate_id, repeat)."""
+    pg = np.array([p[0] for p in parts], dtype=np.int32)
+    pr = np.array([p[1] for p in parts], dtype=np.uint32)
+    arr = (_vp * len(tables))(*[t.h for t in tables])
+    gp, cl, pt = _limbs(gamma_pows).reshape(-1, 4), _limbs(claim).reshape(4), _limbs(point).reshape(-1, 4)
+    h = _vp()
+    self.check(self.lib.gkr_so_create_deg2_dense(self.h, _ptr(pg), _ptr(pr), len(parts), arr, len(tables), _ptr(gp), _ptr(cl), _ptr(pt),
+                                                 pt.shape[0], C.byref(h)))
+    return SumcheckObject(self, h, list(tables))
+
+
+def _ctx_deg2_vecvec_so(self, gate, polys, gamma_pows, claim, point, col_logsize) -> "SumcheckObject":
+    arr = (_vp * len(polys))(*[p.h for p in polys])
+    gp, cl, pt = _limbs(gamma_pows).reshape(-1, 4), _limbs(claim).reshape(4), _limbs(point).reshape(-1, 4)
+    h = _vp()
+    self.check(self.lib.gkr_so_create_deg2_vecvec(self.h, gate, arr, len(polys), _ptr(gp), _ptr(cl), _ptr(pt), pt.shape[0], col_logsize,
+                                                  C.byref(h)))
+    return SumcheckObject(self, h, list(polys))
+
+
+Context.upload_vecvec = _ctx_upload_vecvec
+Context.deg2_dense_so = _ctx_deg2_dense_so
+Context.deg2_vecvec_so = _ctx_deg2_vecvec_so
+
+
+class VecVec:
+    """gkr_vecvec: VecVecPolynomial<F> resident in HBM."""
+
+    def __init__(self, ctx, h):
+        self.ctx, self.h = ctx, h
+
+    @property
+    def num_rows(self) -> int:
+        return int(self.ctx.lib.gkr_vecvec_num_rows(self.h))
+
+    @property
+    def total_len(self) -> int:
+        return int(self.ctx.lib.gkr_vecvec_total_len(self.h))
+
+    def download(self):
+        """(rows: list of (len, 4) arrays, row_pad, col_pad, row_logsize, col_logsize)"""
+        flat = np.zeros((max(self.total_len, 1), 4), np.uint64)
+        lens = np.zeros(max(self.num_rows, 1), np.uint32)
+        rp, cp = np.zeros(4, np.uint64), np.zeros(4, np.uint64)
+        rl, cl = C.c_uint32(0), C.c_uint32(0)
+        self.ctx.check(self.ctx.lib.gkr_vecvec_download(self.ctx.h, self.h, _ptr(flat), _ptr(lens), _ptr(rp), _ptr(cp), C.byref(rl), C.byref(cl)))
+        rows, off = [], 0
+        for r in range(self.num_rows):
+            rows.append(flat[off:off + int(lens[r])].copy())
+            off += int(lens[r])
+        return rows, rp, cp, rl.value, cl.value
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.gkr_vecvec_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
 
 
 MONT_ONE = np.array([0x00000001FFFFFFFE, 0x5884B7FA00034802, 0x998C4FEFECBC4FF5, 0x1824B159ACC5056F], dtype=np.uint64)

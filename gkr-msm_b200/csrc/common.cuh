@@ -142,7 +142,8 @@ __device__ __forceinline__ void block_reduce_fr(Fr* acc, Fr* smem /* [N * warps]
 template <int N>
 __device__ __forceinline__ void grid_reduce_fr(Fr* acc, Fr* smem, Fr* partials, unsigned int* ticket, Fr* result) {
     block_reduce_fr<N>(acc, smem);
-    if (gridDim.x == 1) {
+    const unsigned int n_blocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (n_blocks == 1) {
         if (threadIdx.x == 0) {
 #pragma unroll
             for (int s = 0; s < N; s++) result[s] = acc[s];
@@ -152,17 +153,17 @@ __device__ __forceinline__ void grid_reduce_fr(Fr* acc, Fr* smem, Fr* partials, 
     __shared__ bool is_last;
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < N; s++) partials[(size_t)blockIdx.x * N + s] = acc[s];
+        for (int s = 0; s < N; s++) partials[(size_t)bid * N + s] = acc[s];
         __threadfence();
         unsigned int tk = atomicAdd(ticket, 1u);
-        is_last = (tk == gridDim.x - 1);
+        is_last = (tk == n_blocks - 1);
     }
     __syncthreads();
     if (!is_last) return;
     __threadfence();
 #pragma unroll
     for (int s = 0; s < N; s++) acc[s] = fr_zero();
-    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+    for (unsigned int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
 #pragma unroll
         for (int s = 0; s < N; s++) {
             const Fr* p = &partials[(size_t)b * N + s];

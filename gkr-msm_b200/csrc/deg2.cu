@@ -1,0 +1,900 @@
+// Degree-2 gate sumchecks with the eq factor pulled out (Gruen-style), dense and ragged:
+//   DenseDeg2SumcheckObjectSO      src/cleanup/protocols/sumchecks/dense_eq.rs:62-173
+//   VecVecDeg2(Lo)SumcheckObjectSO src/cleanup/protocols/sumchecks/vecvec_eq.rs:74-398
+//   EQPolyData / EQPolyPointParts  src/cleanup/polys/vecvec.rs:20-147
+//   VecVecPolynomial, bind_21      src/cleanup/polys/vecvec.rs:149-206, 420-441
+//   UnivarFormat::from12           src/cleanup/protocols/sumchecks/vecvec_eq.rs:197-216
+//
+// Device layout of a VecVecPolynomial: CSR -- one flat Fr array (rows concatenated, every row even-length
+// as VecVecPolynomial::new pads them) plus per-round row offsets precomputed on the host for ALL sparse
+// rounds at construction (row lengths halve and re-pad deterministically, vecvec.rs:432-437).
+// The reference's in-place `make_21` (p[2i] <- 2 p[2i+1] - p[2i]) is never materialised: the eval kernel
+// forms the value at "2" in registers, and the fold p[2i+1] + (t-1)(p2 - p[2i+1]) == p[2i] + t (p[2i+1]-p[2i]).
+// Per round the device returns S1 = sum_pairs w*G(p at 1), S2 = sum_pairs w*G(p at 2) with
+// w = eq_row[idx] * row_eq_coefs[row] and G = sum_o gamma^o f_o, plus T = sum_rows row_eq_coefs[row] *
+// (1 - sum_{idx < len/2} eq_row[idx]) for the closed-form padding term; the O(1) rest (pad_results, col pad,
+// multiplier, from12) is host arithmetic exactly as in the reference.
+#include <algorithm>
+#include "common.cuh"
+#include "gates.cuh"
+#include "host_gates.hpp"
+#include "so.hpp"
+
+int gkr_result_slot_acquire(gkr_ctx* ctx);
+void gkr_result_slot_release(gkr_ctx* ctx, int slot);
+int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out);
+
+struct gkr_vecvec {
+    gkr_ctx* ctx = nullptr;
+    Fr* d = nullptr;
+    uint64_t total = 0;
+    std::vector<uint32_t> row_len;  // host copy (even lengths)
+    gkr::FrH row_pad, col_pad;
+    uint32_t row_logsize = 0, col_logsize = 0;
+};
+
+struct Deg2Block {
+    int gate;
+    int in_idx[6];
+    int out_off;
+};
+
+struct Deg2EvalArgs {
+    const Fr* const* tabs;     // [P] flat data of the current round
+    const Deg2Block* blocks;   // [gridDim.y]
+    const Fr* gammas;          // [n_outs], gammas[0] == 1
+    const uint32_t* pair_off;  // [nrows + 1] row offsets in PAIRS; nullptr: one dense row
+    uint32_t nrows;
+    const Fr* eq;              // eq table of this round (row-local part)
+    const Fr* rowcoef;         // [nrows] or nullptr
+    uint64_t n_pairs;
+    Fr* partials;
+    unsigned int* ticket;
+    Fr* result;                // 2 values: S1, S2
+};
+
+template <int G>
+__device__ __forceinline__ void deg2_block_eval(const Deg2EvalArgs& A, const Deg2Block& blk, uint64_t q, const Fr& w, Fr* acc) {
+    constexpr int NI = MoGate<G>::N_INS, NO = MoGate<G>::N_OUTS;
+    Fr a1[NI], a2[NI];
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+        const Fr* src = A.tabs[blk.in_idx[j]] + 2 * q;
+        Fr p0 = src[0], p1 = src[1];
+        a1[j] = p1;
+        a2[j] = fr_sub(fr_dbl(p1), p0);
+    }
+    Fr o1[NO], o2[NO];
+    MoGate<G>::eval(a1, o1);
+    MoGate<G>::eval(a2, o2);
+    Fr g1, g2;
+    if (blk.out_off == 0) {
+        g1 = o1[0];
+        g2 = o2[0];
+    } else {
+        Fr gm = A.gammas[blk.out_off];
+        g1 = fr_mul(o1[0], gm);
+        g2 = fr_mul(o2[0], gm);
+    }
+#pragma unroll
+    for (int o = 1; o < NO; o++) {
+        Fr gm = A.gammas[blk.out_off + o];
+        g1 = fr_add(g1, fr_mul(o1[o], gm));
+        g2 = fr_add(g2, fr_mul(o2[o], gm));
+    }
+    acc[0] = fr_add(acc[0], fr_mul(g1, w));
+    acc[1] = fr_add(acc[1], fr_mul(g2, w));
+}
+
+// grid = (x: pairs, y: gate blocks).  All blocks of all y reduce into the same two sums.
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_eval_kernel(const __grid_constant__ Deg2EvalArgs A) {
+    __shared__ Fr smem[2 * (GKR_REDUCE_THREADS / 32)];
+    Fr acc[2] = {fr_zero(), fr_zero()};
+    const Deg2Block blk = A.blocks[blockIdx.y];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < A.n_pairs; q += stride) {
+        Fr w;
+        if (A.pair_off) {
+            uint32_t lo = 0, hi = A.nrows;  // largest r with pair_off[r] <= q  (empty rows repeat an offset)
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if ((uint64_t)A.pair_off[mid] <= q) lo = mid; else hi = mid;
+            }
+            // rows of length zero share their offset with the next row: step to the last row starting at <= q
+            w = fr_mul(A.eq[q - A.pair_off[lo]], A.rowcoef[lo]);
+        } else {
+            w = A.eq[q];
+        }
+        switch (blk.gate) {
+            case GATE_AFF_L1: deg2_block_eval<GATE_AFF_L1>(A, blk, q, w, acc); break;
+            case GATE_AFF_L2: deg2_block_eval<GATE_AFF_L2>(A, blk, q, w, acc); break;
+            case GATE_AFF_L3: deg2_block_eval<GATE_AFF_L3>(A, blk, q, w, acc); break;
+            case GATE_PRJ_L1: deg2_block_eval<GATE_PRJ_L1>(A, blk, q, w, acc); break;
+            case GATE_PRJ_L2: deg2_block_eval<GATE_PRJ_L2>(A, blk, q, w, acc); break;
+            case GATE_PRJ_L3: deg2_block_eval<GATE_PRJ_L3>(A, blk, q, w, acc); break;
+            case GATE_BITCHECK: deg2_block_eval<GATE_BITCHECK>(A, blk, q, w, acc); break;
+            case GATE_LOGUP_LAYER: deg2_block_eval<GATE_LOGUP_LAYER>(A, blk, q, w, acc); break;
+            case GATE_ADD_INVERSES: deg2_block_eval<GATE_ADD_INVERSES>(A, blk, q, w, acc); break;
+            default: break;
+        }
+    }
+    grid_reduce_fr<2>(acc, smem, A.partials, A.ticket, A.result);
+}
+
+// T = sum_rows rowcoef[row] * (1 - eq_sum(pt, len_row / 2)): the closed form of src/utils.rs:265-291 per row
+struct Deg2PadArgs {
+    const uint32_t* pair_off;
+    uint32_t nrows;
+    const Fr* rowcoef;
+    const Fr* pt;  // the row variables of this round's eq table (n_pt of them), pt[0] <-> most significant bit
+    uint32_t n_pt;
+    Fr* partials;
+    unsigned int* ticket;
+    Fr* result;
+};
+
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_pad_kernel(const __grid_constant__ Deg2PadArgs A) {
+    __shared__ Fr smem[GKR_REDUCE_THREADS / 32];
+    Fr acc[1] = {fr_zero()};
+    const Fr one = fr_one();
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < A.nrows; r += gridDim.x * blockDim.x) {
+        uint64_t k = A.pair_off[r + 1] - A.pair_off[r];
+        Fr s;  // eq_sum(pt, k)
+        if (k >= ((uint64_t)1 << A.n_pt)) {
+            s = one;
+        } else {
+            Fr mult = one;
+            s = fr_zero();
+            for (uint32_t i = 0; i < A.n_pt; i++) {
+                uint32_t bit = (uint32_t)(k >> (A.n_pt - i - 1)) & 1u;
+                Fr p = A.pt[i];
+                if (bit) {
+                    Fr nm = fr_mul(mult, p);
+                    s = fr_add(s, fr_sub(mult, nm));
+                    mult = nm;
+                } else {
+                    mult = fr_mul(mult, fr_sub(one, p));
+                }
+            }
+        }
+        acc[0] = fr_add(acc[0], fr_mul(A.rowcoef[r], fr_sub(one, s)));
+    }
+    grid_reduce_fr<1>(acc, smem, A.partials, A.ticket, A.result);
+}
+
+// ragged fold (VecVecPolynomial::bind_21): grid.y = table
+struct VvFoldArgs {
+    const Fr* const* in;
+    Fr* const* out;
+    const uint32_t* off_old;  // element offsets [nrows + 1]
+    const uint32_t* off_new;
+    uint32_t nrows;
+    uint64_t n_new;
+    Fr t;
+    const Fr* row_pads;  // [P]
+};
+
+__global__ void vv_fold_kernel(const __grid_constant__ VvFoldArgs A) {
+    const int j = blockIdx.y;
+    const Fr* in = A.in[j];
+    Fr* out = A.out[j];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < A.n_new; e += stride) {
+        uint32_t lo = 0, hi = A.nrows;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if ((uint64_t)A.off_new[mid] <= e) lo = mid; else hi = mid;
+        }
+        uint64_t i = e - A.off_new[lo];
+        uint64_t half_old = (A.off_old[lo + 1] - A.off_old[lo]) >> 1;
+        Fr v;
+        if (i < half_old) {
+            const Fr* src = in + A.off_old[lo] + 2 * i;
+            Fr e0 = src[0], e1 = src[1];
+            v = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+        } else {
+            v = A.row_pads[j];  // odd half re-padded with row_pad (vecvec.rs:432-436)
+        }
+        out[e] = v;
+    }
+}
+
+// bind_into_dense (vecvec_eq.rs:157-175): one value per bucket row, col_pad beyond the last row
+struct VvToDenseArgs {
+    const Fr* const* in;
+    Fr* const* out;
+    const uint32_t* off_old;
+    uint32_t nrows;
+    uint64_t n_out;
+    Fr t;
+    const Fr* row_pads;
+    const Fr* col_pads;
+};
+
+__global__ void vv_to_dense_kernel(const __grid_constant__ VvToDenseArgs A) {
+    const int j = blockIdx.y;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.n_out; r += (uint64_t)gridDim.x * blockDim.x) {
+        Fr v;
+        if (r < A.nrows) {
+            uint32_t len = A.off_old[r + 1] - A.off_old[r];
+            if (len == 0) {
+                v = A.row_pads[j];
+            } else {
+                const Fr* src = A.in[j] + A.off_old[r];
+                Fr e0 = src[0], e1 = src[1];
+                v = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+            }
+        } else {
+            v = A.col_pads[j];
+        }
+        A.out[j][r] = v;
+    }
+}
+
+__global__ void eq_halve_kernel(Fr* out, const Fr* in, uint64_t n_out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = fr_add(in[2 * i], in[2 * i + 1]);
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------
+static uint32_t log2_ceil_lasso(uint64_t n) {  // liblasso Math::log_2: exact for powers of two, ceil otherwise
+    if (n <= 1) return 0;
+    uint32_t l = 0;
+    while (((uint64_t)1 << l) < n) l++;
+    return l;
+}
+
+static gkr::FrH host_eq_sum(const gkr::FrH* pt, uint32_t n, uint64_t k) {  // src/utils.rs:265-291
+    using namespace gkr::frh;
+    if (k >= ((uint64_t)1 << n)) return ONE;
+    gkr::FrH mult = ONE, acc = ZERO;
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t bit = (uint32_t)(k >> (n - i - 1)) & 1u;
+        if (bit) {
+            gkr::FrH nm = mul(mult, pt[i]);
+            acc = add(acc, sub(mult, nm));
+            mult = nm;
+        } else {
+            mult = mul(mult, sub(ONE, pt[i]));
+        }
+    }
+    return acc;
+}
+
+static std::vector<Deg2Block> expand_blocks(const gkr::GateStack& gs) {
+    std::vector<Deg2Block> out;
+    int in_off = 0, out_off = 0;
+    for (size_t p = 0; p < gs.gate.size(); p++) {
+        int ni = 0, no = 0;
+        gkr::base_gate_io(gs.gate[p], &ni, &no);
+        for (int k = 0; k < gs.repeat[p]; k++) {
+            auto push = [&](int gate, std::initializer_list<int> idx, int ooff) {
+                Deg2Block b;
+                b.gate = gate;
+                int c = 0;
+                for (int x : idx) b.in_idx[c++] = in_off + x;
+                for (; c < 6; c++) b.in_idx[c] = 0;
+                b.out_off = out_off + ooff;
+                out.push_back(b);
+            };
+            switch (gs.gate[p]) {
+                case GKR_GATE_TRI_L1:  // three projective L1 on (a,c), (b,d), (c,d)   twisted_edwards_ops.rs:67-80
+                    push(GATE_PRJ_L1, {0, 1, 2, 6, 7, 8}, 0);
+                    push(GATE_PRJ_L1, {3, 4, 5, 9, 10, 11}, 4);
+                    push(GATE_PRJ_L1, {6, 7, 8, 9, 10, 11}, 8);
+                    break;
+                case GKR_GATE_AFF_L1_BITCHECK2:
+                    push(GATE_AFF_L1, {0, 1, 2, 3}, 0);
+                    push(GATE_BITCHECK, {4}, 3);
+                    push(GATE_BITCHECK, {5}, 4);
+                    break;
+                case GKR_GATE_AFF_L1: push(GATE_AFF_L1, {0, 1, 2, 3}, 0); break;
+                case GKR_GATE_AFF_L2: push(GATE_AFF_L2, {0, 1, 2}, 0); break;
+                case GKR_GATE_AFF_L3: push(GATE_AFF_L3, {0, 1, 2}, 0); break;
+                case GKR_GATE_PRJ_L1: push(GATE_PRJ_L1, {0, 1, 2, 3, 4, 5}, 0); break;
+                case GKR_GATE_PRJ_L2: push(GATE_PRJ_L2, {0, 1, 2, 3}, 0); break;
+                case GKR_GATE_PRJ_L3: push(GATE_PRJ_L3, {0, 1, 2, 3}, 0); break;
+                case GKR_GATE_BITCHECK: push(GATE_BITCHECK, {0}, 0); break;
+                case GKR_GATE_LOGUP_LAYER: push(GATE_LOGUP_LAYER, {0, 1, 2, 3}, 0); break;
+                case GKR_GATE_ADD_INVERSES: push(GATE_ADD_INVERSES, {0, 1}, 0); break;
+                default: break;
+            }
+            in_off += ni;
+            out_off += no;
+        }
+    }
+    return out;
+}
+
+// from12 (vecvec_eq.rs:197-216) with the inverse of eq0 supplied (batch-inverted once per object)
+static void from12(const gkr::FrH& p1, const gkr::FrH& p2, const gkr::FrH& eq1, const gkr::FrH& eq0_inv, const gkr::FrH& prev_claim, gkr::FrH* evals) {
+    using namespace gkr::frh;
+    gkr::FrH eq0 = sub(ONE, eq1);
+    gkr::FrH eq2 = sub(dbl(eq1), eq0);
+    gkr::FrH eq3 = sub(dbl(eq2), eq1);
+    gkr::FrH prod1 = mul(p1, eq1);
+    gkr::FrH prod0 = sub(prev_claim, prod1);
+    gkr::FrH p0 = mul(prod0, eq0_inv);
+    gkr::FrH p3 = add(sub(add(dbl(p2), p2), add(dbl(p1), p1)), p0);
+    evals[0] = prod0;
+    evals[1] = prod1;
+    evals[2] = mul(p2, eq2);
+    evals[3] = mul(p3, eq3);
+}
+
+// Shared machinery of the two Deg2 objects: P ragged (or single-row dense) tables, per-round offsets and eq levels.
+class Deg2SO : public gkr_so {
+   public:
+    bool is_vecvec = false;
+    gkr::GateStack gs;
+    int tail_gate = -1;  // public gate id for the dense tail after bind_into_dense
+    int P = 0;
+    uint32_t n_vars = 0, col = 0, row_logsize = 0, nrows = 0;
+    uint32_t n_sparse = 0;   // number of rounds run by the Deg2 kernels (dense object: all n_vars)
+    uint32_t round_idx = 0;
+    std::vector<gkr::FrH> point, gamma_pows, eq0_inv;  // eq0_inv[i] = 1 / (1 - point[i])
+    std::vector<gkr::FrH> row_pads, col_pads;
+    gkr::FrH claim_, multiplier, padG, colpadG, col_tail;
+    bool has_col_tail = false;
+    // per-round layout
+    std::vector<std::vector<uint32_t>> lens;  // [round][row] element counts (even)
+    std::vector<uint64_t> totals;             // [round] total elements
+    uint32_t* d_off = nullptr;                // [(n_sparse + 1) * (nrows + 1)] ELEMENT offsets per round
+    uint32_t* d_poff = nullptr;               // same in PAIRS
+    // eq levels
+    Fr* d_eq = nullptr;
+    std::vector<uint64_t> eq_off;  // offset of the level used in round b
+    Fr* d_rowcoef = nullptr;
+    Fr* d_pt_row = nullptr;  // device copy of the row variables (for the pad kernel)
+    uint32_t m_row = 0;      // number of row variables excluding the binding one at round 0
+    // data
+    Fr* slab[2] = {nullptr, nullptr};
+    const Fr** d_tabs[3] = {nullptr, nullptr, nullptr};  // device pointer arrays: [0] inputs, [1]/[2] ping-pong
+    std::vector<const Fr*> h_cur;
+    int cur_set = 0;
+    Deg2Block* d_blocks = nullptr;
+    int n_blocks = 0;
+    Fr* d_gammas = nullptr;
+    Fr* d_pads = nullptr;  // [2P]: row pads then col pads
+    bool cached = false, sums_pending = false;
+    gkr::FrH evals[4];
+    int slot = -1;
+    gkr_so* dense = nullptr;  // after bind_into_dense
+    std::vector<gkr_table*> dense_tables;
+
+    ~Deg2SO() override {
+        delete dense;
+        for (auto* t : dense_tables) gkr_table_free(t);
+        cudaStream_t s = ctx->stream;
+        if (d_off) cudaFreeAsync(d_off, s);
+        if (d_poff) cudaFreeAsync(d_poff, s);
+        if (d_eq) cudaFreeAsync(d_eq, s);
+        if (d_rowcoef) cudaFreeAsync(d_rowcoef, s);
+        if (d_pt_row) cudaFreeAsync(d_pt_row, s);
+        for (int i = 0; i < 2; i++) if (slab[i]) cudaFreeAsync(slab[i], s);
+        for (int i = 0; i < 3; i++) if (d_tabs[i]) cudaFreeAsync(d_tabs[i], s);
+        if (d_blocks) cudaFreeAsync(d_blocks, s);
+        if (d_gammas) cudaFreeAsync(d_gammas, s);
+        if (d_pads) cudaFreeAsync(d_pads, s);
+        if (slot >= 0) gkr_result_slot_release(ctx, slot);
+    }
+
+    Fr* res_dev() const { return ctx->result_dev + (size_t)slot * GKR_MAX_DEG; }
+    Fr* res_host() const { return ctx->result_host + (size_t)slot * GKR_MAX_DEG; }
+    uint32_t binding_idx() const { return n_vars - 1 - round_idx; }
+
+    int launch_eval() {
+        const uint64_t n_pairs = totals[round_idx] / 2;
+        Deg2EvalArgs a;
+        a.tabs = d_tabs[cur_set];
+        a.blocks = d_blocks;
+        a.gammas = d_gammas;
+        a.pair_off = is_vecvec ? d_poff + (size_t)round_idx * (nrows + 1) : nullptr;
+        a.nrows = nrows;
+        a.eq = d_eq + eq_off[round_idx];
+        a.rowcoef = d_rowcoef;
+        a.n_pairs = n_pairs;
+        a.partials = ctx->partials;
+        a.ticket = ctx->ticket;
+        a.result = res_dev();
+        if (n_pairs > 0) {
+            uint64_t want = (n_pairs + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
+            uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->num_sms * 3, GKR_MAX_BLOCKS / 2) / n_blocks);
+            dim3 grid((unsigned)std::max<uint64_t>(1, std::min(want, cap)), (unsigned)n_blocks);
+            deg2_eval_kernel<<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(a);
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+        } else {
+            GKR_CUDA_OK(ctx, cudaMemsetAsync(res_dev(), 0, 2 * sizeof(Fr), ctx->stream));
+        }
+        if (is_vecvec) {
+            Deg2PadArgs p;
+            p.pair_off = d_poff + (size_t)round_idx * (nrows + 1);
+            p.nrows = nrows;
+            p.rowcoef = d_rowcoef;
+            p.pt = d_pt_row;
+            p.n_pt = m_row - round_idx;  // row variables still in the eq table of this round
+            p.partials = ctx->partials;
+            p.ticket = ctx->ticket;
+            p.result = res_dev() + 2;
+            unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((nrows + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS, 256));
+            deg2_pad_kernel<<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(p);
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+        }
+        return GKR_OK;
+    }
+
+    int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
+        if (dense) return dense->unipoly(out, n_evals);
+        if (round_idx >= n_sparse) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly: the protocol has already ended");
+        if (cached) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly called twice in a round");  // dense_eq.rs:109-111
+        using namespace gkr::frh;
+        if (!sums_pending) {
+            int rc = launch_eval();
+            if (rc) return rc;
+        }
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        sums_pending = false;
+        const Fr* r = res_host();
+        gkr::FrH s1 = fr_to_host(r[0]), s2 = fr_to_host(r[1]);
+        gkr::FrH padterm;
+        if (is_vecvec) {
+            padterm = mul(padG, fr_to_host(r[2]));
+            if (has_col_tail) padterm = add(padterm, mul(colpadG, col_tail));
+        } else {
+            // trailing_sum = 1 - sum_{idx < len/2} eq[idx]   (dense_eq.rs:141); tables are full here, so it is zero
+            padterm = ZERO;
+        }
+        gkr::FrH total1 = mul(add(s1, padterm), multiplier);
+        gkr::FrH total2 = mul(add(s2, padterm), multiplier);
+        const uint32_t b = binding_idx();
+        from12(total1, total2, point[b], eq0_inv[b], claim_, evals);
+        cached = true;
+        for (int i = 0; i < 4; i++) out[i] = evals[i];
+        if (n_evals) *n_evals = 4;
+        return GKR_OK;
+    }
+
+    int fold_to_next(const gkr::FrH& t) {
+        const uint32_t b = round_idx;  // folding round b -> b + 1
+        int dst_set = (cur_set == 1) ? 2 : 1;
+        VvFoldArgs f;
+        f.in = d_tabs[cur_set];
+        f.out = (Fr* const*)d_tabs[dst_set];
+        f.off_old = d_off + (size_t)b * (nrows + 1);
+        f.off_new = d_off + (size_t)(b + 1) * (nrows + 1);
+        f.nrows = nrows;
+        f.n_new = totals[b + 1];
+        f.t = fr_from_host(t);
+        f.row_pads = d_pads;
+        if (f.n_new > 0) {
+            dim3 grid((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((f.n_new + 255) / 256, (uint64_t)ctx->num_sms * 4)), (unsigned)P);
+            vv_fold_kernel<<<grid, 256, 0, ctx->stream>>>(f);
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+        }
+        cur_set = dst_set;
+        return GKR_OK;
+    }
+
+    int bind(const gkr::FrH& t) override {
+        if (dense) return dense->bind(t);
+        if (round_idx >= n_sparse) return ctx->fail(GKR_ERR_PROTOCOL, "bind: the protocol has already ended");
+        if (!cached) return ctx->fail(GKR_ERR_PROTOCOL, "bind: should evaluate unipoly before binding");
+        if (!frh_canonical(t)) return ctx->fail(GKR_ERR_ARG, "bind: challenge is not canonical");
+        using namespace gkr::frh;
+        const uint32_t b = binding_idx();
+        gkr::FrH new_claim = interpolate_eval(evals, 4, t);
+        gkr::FrH new_mult = mul(multiplier, eq1(point[b], t));
+        if (is_vecvec && round_idx + 1 == n_sparse) return bind_into_dense(t, new_claim, new_mult);
+        int rc = fold_to_next(t);
+        if (rc) return rc;
+        multiplier = new_mult;
+        claim_ = new_claim;
+        cached = false;
+        round_idx++;
+        if (round_idx < n_sparse) {
+            rc = launch_eval();
+            if (rc) return rc;
+            sums_pending = true;
+        }
+        return GKR_OK;
+    }
+
+    int bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const gkr::FrH& new_mult);
+
+    int final_evals(gkr::FrH* out) override {
+        if (dense) return dense->final_evals(out);
+        if (is_vecvec) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: sparse stage has no final evals (vecvec_eq.rs:390-393)");
+        if (round_idx != n_sparse) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: can only be called after the last round");
+        std::vector<const Fr*> ptrs(P);
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(ptrs.data(), d_tabs[cur_set], sizeof(Fr*) * P, cudaMemcpyDeviceToHost, ctx->stream));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        std::vector<Fr> v(P);
+        for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&v[j], ptrs[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < P; j++) out[j] = fr_to_host(v[j]);
+        return GKR_OK;
+    }
+
+    gkr::FrH claim() const override { return dense ? dense->claim() : claim_; }
+    uint32_t degree() const override { return 3; }
+    uint32_t num_polys() const override { return dense ? dense->num_polys() : (uint32_t)P; }
+    uint32_t round() const override { return dense ? n_sparse + dense->round() : round_idx; }
+
+    // common construction once lens[0], data pointers, point, gammas are known
+    int setup(const std::vector<const Fr*>& inputs);
+};
+
+int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
+    using namespace gkr::frh;
+    cudaStream_t s = ctx->stream;
+    // batch inversion of (1 - point[i])
+    {
+        const size_t n = point.size();
+        eq0_inv.assign(n, ZERO);
+        std::vector<gkr::FrH> pref(n + 1, ONE);
+        for (size_t i = 0; i < n; i++) {
+            gkr::FrH e0 = sub(ONE, point[i]);
+            if (is_zero(e0)) return ctx->fail(GKR_ERR_ARG, "point coordinate equal to one: eq0 is not invertible (from12 would panic)");
+            pref[i + 1] = mul(pref[i], e0);
+        }
+        gkr::FrH inv_all = inverse(pref[n]);
+        for (size_t i = n; i-- > 0;) {
+            eq0_inv[i] = mul(inv_all, pref[i]);
+            inv_all = mul(inv_all, sub(ONE, point[i]));
+        }
+    }
+    // per-round row lengths and offsets
+    lens.resize(n_sparse + 1);
+    totals.assign(n_sparse + 1, 0);
+    for (uint32_t b = 0; b <= n_sparse; b++) {
+        if (b > 0) {
+            lens[b].resize(nrows);
+            for (uint32_t r = 0; r < nrows; r++) {
+                uint32_t h = lens[b - 1][r] / 2;
+                lens[b][r] = is_vecvec ? ((h + 1) & ~1u) : h;
+            }
+        }
+        uint64_t tot = 0;
+        for (uint32_t r = 0; r < nrows; r++) tot += lens[b][r];
+        if (tot >= ((uint64_t)1 << 32)) return ctx->fail(GKR_ERR_UNSUPPORTED, "more than 2^32 elements per polynomial");
+        totals[b] = tot;
+    }
+    std::vector<uint32_t> h_off((size_t)(n_sparse + 1) * (nrows + 1)), h_poff(h_off.size());
+    for (uint32_t b = 0; b <= n_sparse; b++) {
+        uint32_t acc = 0;
+        for (uint32_t r = 0; r <= nrows; r++) {
+            h_off[(size_t)b * (nrows + 1) + r] = acc;
+            h_poff[(size_t)b * (nrows + 1) + r] = acc / 2;
+            if (r < nrows) acc += lens[b][r];
+        }
+    }
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_off, sizeof(uint32_t) * h_off.size(), s));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_poff, sizeof(uint32_t) * h_off.size(), s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(uint32_t) * h_off.size(), cudaMemcpyHostToDevice, s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_poff, h_poff.data(), sizeof(uint32_t) * h_off.size(), cudaMemcpyHostToDevice, s));
+
+    // gate program, gammas, pads
+    std::vector<Deg2Block> blocks = expand_blocks(gs);
+    n_blocks = (int)blocks.size();
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_blocks, sizeof(Deg2Block) * blocks.size(), s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(Deg2Block) * blocks.size(), cudaMemcpyHostToDevice, s));
+    std::vector<Fr> g(gs.n_outs);
+    for (int i = 0; i < gs.n_outs; i++) g[i] = fr_from_host(gamma_pows[i]);
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_gammas, sizeof(Fr) * g.size(), s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_gammas, g.data(), sizeof(Fr) * g.size(), cudaMemcpyHostToDevice, s));
+    std::vector<Fr> pads(2 * P);
+    for (int j = 0; j < P; j++) {
+        pads[j] = fr_from_host(row_pads[j]);
+        pads[P + j] = fr_from_host(col_pads[j]);
+    }
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_pads, sizeof(Fr) * pads.size(), s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_pads, pads.data(), sizeof(Fr) * pads.size(), cudaMemcpyHostToDevice, s));
+    // pad_results / col_pad_results folded with gamma (vecvec_eq.rs:309-315, 372-378)
+    {
+        std::vector<gkr::FrH> o(gs.n_outs);
+        gs.eval(row_pads.data(), o.data());
+        padG = o[0];
+        for (int i = 1; i < gs.n_outs; i++) padG = add(padG, mul(o[i], gamma_pows[i]));
+        gs.eval(col_pads.data(), o.data());
+        colpadG = o[0];
+        for (int i = 1; i < gs.n_outs; i++) colpadG = add(colpadG, mul(o[i], gamma_pows[i]));
+    }
+
+    // eq levels.  Row variables: point[col .. n_vars-1); the last one (binding variable of round 0) is excluded.
+    m_row = (n_vars - col) - 1;  // == row_logsize - 1
+    uint64_t max_len = 0;
+    for (uint32_t r = 0; r < nrows; r++) max_len = std::max<uint64_t>(max_len, lens[0][r]);
+    uint32_t max_seg_log = log2_ceil_lasso(max_len);
+    if (!is_vecvec) max_seg_log = n_vars;  // dense tables span all variables
+    // number of leading row variables over which every row is padding (EQPolyPointParts::padded_vars_range)
+    uint32_t seg_idx = n_vars - std::min(max_seg_log, n_vars);
+    uint32_t pad_lo = col, pad_hi = std::min(seg_idx, n_vars - 1);
+    uint32_t npad = pad_hi > pad_lo ? pad_hi - pad_lo : 0;
+    const gkr::FrH* pt_row = point.data() + col;
+    std::vector<gkr::FrH> prefix(m_row + 1, ONE);  // prefix[i] = prod_{k<i} (1 - pt_row[k])
+    for (uint32_t i = 0; i < m_row; i++) prefix[i + 1] = mul(prefix[i], sub(ONE, pt_row[i]));
+    eq_off.assign(n_sparse + 1, 0);
+    uint64_t eq_total = 0;
+    std::vector<uint64_t> lvl_size(n_sparse + 1, 1);
+    for (uint32_t b = 0; b < n_sparse; b++) {
+        uint32_t lvl = m_row >= b ? m_row - b : 0;  // number of variables in this round's eq table
+        lvl_size[b] = lvl > npad ? ((uint64_t)1 << (lvl - npad)) : 1;
+        eq_off[b] = eq_total;
+        eq_total += lvl_size[b];
+    }
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_eq, sizeof(Fr) * std::max<uint64_t>(eq_total, 1), s));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_pt_row, sizeof(Fr) * std::max<uint32_t>(m_row, 1), s));
+    {
+        std::vector<Fr> p(std::max<uint32_t>(m_row, 1));
+        for (uint32_t i = 0; i < m_row; i++) p[i] = fr_from_host(pt_row[i]);
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_pt_row, p.data(), sizeof(Fr) * p.size(), cudaMemcpyHostToDevice, s));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));  // `p`, `pads`, `g`, `blocks`, offsets are stack/heap temporaries
+    }
+    for (uint32_t b = 0; b < n_sparse; b++) {
+        uint32_t lvl = m_row >= b ? m_row - b : 0;
+        if (lvl <= npad) {
+            Fr v = fr_from_host(prefix[lvl]);
+            GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_eq + eq_off[b], &v, sizeof(Fr), cudaMemcpyHostToDevice, s));
+            GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
+        } else if (b == 0) {
+            int rc = gkr_eq_build_device(ctx, d_pt_row + npad, lvl - npad, fr_from_host(prefix[npad]), d_eq + eq_off[0]);
+            if (rc) return rc;
+        } else {
+            uint64_t n_out = lvl_size[b];
+            unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_out + 255) / 256, (uint64_t)ctx->num_sms * 4));
+            eq_halve_kernel<<<grid, 256, 0, s>>>(d_eq + eq_off[b], d_eq + eq_off[b - 1], n_out);
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+        }
+    }
+    if (is_vecvec) {
+        GKR_CUDA_OK(ctx, cudaMallocAsync(&d_rowcoef, sizeof(Fr) << col, s));
+        Fr* d_pt_col = nullptr;
+        GKR_CUDA_OK(ctx, cudaMallocAsync(&d_pt_col, sizeof(Fr) * std::max<uint32_t>(col, 1), s));
+        std::vector<Fr> p(std::max<uint32_t>(col, 1));
+        for (uint32_t i = 0; i < col; i++) p[i] = fr_from_host(point[i]);
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_pt_col, p.data(), sizeof(Fr) * p.size(), cudaMemcpyHostToDevice, s));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
+        int rc = gkr_eq_build_device(ctx, d_pt_col, col, fr_from_host(ONE), d_rowcoef);
+        cudaFreeAsync(d_pt_col, s);
+        if (rc) return rc;
+        has_col_tail = nrows < ((uint64_t)1 << col);
+        col_tail = sub(ONE, host_eq_sum(point.data(), col, nrows));  // row_eq_coefs_tail_sums[row_count]
+    }
+
+    // data: pointer arrays + ping-pong slabs sized for round 1 and round 2
+    for (int i = 0; i < 3; i++) GKR_CUDA_OK(ctx, cudaMallocAsync(&d_tabs[i], sizeof(Fr*) * P, s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[0], inputs.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
+    uint64_t sz1 = n_sparse >= 1 ? totals[1] : 0, sz2 = n_sparse >= 2 ? totals[2] : 0;
+    std::vector<const Fr*> p1(P), p2(P);
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[0], sizeof(Fr) * std::max<uint64_t>(sz1 * P, 1), s));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[1], sizeof(Fr) * std::max<uint64_t>(sz2 * P, 1), s));
+    for (int j = 0; j < P; j++) {
+        p1[j] = slab[0] + (size_t)j * sz1;
+        p2[j] = slab[1] + (size_t)j * sz2;
+    }
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[1], p1.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[2], p2.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
+    cur_set = 0;
+    multiplier = ONE;
+    slot = gkr_result_slot_acquire(ctx);
+    if (slot < 0) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many live sumcheck objects");
+    return GKR_OK;
+}
+
+int Deg2SO::bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const gkr::FrH& new_mult) {
+    using namespace gkr::frh;
+    cudaStream_t s = ctx->stream;
+    const uint64_t n_out = (uint64_t)1 << col;
+    dense_tables.assign(P + 1, nullptr);
+    std::vector<Fr*> outs(P);
+    for (int j = 0; j < P; j++) {
+        int rc = gkr_table_alloc(ctx, n_out, &dense_tables[j]);
+        if (rc) return rc;
+        outs[j] = dense_tables[j]->d;
+    }
+    Fr** d_outs = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_outs, sizeof(Fr*) * P, s));
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_outs, outs.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
+    VvToDenseArgs a;
+    a.in = d_tabs[cur_set];
+    a.out = d_outs;
+    a.off_old = d_off + (size_t)round_idx * (nrows + 1);
+    a.nrows = nrows;
+    a.n_out = n_out;
+    a.t = fr_from_host(t);
+    a.row_pads = d_pads;
+    a.col_pads = d_pads + P;
+    dim3 grid((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_out + 255) / 256, (uint64_t)ctx->num_sms * 4)), (unsigned)P);
+    vv_to_dense_kernel<<<grid, 256, 0, s>>>(a);
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));  // `outs` is a host temporary
+    cudaFreeAsync(d_outs, s);
+    // eq table over the vertical variables scaled by the multiplier of all bound variables (vecvec_eq.rs:176-179)
+    std::vector<uint64_t> pt(4 * std::max<uint32_t>(col, 1));
+    for (uint32_t i = 0; i < col; i++) frh_to_limbs(point[i], pt.data() + 4 * i);
+    uint64_t m[4];
+    frh_to_limbs(new_mult, m);
+    int rc = gkr_eq_table(ctx, pt.data(), col, m, &dense_tables[P]);
+    if (rc) return rc;
+    // DenseSumcheckObjectSO over EqWrapper(GammaWrapper(func, gamma)) (vecvec_eq.rs:182-189)
+    std::vector<gkr::FrH> consts(gamma_pows.begin(), gamma_pows.end());
+    rc = gkr_make_dense_so(ctx, GKR_SO_EQ_GAMMA, tail_gate, 0, consts.data(), (uint32_t)std::min<size_t>(consts.size(), GKR_MAX_GATE_CONSTS),
+                           dense_tables.data(), (uint32_t)P + 1, col, new_claim, &dense);
+    if (rc) return rc;
+    multiplier = new_mult;
+    claim_ = new_claim;
+    cached = false;
+    round_idx++;
+    return GKR_OK;
+}
+
+static int load_stack(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repeat, uint32_t n_parts, gkr::GateStack* gs) {
+    if (!part_gate || !part_repeat || !gs->init(part_gate, part_repeat, n_parts)) return ctx->fail(GKR_ERR_ARG, "invalid gate stack");
+    return GKR_OK;
+}
+
+// DenseDeg2SumcheckObjectSO::new   dense_eq.rs:75-95
+extern "C" int gkr_so_create_deg2_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repeat, uint32_t n_parts,
+                                        gkr_table* const* tables, uint32_t n_polys, const uint64_t* gamma_pows,
+                                        const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, gkr_so** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!tables || !gamma_pows || !claim || !point || !out) return ctx->fail(GKR_ERR_ARG, "null argument");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    Deg2SO* so = new Deg2SO();
+    so->ctx = ctx;
+    int rc = load_stack(ctx, part_gate, part_repeat, n_parts, &so->gs);
+    if (rc) { delete so; return rc; }
+    if ((int)n_polys != so->gs.n_ins) { delete so; return ctx->fail(GKR_ERR_ARG, "number of tables != f.n_ins()"); }
+    if (num_vars == 0 || num_vars >= 32) { delete so; return ctx->fail(GKR_ERR_ARG, "bad num_vars"); }
+    for (uint32_t j = 0; j < n_polys; j++) {
+        if (!tables[j] || tables[j]->n != ((uint64_t)1 << num_vars)) {
+            delete so;
+            // the reference accepts shorter tables only in its non-`parallel` build (dense.rs:39-61); the README build
+            // (`--features parallel`) indexes out of bounds on them, so full tables are required here
+            return ctx->fail(GKR_ERR_UNSUPPORTED, "Deg2 dense object: every table must have 1 << num_vars entries");
+        }
+    }
+    so->is_vecvec = false;
+    so->P = (int)n_polys;
+    so->n_vars = num_vars;
+    so->col = 0;
+    so->row_logsize = num_vars;
+    so->nrows = 1;
+    so->n_sparse = num_vars;
+    so->point.resize(num_vars);
+    for (uint32_t i = 0; i < num_vars; i++) so->point[i] = frh_from_limbs(point + 4 * i);
+    so->gamma_pows.resize(so->gs.n_outs);
+    for (int i = 0; i < so->gs.n_outs; i++) so->gamma_pows[i] = frh_from_limbs(gamma_pows + 4 * i);
+    so->claim_ = frh_from_limbs(claim);
+    so->row_pads.assign(n_polys, gkr::frh::ZERO);
+    so->col_pads.assign(n_polys, gkr::frh::ZERO);
+    so->lens.resize(1);
+    so->lens[0].assign(1, (uint32_t)((uint64_t)1 << num_vars));
+    std::vector<const Fr*> in(n_polys);
+    for (uint32_t j = 0; j < n_polys; j++) in[j] = tables[j]->d;
+    rc = so->setup(in);
+    if (rc) { delete so; return rc; }
+    *out = so;
+    return GKR_OK;
+}
+
+// VecVecDeg2SumcheckObjectSO::new   vecvec_eq.rs:94-118
+extern "C" int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
+                                         const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, uint32_t col_logsize,
+                                         gkr_so** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!polys || !gamma_pows || !claim || !point || !out) return ctx->fail(GKR_ERR_ARG, "null argument");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    Deg2SO* so = new Deg2SO();
+    so->ctx = ctx;
+    uint32_t one = 1;
+    int rc = load_stack(ctx, &gate, &one, 1, &so->gs);
+    if (rc) { delete so; return rc; }
+    if ((int)n_polys != so->gs.n_ins) { delete so; return ctx->fail(GKR_ERR_ARG, "number of polynomials != f.n_ins()"); }
+    const gkr_vecvec* p0 = polys[0];
+    if (!p0 || p0->col_logsize != col_logsize || p0->row_logsize + col_logsize != num_vars || p0->row_logsize == 0) {
+        delete so;
+        return ctx->fail(GKR_ERR_ARG, "row_logsize + col_logsize must equal the point length");
+    }
+    for (uint32_t j = 0; j < n_polys; j++) {
+        if (!polys[j] || polys[j]->row_len != p0->row_len || polys[j]->row_logsize != p0->row_logsize || polys[j]->col_logsize != col_logsize) {
+            delete so;
+            return ctx->fail(GKR_ERR_ARG, "all polynomials of a bundle must share the row structure");
+        }
+    }
+    if (p0->row_len.empty()) { delete so; return ctx->fail(GKR_ERR_ARG, "empty polynomial (reference: max() of empty iterator panics)"); }
+    so->is_vecvec = true;
+    so->tail_gate = gate;
+    so->P = (int)n_polys;
+    so->n_vars = num_vars;
+    so->col = col_logsize;
+    so->row_logsize = p0->row_logsize;
+    so->nrows = (uint32_t)p0->row_len.size();
+    so->n_sparse = p0->row_logsize;
+    so->point.resize(num_vars);
+    for (uint32_t i = 0; i < num_vars; i++) so->point[i] = frh_from_limbs(point + 4 * i);
+    so->gamma_pows.resize(std::max(so->gs.n_outs, 2));
+    for (size_t i = 0; i < so->gamma_pows.size(); i++) so->gamma_pows[i] = frh_from_limbs(gamma_pows + 4 * i);
+    so->claim_ = frh_from_limbs(claim);
+    so->row_pads.resize(n_polys);
+    so->col_pads.resize(n_polys);
+    std::vector<const Fr*> in(n_polys);
+    for (uint32_t j = 0; j < n_polys; j++) {
+        so->row_pads[j] = polys[j]->row_pad;
+        so->col_pads[j] = polys[j]->col_pad;
+        in[j] = polys[j]->d;
+    }
+    so->lens.resize(1);
+    so->lens[0] = p0->row_len;
+    rc = so->setup(in);
+    if (rc) { delete so; return rc; }
+    *out = so;
+    return GKR_OK;
+}
+
+// ---- VecVecPolynomial handles ------------------------------------------------------------------------------
+// VecVecPolynomial::new (vecvec.rs:179-189): rows of odd length are padded with row_pad
+extern "C" int gkr_vecvec_upload(gkr_ctx* ctx, const uint64_t* flat, const uint32_t* row_len, uint32_t n_rows, const uint64_t row_pad[4],
+                                 const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!out || !row_pad || !col_pad || (n_rows && !row_len)) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (col_logsize >= 32 || row_logsize >= 32 || n_rows > ((uint64_t)1 << col_logsize)) return ctx->fail(GKR_ERR_ARG, "too many rows for col_logsize");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    gkr_vecvec* v = new gkr_vecvec();
+    v->ctx = ctx;
+    v->row_pad = frh_from_limbs(row_pad);
+    v->col_pad = frh_from_limbs(col_pad);
+    v->row_logsize = row_logsize;
+    v->col_logsize = col_logsize;
+    v->row_len.resize(n_rows);
+    uint64_t total = 0, src_total = 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        if (row_len[r] > ((uint64_t)1 << row_logsize)) { delete v; return ctx->fail(GKR_ERR_ARG, "row longer than 1 << row_logsize"); }
+        v->row_len[r] = (row_len[r] + 1) & ~1u;
+        total += v->row_len[r];
+        src_total += row_len[r];
+    }
+    v->total = total;
+    std::vector<uint64_t> padded((size_t)4 * std::max<uint64_t>(total, 1));
+    uint64_t so = 0, dof = 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        if (row_len[r]) std::memcpy(padded.data() + 4 * dof, flat + 4 * so, (size_t)32 * row_len[r]);
+        if (row_len[r] & 1) std::memcpy(padded.data() + 4 * (dof + row_len[r]), row_pad, 32);
+        so += row_len[r];
+        dof += v->row_len[r];
+    }
+    cudaError_t e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), ctx->stream);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(v->d, padded.data(), sizeof(Fr) * total, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { delete v; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = v;
+    return GKR_OK;
+}
+
+extern "C" uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v) { return v ? (uint32_t)v->row_len.size() : 0; }
+extern "C" uint64_t gkr_vecvec_total_len(const gkr_vecvec* v) { return v ? v->total : 0; }
+
+extern "C" int gkr_vecvec_download(gkr_ctx* ctx, const gkr_vecvec* v, uint64_t* flat_out, uint32_t* row_len_out, uint64_t row_pad[4],
+                                   uint64_t col_pad[4], uint32_t* row_logsize, uint32_t* col_logsize) {
+    if (!ctx || !v) return GKR_ERR_ARG;
+    if (flat_out && v->total) GKR_CUDA_OK(ctx, cudaMemcpyAsync(flat_out, v->d, sizeof(Fr) * v->total, cudaMemcpyDeviceToHost, ctx->stream));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (row_len_out) std::memcpy(row_len_out, v->row_len.data(), sizeof(uint32_t) * v->row_len.size());
+    if (row_pad) frh_to_limbs(v->row_pad, row_pad);
+    if (col_pad) frh_to_limbs(v->col_pad, col_pad);
+    if (row_logsize) *row_logsize = v->row_logsize;
+    if (col_logsize) *col_logsize = v->col_logsize;
+    return GKR_OK;
+}
+
+extern "C" void gkr_vecvec_free(gkr_vecvec* v) {
+    if (!v) return;
+    if (v->d) cudaFreeAsync(v->d, v->ctx->stream);
+    delete v;
+}

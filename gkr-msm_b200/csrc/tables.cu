@@ -54,6 +54,14 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e);
     ctx->num_sms = prop.multiProcessorCount;
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
+    {
+        // stream-ordered allocator with an unbounded release threshold: after warm-up a table / ping-pong slab
+        // allocation is a pointer bump, not a driver call (a proof creates ~10^3 short-lived objects)
+        cudaMemPool_t pool;
+        if ((e = cudaDeviceGetDefaultMemPool(&pool, device)) != cudaSuccess) return bail(e);
+        uint64_t thr = UINT64_MAX;
+        if ((e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr)) != cudaSuccess) return bail(e);
+    }
     if ((e = cudaMalloc(&ctx->partials, sizeof(Fr) * GKR_MAX_BLOCKS * GKR_MAX_DEG)) != cudaSuccess) return bail(e);
     if ((e = cudaMalloc(&ctx->ticket, sizeof(unsigned int))) != cudaSuccess) return bail(e);
     if ((e = cudaMemset(ctx->ticket, 0, sizeof(unsigned int))) != cudaSuccess) return bail(e);
@@ -106,10 +114,10 @@ extern "C" int gkr_table_alloc(gkr_ctx* ctx, uint64_t n, gkr_table** out) {
     gkr_table* t = new gkr_table();
     t->ctx = ctx;
     t->n = n;
-    cudaError_t e = cudaMalloc(&t->d, sizeof(Fr) * std::max<uint64_t>(n, 1));
+    cudaError_t e = cudaMallocAsync(&t->d, sizeof(Fr) * std::max<uint64_t>(n, 1), ctx->stream);
     if (e != cudaSuccess) {
         delete t;
-        return ctx->fail(GKR_ERR_CUDA, std::string("cudaMalloc(table): ") + cudaGetErrorString(e));
+        return ctx->fail(GKR_ERR_CUDA, std::string("cudaMallocAsync(table): ") + cudaGetErrorString(e));
     }
     *out = t;
     return GKR_OK;
@@ -135,10 +143,7 @@ extern "C" void* gkr_table_device_ptr(gkr_table* t) { return t ? (void*)t->d : n
 
 extern "C" void gkr_table_free(gkr_table* t) {
     if (!t) return;
-    if (t->owned && t->d) {
-        cudaStreamSynchronize(t->ctx->stream);
-        cudaFree(t->d);
-    }
+    if (t->owned && t->d) cudaFreeAsync(t->d, t->ctx->stream);  // stream-ordered: queued kernels finish first
     delete t;
 }
 
@@ -263,6 +268,8 @@ static int eq_build(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult,
     cudaFreeAsync(lo, ctx->stream);
     return rc;
 }
+
+int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out) { return eq_build(ctx, d_point, n, mult, d_out); }
 
 extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, const uint64_t mult[4], gkr_table** out) {
     if (!ctx || !out || (!point && n) || !mult) return GKR_ERR_ARG;

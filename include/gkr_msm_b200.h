@@ -129,6 +129,34 @@ uint32_t gkr_so_num_polys(const gkr_so* so);
 uint32_t gkr_so_round(const gkr_so* so);
 void gkr_so_destroy(gkr_so* so);
 
+/* ---- VecVecPolynomial<F> resident in HBM (CSR)   src/cleanup/polys/vecvec.rs:149-206 -------------------
+ * gkr_vecvec_upload == VecVecPolynomial::new: `flat` holds the rows back to back (row r has row_len[r]
+ * elements); rows of odd length get one row_pad appended (vecvec.rs:183-185). */
+typedef struct gkr_vecvec gkr_vecvec;
+int gkr_vecvec_upload(gkr_ctx* ctx, const uint64_t* flat, const uint32_t* row_len, uint32_t n_rows, const uint64_t row_pad[4],
+                      const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out);
+uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v);
+uint64_t gkr_vecvec_total_len(const gkr_vecvec* v); /* elements after even-padding */
+int gkr_vecvec_download(gkr_ctx* ctx, const gkr_vecvec* v, uint64_t* flat_out, uint32_t* row_len_out, uint64_t row_pad[4],
+                        uint64_t col_pad[4], uint32_t* row_logsize, uint32_t* col_logsize);
+void gkr_vecvec_free(gkr_vecvec* v);
+
+/* DenseDeg2SumcheckObjectSO::new(polys, func, gamma_pows, claim, point)  sumchecks/dense_eq.rs:75-95
+ * The gate is a stack Stacked(Repeated(g_0, r_0), Repeated(g_1, r_1), ..) of base gates (algfn.rs:187-259),
+ * e.g. triangle layer k: {TRI_L1 x1, PRJ_L1 xk} (triangle_add.rs:199-231).  gamma_pows: n_outs elements
+ * = make_gamma_pows(gamma, n_outs) (src/utils.rs:126-135).  unipoly() returns 4 evaluations (nodes 0..3, the
+ * output of UnivarFormat::from12, vecvec_eq.rs:197-216); a second unipoly() in a round is an error like the
+ * reference's panic (dense_eq.rs:109-111). */
+int gkr_so_create_deg2_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repeat, uint32_t n_parts,
+                             gkr_table* const* tables, uint32_t n_polys, const uint64_t* gamma_pows, const uint64_t claim[4],
+                             const uint64_t* point, uint32_t num_vars, gkr_so** out);
+/* VecVecDeg2SumcheckObjectSO::new(polys, func, gamma_pows, claim, point, col_logsize)  sumchecks/vecvec_eq.rs:94-118
+ * Sparse stage over the row variables, then bind_into_dense (:157-190) hands over to a DenseSumcheckObjectSO on
+ * EqWrapper(GammaWrapper(func, gamma)); final_evals() then has n_polys + 1 entries (the eq table last, :443-445).
+ * gamma_pows: max(n_outs, 2) elements. */
+int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
+                              const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, uint32_t col_logsize, gkr_so** out);
+
 /* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
  * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */
 int gkr_transcript_new(const uint8_t* label, size_t label_len, gkr_transcript** out);
