@@ -502,3 +502,49 @@ def sumcheck_prove_sharded(transcript: Transcript, so: SumcheckObject, exchange,
                                                so_kind, gate, gate_param, _ptr(c), c.shape[0], _ptr(gc), _ptr(claim), _ptr(point), _ptr(fe))
     so.ctx.check(rc)
     return claim, point[: local_rounds + g_], fe
+
+
+# ---- witness maps (trait MapSplit) -------------------------------------------------------------------------
+def _parts_arrays(parts):
+    pg = np.array([p[0] for p in parts], dtype=np.int32)
+    pr = np.array([p[1] for p in parts], dtype=np.uint32)
+    return pg, pr
+
+
+def _ctx_map_dense(self, parts, tables, split=None, bundle_size=1):
+    """Vec::algfn_map (split=None) / Vec::algfn_map_split (split=("LO"|"HI", var_idx)).  Returns a list of Tables."""
+    lib = self.lib
+    if not hasattr(lib.gkr_map_dense, "_sig"):
+        lib.gkr_map_dense.restype = C.c_int
+        lib.gkr_map_dense.argtypes = [_vp, _vp, _vp, C.c_uint32, C.POINTER(_vp), C.c_uint32, C.c_int, C.c_uint32, C.c_uint32,
+                                      C.POINTER(_vp), C.POINTER(C.c_uint32)]
+        lib.gkr_map_dense._sig = True
+    pg, pr = _parts_arrays(parts)
+    arr = (_vp * len(tables))(*[t.h for t in tables])
+    out = (_vp * 256)()
+    n = C.c_uint32(0)
+    kind, var = (-1, 0) if split is None else ({"LO": 0, "HI": 1}[split[0]], split[1])
+    self.check(lib.gkr_map_dense(self.h, _ptr(pg), _ptr(pr), len(parts), arr, len(tables), kind, var, bundle_size, out, C.byref(n)))
+    return [Table(self, _vp(out[i])) for i in range(n.value)]
+
+
+def _ctx_map_vecvec(self, parts, polys, mode=0, bundle_size=1):
+    """mode 0: vecvec_map, 1: vecvec_map_split (LO(0)), 2: vecvec_map_split_to_dense (returns Tables)."""
+    lib = self.lib
+    if not hasattr(lib.gkr_map_vecvec, "_sig"):
+        lib.gkr_map_vecvec.restype = C.c_int
+        lib.gkr_map_vecvec.argtypes = [_vp, _vp, _vp, C.c_uint32, C.POINTER(_vp), C.c_uint32, C.c_int, C.c_uint32, C.POINTER(_vp),
+                                       C.POINTER(C.c_uint32)]
+        lib.gkr_map_vecvec._sig = True
+    pg, pr = _parts_arrays(parts)
+    arr = (_vp * len(polys))(*[p.h for p in polys])
+    out = (_vp * 256)()
+    n = C.c_uint32(0)
+    self.check(lib.gkr_map_vecvec(self.h, _ptr(pg), _ptr(pr), len(parts), arr, len(polys), mode, bundle_size, out, C.byref(n)))
+    if mode == 2:
+        return [Table(self, _vp(out[i])) for i in range(n.value)]
+    return [VecVec(self, _vp(out[i])) for i in range(n.value)]
+
+
+Context.map_dense = _ctx_map_dense
+Context.map_vecvec = _ctx_map_vecvec

@@ -57,6 +57,16 @@ struct gkr_table {
     bool owned = true;
 };
 
+// VecVecPolynomial<F> (src/cleanup/polys/vecvec.rs:149-160) in CSR form: rows back to back, every row even-length
+struct gkr_vecvec {
+    gkr_ctx* ctx = nullptr;
+    Fr* d = nullptr;
+    uint64_t total = 0;
+    std::vector<uint32_t> row_len;  // host copy (even lengths)
+    gkr::FrH row_pad, col_pad;
+    uint32_t row_logsize = 0, col_logsize = 0;
+};
+
 // kernel ids reported by gkr_ctx_timing_read
 enum GkrKernelId { GKR_K_DENSE_EVAL = 0, GKR_K_DENSE_FOLD_EVAL = 1, GKR_K_DENSE_SUM = 2, GKR_K_DENSE_FOLD = 3 };
 

@@ -24,15 +24,6 @@ int gkr_result_slot_acquire(gkr_ctx* ctx);
 void gkr_result_slot_release(gkr_ctx* ctx, int slot);
 int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out);
 
-struct gkr_vecvec {
-    gkr_ctx* ctx = nullptr;
-    Fr* d = nullptr;
-    uint64_t total = 0;
-    std::vector<uint32_t> row_len;  // host copy (even lengths)
-    gkr::FrH row_pad, col_pad;
-    uint32_t row_logsize = 0, col_logsize = 0;
-};
-
 struct Deg2Block {
     int gate;
     int in_idx[6];
@@ -520,7 +511,8 @@ class Deg2SO : public gkr_so {
 
     gkr::FrH claim() const override { return dense ? dense->claim() : claim_; }
     uint32_t degree() const override { return 3; }
-    uint32_t num_polys() const override { return dense ? dense->num_polys() : (uint32_t)P; }
+    // number of final evaluations: the VecVec object ends on the dense tail, which carries the eq table as well
+    uint32_t num_polys() const override { return dense ? dense->num_polys() : (uint32_t)(is_vecvec ? P + 1 : P); }
     uint32_t round() const override { return dense ? n_sparse + dense->round() : round_idx; }
 
     // common construction once lens[0], data pointers, point, gammas are known

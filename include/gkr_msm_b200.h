@@ -157,6 +157,19 @@ int gkr_so_create_deg2_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t*
 int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
                               const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, uint32_t col_logsize, gkr_so** out);
 
+/* ---- trait MapSplit / AlgFnUtils: witness generation  (src/cleanup/polys/common.rs:23-35) ------------------
+ * The gate is a stack of repeated base gates as above; GKR_GATE_ID with repeat n is IdAlgFn(n).
+ * gkr_map_dense: Vec::algfn_map (dense.rs:141-184) when split_kind < 0, else Vec::algfn_map_split
+ *   (dense.rs:115-139) with split_kind 0 = SplitIdx::LO(var_idx), 1 = SplitIdx::HI(var_idx); AlgFnUtils::map_split_hi
+ *   (algfn.rs:82-89) is split_kind 1, var_idx 0, bundle_size = n_outs.  `out` receives n_outs (2*n_outs when
+ *   splitting) fresh tables in the reference's output order (chunks of bundle_size interleaved left/right).
+ * gkr_map_vecvec: mode 0 = vecvec_map (vecvec.rs:480-540) -> gkr_vecvec*; mode 1 = vecvec_map_split at LO(0)
+ *   (:542-606) -> gkr_vecvec* with row_logsize - 1; mode 2 = vecvec_map_split_to_dense (:608-654) -> gkr_table*. */
+int gkr_map_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repeat, uint32_t n_parts, gkr_table* const* in,
+                  uint32_t n_in, int split_kind, uint32_t var_idx, uint32_t bundle_size, gkr_table** out, uint32_t* n_out);
+int gkr_map_vecvec(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repeat, uint32_t n_parts, gkr_vecvec* const* in,
+                   uint32_t n_in, int mode, uint32_t bundle_size, void** out, uint32_t* n_out);
+
 /* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
  * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */
 int gkr_transcript_new(const uint8_t* label, size_t label_len, gkr_transcript** out);
