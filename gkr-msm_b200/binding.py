@@ -548,3 +548,44 @@ def _ctx_map_vecvec(self, parts, polys, mode=0, bundle_size=1):
 
 Context.map_dense = _ctx_map_dense
 Context.map_vecvec = _ctx_map_vecvec
+
+
+# ---- commitments ------------------------------------------------------------------------------------------
+class Srs:
+    """gkr_srs: G1 bases resident in HBM (affine (n, 12) or Jacobian (n, 18) uint64 Montgomery limbs)."""
+
+    def __init__(self, ctx: Context, points, projective: bool = False):
+        lib = ctx.lib
+        if not hasattr(lib.gkr_srs_upload, "_sig"):
+            lib.gkr_srs_upload.restype = C.c_int
+            lib.gkr_srs_upload.argtypes = [_vp, _vp, C.c_uint64, C.c_int, C.POINTER(_vp)]
+            lib.gkr_srs_len.restype = C.c_uint64
+            lib.gkr_srs_len.argtypes = [_vp]
+            lib.gkr_srs_free.restype = None
+            lib.gkr_srs_free.argtypes = [_vp]
+            lib.gkr_msm_g1.restype = C.c_int
+            lib.gkr_msm_g1.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]
+            lib.gkr_srs_upload._sig = True
+        a = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 18 if projective else 12)
+        h = _vp()
+        ctx.check(lib.gkr_srs_upload(ctx.h, _ptr(a), a.shape[0], 1 if projective else 0, C.byref(h)))
+        self.ctx, self.h, self.n = ctx, h, a.shape[0]
+
+    def msm(self, scalars: "Table", n: int = None, first: int = 0) -> np.ndarray:
+        """KzgProvingKey::commit: returns the affine result as (12,) uint64 (x | y), zeros for infinity."""
+        n = len(scalars) if n is None else n
+        out = np.zeros(12, np.uint64)
+        self.ctx.check(self.ctx.lib.gkr_msm_g1(self.ctx.h, self.h, first, scalars.h, n, _ptr(out)))
+        return out
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.gkr_srs_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass

@@ -1,0 +1,385 @@
+// Multi-scalar multiplication over BLS12-381 G1 (the multilinear-commitment MSM).
+//   KzgProvingKey::commit / open     src/commitments/kzg.rs:123-133  (-> liblasso::msm::VariableBaseMSM::msm)
+//   msm_nonaff                       src/msm_nonaffine.rs:34-38       (projective bases)
+// The MSM value is a unique group element, so any algorithm that returns its affine coordinates in canonical
+// Montgomery form is bit-exact with the reference.  Bucket method, c-bit unsigned windows:
+//   1. digits:      scalars leave Montgomery form (one multiplication by the raw integer 1), every (point, window)
+//                   digit is histogrammed;
+//   2. scatter:     per-window counting sort of the point indices by digit (offsets from an exclusive scan);
+//   3. accumulate:  one thread per (window, bucket) sums its points with XYZZ mixed additions (8M + 2S, no inversion);
+//   4. reduce:      per window sum_d d*B_d with the running-sum trick split over the threads of one block;
+//   5. combine:     Horner over the windows (c doublings each), one inversion to return to affine.
+// Point arithmetic is integer-pipe (IMAD) bound: a mixed add is ~10 Fq multiplications of 12x12 32-bit limbs.
+#include <algorithm>
+#include "common.cuh"
+
+// q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+__device__ __constant__ uint32_t FQ_P[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                             0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+
+__device__ __forceinline__ Fq fq_one() {  // R mod q
+    Fq r;
+    r.l[0] = 0x0002fffdu; r.l[1] = 0x76090000u; r.l[2] = 0xc40c0002u; r.l[3] = 0xebf4000bu; r.l[4] = 0x53c758bau; r.l[5] = 0x5f489857u;
+    r.l[6] = 0x70525745u; r.l[7] = 0x77ce5853u; r.l[8] = 0xa256ec6du; r.l[9] = 0x5c071a97u; r.l[10] = 0xfa80e493u; r.l[11] = 0x15f65ec3u;
+    return r;
+}
+__device__ __forceinline__ Fq fq_dbl(const Fq& a) { return fq_add(a, a); }
+__device__ __forceinline__ bool fq_eq(const Fq& a, const Fq& b) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) o |= a.l[i] ^ b.l[i];
+    return o == 0;
+}
+
+struct G1Aff {  // (0, 0) encodes the point at infinity (not on y^2 = x^3 + 4)
+    Fq x, y;
+};
+struct G1X {  // extended Jacobian: x = X/ZZ, y = Y/ZZZ, ZZ^3 == ZZZ^2; ZZ == 0 is infinity
+    Fq X, Y, ZZ, ZZZ;
+};
+
+__device__ __forceinline__ G1X g1x_inf() {
+    G1X r;
+    r.X = fq_zero(); r.Y = fq_zero(); r.ZZ = fq_zero(); r.ZZZ = fq_zero();
+    return r;
+}
+__device__ __forceinline__ bool g1x_is_inf(const G1X& p) { return fq_is_zero(p.ZZ); }
+__device__ __forceinline__ bool g1a_is_inf(const G1Aff& p) { return fq_is_zero(p.x) && fq_is_zero(p.y); }
+
+// dbl-2008-s-1 (a = 0)
+__device__ __noinline__ G1X g1x_dbl(const G1X& p) {
+    if (g1x_is_inf(p) || fq_is_zero(p.Y)) return g1x_inf();
+    Fq U = fq_dbl(p.Y);
+    Fq V = fq_sqr(U);
+    Fq W = fq_mul(U, V);
+    Fq S = fq_mul(p.X, V);
+    Fq XX = fq_sqr(p.X);
+    Fq M = fq_add(fq_dbl(XX), XX);
+    G1X r;
+    r.X = fq_sub(fq_sqr(M), fq_dbl(S));
+    r.Y = fq_sub(fq_mul(M, fq_sub(S, r.X)), fq_mul(W, p.Y));
+    r.ZZ = fq_mul(V, p.ZZ);
+    r.ZZZ = fq_mul(W, p.ZZZ);
+    return r;
+}
+
+// madd-2008-s: XYZZ += affine
+__device__ __noinline__ void g1x_madd(G1X& a, const G1Aff& b) {
+    if (g1a_is_inf(b)) return;
+    if (g1x_is_inf(a)) {
+        a.X = b.x; a.Y = b.y; a.ZZ = fq_one(); a.ZZZ = fq_one();
+        return;
+    }
+    Fq U2 = fq_mul(b.x, a.ZZ);
+    Fq S2 = fq_mul(b.y, a.ZZZ);
+    Fq Pp = fq_sub(U2, a.X);
+    Fq R = fq_sub(S2, a.Y);
+    if (fq_is_zero(Pp)) {
+        if (fq_is_zero(R)) {  // same point: double the affine operand
+            G1X t;
+            t.X = b.x; t.Y = b.y; t.ZZ = fq_one(); t.ZZZ = fq_one();
+            a = g1x_dbl(t);
+        } else {
+            a = g1x_inf();
+        }
+        return;
+    }
+    Fq PP = fq_sqr(Pp);
+    Fq PPP = fq_mul(Pp, PP);
+    Fq Q = fq_mul(a.X, PP);
+    Fq X3 = fq_sub(fq_sub(fq_sqr(R), PPP), fq_dbl(Q));
+    Fq Y3 = fq_sub(fq_mul(R, fq_sub(Q, X3)), fq_mul(a.Y, PPP));
+    a.X = X3;
+    a.Y = Y3;
+    a.ZZ = fq_mul(a.ZZ, PP);
+    a.ZZZ = fq_mul(a.ZZZ, PPP);
+}
+
+// add-2008-s: XYZZ += XYZZ
+__device__ __noinline__ void g1x_add(G1X& a, const G1X& b) {
+    if (g1x_is_inf(b)) return;
+    if (g1x_is_inf(a)) { a = b; return; }
+    Fq U1 = fq_mul(a.X, b.ZZ);
+    Fq U2 = fq_mul(b.X, a.ZZ);
+    Fq S1 = fq_mul(a.Y, b.ZZZ);
+    Fq S2 = fq_mul(b.Y, a.ZZZ);
+    Fq Pp = fq_sub(U2, U1);
+    Fq R = fq_sub(S2, S1);
+    if (fq_is_zero(Pp)) {
+        if (fq_is_zero(R)) a = g1x_dbl(a); else a = g1x_inf();
+        return;
+    }
+    Fq PP = fq_sqr(Pp);
+    Fq PPP = fq_mul(Pp, PP);
+    Fq Q = fq_mul(U1, PP);
+    Fq X3 = fq_sub(fq_sub(fq_sqr(R), PPP), fq_dbl(Q));
+    Fq Y3 = fq_sub(fq_mul(R, fq_sub(Q, X3)), fq_mul(S1, PPP));
+    a.X = X3;
+    a.Y = Y3;
+    a.ZZ = fq_mul(fq_mul(a.ZZ, b.ZZ), PP);
+    a.ZZZ = fq_mul(fq_mul(a.ZZZ, b.ZZZ), PPP);
+}
+
+// a^(q-2)
+__device__ Fq fq_inv(const Fq& a) {
+    Fq r = fq_one();
+    uint32_t e[12];
+    for (int i = 0; i < 12; i++) e[i] = FQ_P[i];
+    e[0] -= 2;  // low limb 0xffffaaab, no borrow
+    for (int i = 380; i >= 0; i--) {
+        r = fq_sqr(r);
+        if ((e[i >> 5] >> (i & 31)) & 1) r = fq_mul(r, a);
+    }
+    return r;
+}
+
+// ---- kernels ------------------------------------------------------------------------------------------
+// scalars: Fr in Montgomery form -> plain integers; per (window, digit) histogram
+__global__ void msm_digits_kernel(const Fr* scalars, uint32_t n, int c, int n_windows, uint32_t* digits /* [W][n] */, uint32_t* counts /* [W][2^c] */) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Fr one_raw = fr_zero();
+        one_raw.l[0] = 1;
+        Fr s = fr_mul(scalars[i], one_raw);  // s * R^-1: the canonical integer
+        for (int w = 0; w < n_windows; w++) {
+            int bit = w * c;
+            int limb = bit >> 5, sh = bit & 31;
+            uint64_t v = s.l[limb];
+            if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
+            uint32_t d = (uint32_t)(v >> sh) & ((1u << c) - 1);
+            digits[(size_t)w * n + i] = d;
+            if (d) atomicAdd(&counts[((size_t)w << c) + d], 1u);
+        }
+    }
+}
+
+// exclusive scan of every window's histogram (one block per window)
+__global__ void msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, int c) {
+    __shared__ uint32_t carry;
+    __shared__ uint32_t tmp[1024];
+    const uint32_t nb = 1u << c;
+    const uint32_t* cnt = counts + ((size_t)blockIdx.x << c);
+    uint32_t* off = offsets + ((size_t)blockIdx.x << c);
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += blockDim.x) {
+        uint32_t v = base + threadIdx.x < nb ? cnt[base + threadIdx.x] : 0;
+        tmp[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t s = 1; s < blockDim.x; s <<= 1) {
+            uint32_t t = threadIdx.x >= s ? tmp[threadIdx.x - s] : 0;
+            __syncthreads();
+            tmp[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (base + threadIdx.x < nb) off[base + threadIdx.x] = carry + tmp[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry += tmp[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+__global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, int n_windows, const uint32_t* offsets, uint32_t* cursor,
+                                   uint32_t* sorted /* [W][n] */) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        for (int w = 0; w < n_windows; w++) {
+            uint32_t d = digits[(size_t)w * n + i];
+            if (!d) continue;
+            uint32_t pos = atomicAdd(&cursor[((size_t)w << c) + d], 1u);
+            sorted[(size_t)w * n + offsets[((size_t)w << c) + d] + pos] = i;
+        }
+    }
+}
+
+template <bool PROJ>
+__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts, const uint32_t* offsets,
+                                                              uint32_t n, int c, int n_windows, G1X* buckets) {
+    const uint64_t total = (uint64_t)n_windows << c;
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t cnt = counts[b];
+        G1X acc = g1x_inf();
+        if ((b & ((1u << c) - 1)) != 0 && cnt) {
+            const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
+            for (uint32_t k = 0; k < cnt; k++) {
+                if (PROJ) {
+                    // Jacobian (X, Y, Z) base: ZZ = Z^2, ZZZ = Z^3
+                    const Fq* p = (const Fq*)bases + (size_t)3 * idx[k];
+                    Fq Z = p[2];
+                    if (fq_is_zero(Z)) continue;
+                    G1X t;
+                    t.X = p[0]; t.Y = p[1]; t.ZZ = fq_sqr(Z); t.ZZZ = fq_mul(t.ZZ, Z);
+                    g1x_add(acc, t);
+                } else {
+                    G1Aff p = ((const G1Aff*)bases)[idx[k]];
+                    g1x_madd(acc, p);
+                }
+            }
+        }
+        buckets[b] = acc;
+    }
+}
+
+// per window: sum_d d * B_d.  Thread k owns buckets [k*L, (k+1)*L); descending running sums give
+// tot = sum (d - lo + 1) B_d and run = sum B_d, so sum d*B_d = tot + (lo - 1) * run.
+__global__ void __launch_bounds__(256) msm_reduce_kernel(const G1X* buckets, int c, G1X* window_sums) {
+    extern __shared__ unsigned char smem_raw[];
+    G1X* sh = reinterpret_cast<G1X*>(smem_raw);
+    const uint32_t nb = 1u << c;
+    const G1X* B = buckets + ((size_t)blockIdx.x << c);
+    const uint32_t T = blockDim.x;
+    const uint32_t L = (nb + T - 1) / T;
+    const uint32_t lo = threadIdx.x * L;
+    uint32_t hi = lo + L;
+    if (hi > nb) hi = nb;
+    G1X run = g1x_inf(), tot = g1x_inf();
+    if (lo < nb) {
+        for (uint32_t d = hi; d-- > lo;) {
+            g1x_add(run, B[d]);
+            g1x_add(tot, run);
+        }
+        if (lo >= 2) {  // tot += (lo - 1) * run
+            uint32_t k = lo - 1;
+            G1X acc = g1x_inf(), base = run;
+            while (k) {
+                if (k & 1) g1x_add(acc, base);
+                base = g1x_dbl(base);
+                k >>= 1;
+            }
+            g1x_add(tot, acc);
+        } else if (lo == 0) {
+            // tot counted (d + 1) * B_d for the segment starting at zero: remove one run
+            G1X neg = run;
+            neg.Y = fq_sub(fq_zero(), neg.Y);
+            g1x_add(tot, neg);
+        }
+    }
+    sh[threadIdx.x] = tot;
+    __syncthreads();
+    for (uint32_t s = T >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            G1X a = sh[threadIdx.x];
+            g1x_add(a, sh[threadIdx.x + s]);
+            sh[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) window_sums[blockIdx.x] = sh[0];
+}
+
+// Horner over the windows and normalisation to affine
+__global__ void msm_combine_kernel(const G1X* window_sums, int c, int n_windows, G1Aff* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1X acc = g1x_inf();
+    for (int w = n_windows - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) acc = g1x_dbl(acc);
+        g1x_add(acc, window_sums[w]);
+    }
+    G1Aff r;
+    if (g1x_is_inf(acc)) {
+        r.x = fq_zero();
+        r.y = fq_zero();
+    } else {
+        r.x = fq_mul(acc.X, fq_inv(acc.ZZ));
+        r.y = fq_mul(acc.Y, fq_inv(acc.ZZZ));
+    }
+    *out = r;
+}
+
+// ---- host -------------------------------------------------------------------------------------------------
+struct gkr_srs {
+    gkr_ctx* ctx = nullptr;
+    void* d = nullptr;
+    uint64_t n = 0;
+    bool projective = false;  // false: affine (x, y) 2x6 u64; true: Jacobian (X, Y, Z) 3x6 u64
+};
+
+extern "C" int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, int projective, gkr_srs** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!out || (!points && n)) return ctx->fail(GKR_ERR_ARG, "null argument");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    gkr_srs* s = new gkr_srs();
+    s->ctx = ctx;
+    s->n = n;
+    s->projective = projective != 0;
+    size_t bytes = (size_t)n * (projective ? 3 : 2) * sizeof(Fq);
+    cudaError_t e = cudaMallocAsync(&s->d, std::max<size_t>(bytes, 16), ctx->stream);
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(s->d, points, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        delete s;
+        return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    *out = s;
+    return GKR_OK;
+}
+
+extern "C" uint64_t gkr_srs_len(const gkr_srs* s) { return s ? s->n : 0; }
+
+extern "C" void gkr_srs_free(gkr_srs* s) {
+    if (!s) return;
+    if (s->d) cudaFreeAsync(s->d, s->ctx->stream);
+    delete s;
+}
+
+static int pick_window(uint64_t n) {
+    int lg = 0;
+    while (((uint64_t)1 << lg) < n) lg++;
+    int c = lg - 3;  // bucket work 2^c per window vs n additions per window
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+    return c;
+}
+
+// <bases[first .. first+n), scalars>   scalars: device table of n Fr (Montgomery).  out_xy: affine result, 12 u64
+// (x then y, Montgomery form; all zero for the point at infinity).
+extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!srs || !scalars || !out_xy) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (first + n > srs->n) return ctx->fail(GKR_ERR_ARG, "Vector is too large.");  // kzg.rs:124
+    if (scalars->n < n) return ctx->fail(GKR_ERR_ARG, "fewer scalars than requested");
+    if (n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "MSM larger than 2^31 points");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (n == 0) {
+        std::memset(out_xy, 0, 96);
+        return GKR_OK;
+    }
+    const int c = pick_window(n);
+    const int W = (255 + c - 1) / c;
+    const size_t nbk = (size_t)W << c;
+    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *offsets = nullptr, *cursor = nullptr;
+    G1X *buckets = nullptr, *wsums = nullptr;
+    G1Aff* d_out = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&digits, sizeof(uint32_t) * W * n, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * W * n, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * nbk * 3, st));
+    offsets = counts + nbk;
+    cursor = counts + 2 * nbk;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&buckets, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&wsums, sizeof(G1X) * W, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_out, sizeof(G1Aff), st));
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
+    unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    msm_digits_kernel<<<g1, 256, 0, st>>>(scalars->d, (uint32_t)n, c, W, digits, counts);
+    msm_scan_kernel<<<W, 1024, 0, st>>>(counts, offsets, c);
+    msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, c, W, offsets, cursor, sorted);
+    unsigned g2 = (unsigned)std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16);
+    const size_t psz = srs->projective ? 3 * sizeof(Fq) : sizeof(G1Aff);
+    const void* bases = (const unsigned char*)srs->d + first * psz;
+    if (srs->projective) msm_accumulate_kernel<true><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, W, buckets);
+    else msm_accumulate_kernel<false><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, W, buckets);
+    const int T = 256;
+    GKR_CUDA_OK(ctx, cudaFuncSetAttribute(msm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(G1X) * T)));
+    msm_reduce_kernel<<<W, T, sizeof(G1X) * T, st>>>(buckets, c, wsums);
+    msm_combine_kernel<<<1, 32, 0, st>>>(wsums, c, W, d_out);
+    ctx->launches += 6;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, d_out, sizeof(G1Aff), cudaMemcpyDeviceToHost, st));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(digits, st);
+    cudaFreeAsync(sorted, st);
+    cudaFreeAsync(counts, st);
+    cudaFreeAsync(buckets, st);
+    cudaFreeAsync(wsums, st);
+    cudaFreeAsync(d_out, st);
+    return GKR_OK;
+}

@@ -170,6 +170,19 @@ int gkr_map_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repea
 int gkr_map_vecvec(gkr_ctx* ctx, const int* part_gate, const uint32_t* part_repeat, uint32_t n_parts, gkr_vecvec* const* in,
                    uint32_t n_in, int mode, uint32_t bundle_size, void** out, uint32_t* n_out);
 
+/* ---- commitments: MSM over BLS12-381 G1 ------------------------------------------------------------------
+ * gkr_srs_upload: bases resident in HBM.  projective = 0: affine points, 12 u64 each (x then y, Fq Montgomery limbs,
+ *   ark `Fp384<MontBackend<FqConfig,6>>`; (0,0) = point at infinity) -- `KzgProvingKey::ptau_1` (kzg.rs:18-22);
+ *   projective = 1: Jacobian (X, Y, Z), 18 u64 each -- the bases of msm_nonaff (src/msm_nonaffine.rs:34-38).
+ * gkr_msm_g1: <bases[first..first+n), scalars> with `scalars` a device table of Fr (Montgomery form), i.e.
+ *   KzgProvingKey::commit(poly) (kzg.rs:123-126; fails like its assert when the slice is too long).  out_xy: the
+ *   affine result, 12 u64 (all zero = infinity). */
+typedef struct gkr_srs gkr_srs;
+int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, int projective, gkr_srs** out);
+uint64_t gkr_srs_len(const gkr_srs* s);
+void gkr_srs_free(gkr_srs* s);
+int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
+
 /* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
  * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */
 int gkr_transcript_new(const uint8_t* label, size_t label_len, gkr_transcript** out);

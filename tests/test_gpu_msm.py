@@ -1,0 +1,100 @@
+"""GPU parity for the commitment MSM over BLS12-381 G1 (KzgProvingKey::commit, kzg.rs:123-126; msm_nonaff,
+msm_nonaffine.rs:34-38) against an independent textbook group-law oracle -- the way the reference's own tests
+compare against `G::msm` (pullback.rs:86-107, binary_msm.rs:63-96).  The result is a unique group element, so
+affine coordinates must match bit for bit."""
+import random
+
+import numpy as np
+import pytest
+
+import gkr_msm_b200 as g
+from oracle.pyref import curves as CV
+from oracle.pyref.field import FQ_MODULUS, P, fq_vec_from_mont_u64, fq_vec_to_mont_u64
+from tests.util import to_limbs
+
+pytestmark = pytest.mark.gpu
+
+
+def aff_to_limbs(points):
+    out = np.zeros((len(points), 12), np.uint64)
+    for i, p in enumerate(points):
+        if p is not None:
+            out[i] = fq_vec_to_mont_u64([p[0], p[1]]).reshape(12)
+    return out
+
+
+def res_to_point(xy):
+    x, y = fq_vec_from_mont_u64(xy.reshape(2, 6))
+    return None if (x, y) == (0, 0) else (x, y)
+
+
+def rand_g1(rng):
+    return CV.g1_mul(rng.randrange(1, CV.G1_ORDER), CV.G1_GEN)
+
+
+@pytest.mark.parametrize("n", [1, 2, 17, 300])
+def test_msm_random(ctx, n):
+    rng = random.Random(n)
+    pts = [rand_g1(rng) for _ in range(min(n, 24))]
+    pts = [pts[i % len(pts)] for i in range(n)]  # repeated bases exercise the doubling path inside buckets
+    sc = [rng.randrange(P) for _ in range(n)]
+    srs = g.Srs(ctx, aff_to_limbs(pts))
+    got = res_to_point(srs.msm(ctx.upload(to_limbs(sc))))
+    assert got == CV.g1_msm(pts, sc)
+    assert CV.g1_on_curve(got)
+
+
+def test_msm_edge_cases(ctx):
+    rng = random.Random(5)
+    a, b = rand_g1(rng), rand_g1(rng)
+    # zeros, ones, r-1, infinity bases, P + (-P), equal scalars on equal points
+    pts = [a, CV.g1_neg(a), b, None, b, a, b]
+    sc = [7, 7, 0, 12345, 1, P - 1, 1 << 200]
+    srs = g.Srs(ctx, aff_to_limbs(pts))
+    assert res_to_point(srs.msm(ctx.upload(to_limbs(sc)))) == CV.g1_msm(pts, sc)
+    # everything cancels -> infinity
+    pts2, sc2 = [a, CV.g1_neg(a)], [99, 99]
+    assert res_to_point(g.Srs(ctx, aff_to_limbs(pts2)).msm(ctx.upload(to_limbs(sc2)))) is None
+    # small scalars (the c/d counter tables of the pushforward commit are small integers)
+    pts3 = [rand_g1(rng) for _ in range(8)] * 8
+    sc3 = [rng.randrange(16) for _ in range(64)]
+    assert res_to_point(g.Srs(ctx, aff_to_limbs(pts3)).msm(ctx.upload(to_limbs(sc3)))) == CV.g1_msm(pts3, sc3)
+    # prefix / offset of a longer SRS (kzg.rs:125 `&self.ptau_1[..poly.len()]`), and the too-long assert
+    srs3 = g.Srs(ctx, aff_to_limbs(pts3))
+    assert res_to_point(srs3.msm(ctx.upload(to_limbs(sc3[:10])), n=10, first=3)) == CV.g1_msm(pts3[3:13], sc3[:10])
+    with pytest.raises(g.GkrError):
+        srs3.msm(ctx.upload(to_limbs(sc3)), n=64, first=1)
+
+
+def test_msm_projective_bases(ctx):
+    rng = random.Random(9)
+    pts = [rand_g1(rng) for _ in range(20)]
+    sc = [rng.randrange(P) for _ in range(20)]
+    jac = np.zeros((20, 18), np.uint64)
+    for i, p in enumerate(pts):
+        z = rng.randrange(1, FQ_MODULUS)
+        jac[i] = fq_vec_to_mont_u64([p[0] * z * z % FQ_MODULUS, p[1] * z * z * z % FQ_MODULUS, z]).reshape(18)
+    jac[5] = 0  # Z == 0: infinity
+    want = CV.g1_msm([p for i, p in enumerate(pts) if i != 5], [s for i, s in enumerate(sc) if i != 5])
+    srs = g.Srs(ctx, jac, projective=True)
+    assert res_to_point(srs.msm(ctx.upload(to_limbs(sc)))) == want
+
+
+def test_msm_linearity_large(ctx):
+    """size-independent property at 2^16: msm(bases, a*s + t) == a*msm(bases, s) + msm(bases, t)."""
+    rng = random.Random(11)
+    n = 1 << 16
+    base_pts = [rand_g1(rng) for _ in range(16)]
+    pts = aff_to_limbs(base_pts)[np.arange(n) % 16]
+    srs = g.Srs(ctx, pts)
+    s_tab, t_tab = ctx.synth(1, n), ctx.synth(2, n)
+    s = ctx.upload(s_tab.download())
+    ms, mt = res_to_point(srs.msm(s_tab)), res_to_point(srs.msm(t_tab))
+    # u = s + t computed on the host in Montgomery form (addition commutes with the Montgomery map)
+    from oracle.pyref.field import fr_vec_from_mont_u64
+    sv, tv = fr_vec_from_mont_u64(s_tab.download()), fr_vec_from_mont_u64(t_tab.download())
+    u = ctx.upload(to_limbs([(x + y) % P for x, y in zip(sv, tv)]))
+    assert res_to_point(srs.msm(u)) == CV.g1_add(ms, mt)
+    # and against the oracle through the 16 distinct bases
+    agg = [sum(sv[i] for i in range(j, n, 16)) % P for j in range(16)]
+    assert ms == CV.g1_msm(base_pts, agg)
