@@ -589,3 +589,160 @@ class Srs:
                 self.free()
         except Exception:
             pass
+
+
+def _srs_bucket_sums(self, point_idx, bucket_idx, n_buckets) -> "Srs":
+    """PushForwardState::new bucket accumulation (pushforward.rs:398-429): returns the bucket sums as a resident Srs."""
+    lib = self.ctx.lib
+    if not hasattr(lib.gkr_g1_bucket_sums, "_sig"):
+        lib.gkr_g1_bucket_sums.restype = C.c_int
+        lib.gkr_g1_bucket_sums.argtypes = [_vp, _vp, _vp, _vp, C.c_uint64, C.c_uint32, C.POINTER(_vp)]
+        lib.gkr_g1_weighted_bucket_sum.restype = C.c_int
+        lib.gkr_g1_weighted_bucket_sum.argtypes = [_vp, _vp, _vp]
+        lib.gkr_g1_download_affine.restype = C.c_int
+        lib.gkr_g1_download_affine.argtypes = [_vp, _vp, _vp]
+        lib.gkr_g1_bucket_sums._sig = True
+    p = np.ascontiguousarray(point_idx, dtype=np.uint32)
+    b = np.ascontiguousarray(bucket_idx, dtype=np.uint32)
+    h = _vp()
+    self.ctx.check(lib.gkr_g1_bucket_sums(self.ctx.h, self.h, _ptr(p), _ptr(b), p.shape[0], n_buckets, C.byref(h)))
+    out = Srs.__new__(Srs)
+    out.ctx, out.h, out.n = self.ctx, h, n_buckets
+    return out
+
+
+def _srs_weighted_sum(self) -> np.ndarray:
+    out = np.zeros(12, np.uint64)
+    self.ctx.check(self.ctx.lib.gkr_g1_weighted_bucket_sum(self.ctx.h, self.h, _ptr(out)))
+    return out
+
+
+def _srs_download_affine(self) -> np.ndarray:
+    out = np.zeros((self.n, 12), np.uint64)
+    self.ctx.check(self.ctx.lib.gkr_g1_download_affine(self.ctx.h, self.h, _ptr(out)))
+    return out
+
+
+Srs.bucket_sums = _srs_bucket_sums
+Srs.weighted_sum = _srs_weighted_sum
+Srs.download_affine = _srs_download_affine
+
+
+def _poly_sigs(lib):
+    if hasattr(lib.gkr_u32_upload, "_sig"):
+        return
+    def f(name, res, *args):
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = list(args)
+    f("gkr_u32_upload", C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp))
+    f("gkr_u32_free", None, _vp)
+    f("gkr_table_from_u32", C.c_int, _vp, _vp, C.c_int, C.POINTER(_vp))
+    f("gkr_table_gather", C.c_int, _vp, _vp, _vp, C.POINTER(_vp))
+    f("gkr_table_lincomb", C.c_int, _vp, C.c_uint32, C.POINTER(_vp), _vp, _vp, _vp, _vp, C.c_uint64, C.POINTER(_vp))
+    f("gkr_poly_eval", C.c_int, _vp, _vp, _vp, _vp)
+    f("gkr_poly_div_by_linear", C.c_int, _vp, _vp, _vp, C.POINTER(_vp), _vp)
+    f("gkr_knuckles_create", C.c_int, _vp, C.c_uint32, _vp, C.POINTER(_vp))
+    f("gkr_knuckles_free", None, _vp)
+    f("gkr_knuckles_compute_t", C.c_int, _vp, _vp, _vp, _vp, C.c_uint32, C.POINTER(_vp), _vp)
+    lib.gkr_u32_upload._sig = True
+
+
+class U32Buf:
+    """gkr_u32buf: digit / counter arrays resident on the device."""
+
+    def __init__(self, ctx: Context, vals):
+        _poly_sigs(ctx.lib)
+        a = np.ascontiguousarray(vals, dtype=np.uint32).reshape(-1)
+        h = _vp()
+        ctx.check(ctx.lib.gkr_u32_upload(ctx.h, _ptr(a), a.shape[0], C.byref(h)))
+        self.ctx, self.h, self.n = ctx, h, a.shape[0]
+
+    def to_field(self, negate=False) -> Table:
+        h = _vp()
+        self.ctx.check(self.ctx.lib.gkr_table_from_u32(self.ctx.h, self.h, 1 if negate else 0, C.byref(h)))
+        return Table(self.ctx, h)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.gkr_u32_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass
+
+
+def _ctx_gather(self, src: Table, idx: U32Buf) -> Table:
+    _poly_sigs(self.lib)
+    h = _vp()
+    self.check(self.lib.gkr_table_gather(self.h, src.h, idx.h, C.byref(h)))
+    return Table(self, h)
+
+
+def _ctx_lincomb(self, terms, out_len) -> Table:
+    """terms: list of (table, coef_limbs, src_off, dst_off, length); out[dst_off+i] += coef*table[src_off+i]."""
+    _poly_sigs(self.lib)
+    k = len(terms)
+    arr = (_vp * max(k, 1))(*[t[0].h for t in terms])
+    coefs = np.ascontiguousarray(np.stack([_limbs(t[1]).reshape(4) for t in terms]) if k else np.zeros((0, 4), np.uint64))
+    so = np.array([t[2] for t in terms], dtype=np.uint64)
+    do = np.array([t[3] for t in terms], dtype=np.uint64)
+    ln = np.array([t[4] for t in terms], dtype=np.uint64)
+    h = _vp()
+    self.check(self.lib.gkr_table_lincomb(self.h, k, arr, _ptr(coefs), _ptr(so), _ptr(do), _ptr(ln), out_len, C.byref(h)))
+    return Table(self, h)
+
+
+def _ctx_poly_eval(self, poly: Table, x) -> np.ndarray:
+    _poly_sigs(self.lib)
+    xx, out = _limbs(x).reshape(4), np.zeros(4, np.uint64)
+    self.check(self.lib.gkr_poly_eval(self.h, poly.h, _ptr(xx), _ptr(out)))
+    return out
+
+
+def _ctx_div_by_linear(self, poly: Table, pt):
+    _poly_sigs(self.lib)
+    xx, rem = _limbs(pt).reshape(4), np.zeros(4, np.uint64)
+    h = _vp()
+    self.check(self.lib.gkr_poly_div_by_linear(self.h, poly.h, _ptr(xx), C.byref(h), _ptr(rem)))
+    return Table(self, h), rem
+
+
+Context.gather = _ctx_gather
+Context.lincomb = _ctx_lincomb
+Context.poly_eval = _ctx_poly_eval
+Context.div_by_linear = _ctx_div_by_linear
+
+
+class Knuckles:
+    """gkr_knuckles: KnucklesProvingKey's field part (inverses table) + compute_t (knuckles.rs:65-81, 111-154)."""
+
+    def __init__(self, ctx: Context, num_vars: int, k):
+        _poly_sigs(ctx.lib)
+        kk = _limbs(k).reshape(4)
+        h = _vp()
+        ctx.check(ctx.lib.gkr_knuckles_create(ctx.h, num_vars, _ptr(kk), C.byref(h)))
+        self.ctx, self.h, self.num_vars = ctx, h, num_vars
+
+    def compute_t(self, poly: Table, point):
+        pt = _limbs(point).reshape(-1, 4)
+        opening = np.zeros(4, np.uint64)
+        h = _vp()
+        self.ctx.check(self.ctx.lib.gkr_knuckles_compute_t(self.ctx.h, self.h, poly.h, _ptr(pt), pt.shape[0], C.byref(h), _ptr(opening)))
+        return Table(self.ctx, h), opening
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.gkr_knuckles_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.ctx.h:
+                self.free()
+        except Exception:
+            pass

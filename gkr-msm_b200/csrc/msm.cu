@@ -190,17 +190,19 @@ __global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, in
     }
 }
 
-template <bool PROJ>
+// KIND 0: affine bases, 1: Jacobian (X, Y, Z), 2: extended Jacobian (X, Y, ZZ, ZZZ) as produced by gkr_g1_bucket_sums
+template <int KIND>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts, const uint32_t* offsets,
-                                                              uint32_t n, int c, int n_windows, G1X* buckets) {
-    const uint64_t total = (uint64_t)n_windows << c;
+                                                              uint32_t n, int c, uint64_t total, int skip_zero, G1X* buckets) {
     for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t cnt = counts[b];
         G1X acc = g1x_inf();
-        if ((b & ((1u << c) - 1)) != 0 && cnt) {
+        if (!(skip_zero && (b & ((1u << c) - 1)) == 0) && cnt) {
             const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
             for (uint32_t k = 0; k < cnt; k++) {
-                if (PROJ) {
+                if (KIND == 2) {
+                    g1x_add(acc, ((const G1X*)bases)[idx[k]]);
+                } else if (KIND == 1) {
                     // Jacobian (X, Y, Z) base: ZZ = Z^2, ZZZ = Z^3
                     const Fq* p = (const Fq*)bases + (size_t)3 * idx[k];
                     Fq Z = p[2];
@@ -289,7 +291,8 @@ struct gkr_srs {
     gkr_ctx* ctx = nullptr;
     void* d = nullptr;
     uint64_t n = 0;
-    bool projective = false;  // false: affine (x, y) 2x6 u64; true: Jacobian (X, Y, Z) 3x6 u64
+    int kind = 0;  // 0: affine (x, y) 2x6 u64; 1: Jacobian (X, Y, Z) 3x6 u64; 2: XYZZ 4x6 u64 (device-produced bucket sums)
+    size_t stride() const { return kind == 0 ? sizeof(G1Aff) : (kind == 1 ? 3 * sizeof(Fq) : sizeof(G1X)); }
 };
 
 extern "C" int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, int projective, gkr_srs** out) {
@@ -299,8 +302,8 @@ extern "C" int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, 
     gkr_srs* s = new gkr_srs();
     s->ctx = ctx;
     s->n = n;
-    s->projective = projective != 0;
-    size_t bytes = (size_t)n * (projective ? 3 : 2) * sizeof(Fq);
+    s->kind = projective ? 1 : 0;
+    size_t bytes = (size_t)n * s->stride();
     cudaError_t e = cudaMallocAsync(&s->d, std::max<size_t>(bytes, 16), ctx->stream);
     if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(s->d, points, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -363,10 +366,10 @@ extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, cons
     msm_scan_kernel<<<W, 1024, 0, st>>>(counts, offsets, c);
     msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, c, W, offsets, cursor, sorted);
     unsigned g2 = (unsigned)std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16);
-    const size_t psz = srs->projective ? 3 * sizeof(Fq) : sizeof(G1Aff);
-    const void* bases = (const unsigned char*)srs->d + first * psz;
-    if (srs->projective) msm_accumulate_kernel<true><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, W, buckets);
-    else msm_accumulate_kernel<false><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, W, buckets);
+    const void* bases = (const unsigned char*)srs->d + first * srs->stride();
+    if (srs->kind == 2) msm_accumulate_kernel<2><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, nbk, 1, buckets);
+    else if (srs->kind == 1) msm_accumulate_kernel<1><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, nbk, 1, buckets);
+    else msm_accumulate_kernel<0><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, nbk, 1, buckets);
     const int T = 256;
     GKR_CUDA_OK(ctx, cudaFuncSetAttribute(msm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(G1X) * T)));
     msm_reduce_kernel<<<W, T, sizeof(G1X) * T, st>>>(buckets, c, wsums);
@@ -381,5 +384,142 @@ extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, cons
     cudaFreeAsync(buckets, st);
     cudaFreeAsync(wsums, st);
     cudaFreeAsync(d_out, st);
+    return GKR_OK;
+}
+
+
+// ---- bucket accumulation for the c / d commitments ----------------------------------------
+//   PushForwardState::new       src/cleanup/protocols/pushforward/pushforward.rs:398-429, 433-456
+//   Pullback::bucketed_msm      src/pullback.rs:28-59
+// B[b] = sum over incidences k with bucket_idx[k] == b of bases[point_idx[k]].  Merging the rows of one commitment
+// chunk (pushforward.rs:433-456) is implicit: all incidences of the chunk are accumulated into one bucket array.
+__global__ void g1_hist_kernel(const uint32_t* bidx, uint32_t n, uint32_t n_buckets, uint32_t* counts, int* bad) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t b = bidx[i];
+        if (b >= n_buckets) { *bad = 1; continue; }
+        atomicAdd(&counts[b], 1u);
+    }
+}
+__global__ void g1_scatter_kernel(const uint32_t* bidx, const uint32_t* pidx, uint32_t n, uint32_t n_buckets, const uint32_t* offsets,
+                                  uint32_t* cursor, uint32_t* sorted) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t b = bidx[i];
+        if (b >= n_buckets) continue;
+        uint32_t pos = atomicAdd(&cursor[b], 1u);
+        sorted[offsets[b] + pos] = pidx[i];
+    }
+}
+
+extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* point_idx, const uint32_t* bucket_idx, uint64_t n,
+                                  uint32_t n_buckets, gkr_srs** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!srs || !out || (n && (!point_idx || !bucket_idx)) || n_buckets == 0) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (srs->kind != 0) return ctx->fail(GKR_ERR_ARG, "bucket sums need affine bases");
+    if (n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many incidences");
+    for (uint64_t k = 0; k < n; k++)
+        if (point_idx[k] >= srs->n) return ctx->fail(GKR_ERR_ARG, "point index out of range");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int c = 0;
+    while ((1u << c) < n_buckets) c++;
+    const size_t nbk = (size_t)1 << c;
+    uint32_t *d_p = nullptr, *d_b = nullptr, *sorted = nullptr, *counts = nullptr;
+    int* d_bad = nullptr;
+    gkr_srs* res = new gkr_srs();
+    res->ctx = ctx;
+    res->n = n_buckets;
+    res->kind = 2;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&res->d, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_p, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_b, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * nbk * 3 + sizeof(int), st));
+    uint32_t* offsets = counts + nbk;
+    uint32_t* cursor = counts + 2 * nbk;
+    d_bad = (int*)(counts + 3 * nbk);
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3 + sizeof(int), st));
+    if (n) {
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_p, point_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_b, bucket_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
+        unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
+        g1_hist_kernel<<<g1, 256, 0, st>>>(d_b, (uint32_t)n, n_buckets, counts, d_bad);
+        msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, c);
+        g1_scatter_kernel<<<g1, 256, 0, st>>>(d_b, d_p, (uint32_t)n, n_buckets, offsets, cursor, sorted);
+        ctx->launches += 3;
+    }
+    unsigned g2 = (unsigned)std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16);
+    msm_accumulate_kernel<0><<<g2, 128, 0, st>>>(srs->d, sorted, counts, offsets, (uint32_t)n, c, nbk, 0, (G1X*)res->d);
+    ctx->launches++;
+    int bad = 0;
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));  // host index arrays may be released by the caller now
+    cudaFreeAsync(d_p, st);
+    cudaFreeAsync(d_b, st);
+    cudaFreeAsync(sorted, st);
+    cudaFreeAsync(counts, st);
+    if (bad) {
+        gkr_srs_free(res);
+        return ctx->fail(GKR_ERR_ARG, "bucket index out of range");
+    }
+    *out = res;
+    return GKR_OK;
+}
+
+// sum_{i=1}^{len-1} i * B[i]: the running-sum commitment of pushforward.rs:504-524 (== commit of the digit / counter table)
+extern "C" int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t* out_xy) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!buckets || !out_xy || buckets->kind != 2) return ctx->fail(GKR_ERR_ARG, "expects bucket sums");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int c = 0;
+    while (((uint64_t)1 << c) < buckets->n) c++;
+    G1X* wsum = nullptr;
+    G1Aff* d_out = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&wsum, sizeof(G1X), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_out, sizeof(G1Aff), st));
+    const int T = 256;
+    GKR_CUDA_OK(ctx, cudaFuncSetAttribute(msm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(G1X) * T)));
+    // buckets beyond n (up to the power of two) were written as infinity by the accumulate kernel
+    msm_reduce_kernel<<<1, T, sizeof(G1X) * T, st>>>((const G1X*)buckets->d, c, wsum);
+    msm_combine_kernel<<<1, 32, 0, st>>>(wsum, c, 1, d_out);
+    ctx->launches += 2;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, d_out, sizeof(G1Aff), cudaMemcpyDeviceToHost, st));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(wsum, st);
+    cudaFreeAsync(d_out, st);
+    return GKR_OK;
+}
+
+// download bucket sums / any point set as affine (x, y) pairs (tests, and `c_comm`-style per-bucket inspection)
+__global__ void g1_to_affine_kernel(const G1X* in, uint64_t n, G1Aff* out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        G1X p = in[i];
+        G1Aff r;
+        if (g1x_is_inf(p)) { r.x = fq_zero(); r.y = fq_zero(); }
+        else { r.x = fq_mul(p.X, fq_inv(p.ZZ)); r.y = fq_mul(p.Y, fq_inv(p.ZZZ)); }
+        out[i] = r;
+    }
+}
+
+extern "C" int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!pts || !out_xy) return ctx->fail(GKR_ERR_ARG, "null argument");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (pts->kind == 0) {
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, pts->d, sizeof(G1Aff) * pts->n, cudaMemcpyDeviceToHost, st));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+        return GKR_OK;
+    }
+    if (pts->kind != 2) return ctx->fail(GKR_ERR_UNSUPPORTED, "download of Jacobian bases is not needed by the path");
+    G1Aff* tmp = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&tmp, sizeof(G1Aff) * std::max<uint64_t>(pts->n, 1), st));
+    unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((pts->n + 63) / 64, (uint64_t)ctx->num_sms * 8));
+    g1_to_affine_kernel<<<g, 64, 0, st>>>((const G1X*)pts->d, pts->n, tmp);
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, tmp, sizeof(G1Aff) * pts->n, cudaMemcpyDeviceToHost, st));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(tmp, st);
     return GKR_OK;
 }

@@ -183,6 +183,39 @@ uint64_t gkr_srs_len(const gkr_srs* s);
 void gkr_srs_free(gkr_srs* s);
 int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
 
+/* bucket accumulation of the c / d commitments: B[b] = sum_{k: bucket_idx[k] == b} bases[point_idx[k]]
+ * (PushForwardState::new, pushforward.rs:398-429, 433-456; Pullback::bucketed_msm, src/pullback.rs:28-59).
+ * The result (n_buckets projective points, resident) is a valid `gkr_srs` for gkr_msm_g1 -- that call is then
+ * msm_nonaff over the bucket bases (pushforward.rs:598-604).  gkr_g1_weighted_bucket_sum = sum_i i*B[i], the
+ * running-sum commitment of pushforward.rs:504-524.  gkr_g1_download_affine normalises points for inspection. */
+int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* point_idx, const uint32_t* bucket_idx, uint64_t n,
+                       uint32_t n_buckets, gkr_srs** out);
+int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t* out_xy);
+int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
+
+/* ---- univariate / element-wise table algebra -----------------------------------------
+ * gkr_u32buf: digit / counter arrays resident on the device.
+ * gkr_table_from_u32: F::from(v) per entry, negated for the access counts (pushforward.rs:479-500).
+ * gkr_table_gather:   out[i] = src[idx[i]] (c_pull / d_pull, pushforward.rs:585-595).
+ * gkr_table_lincomb:  out = 0; out[dst_off_k + i] += coef_k * src_k[src_off_k + i] -- p_0 + gamma p_1, combined_witness,
+ *                     folded_witness (pippenger.rs:209-231, 274-279), p_lt = lambda t + p (opening.rs:65-75).
+ * gkr_poly_eval / gkr_poly_div_by_linear: `ev`, `div_by_linear` (kzg.rs:73-81, 142-150).
+ * gkr_knuckles_*: KnucklesProvingKey::new inverses and compute_t (knuckles.rs:65-81, 111-154). */
+typedef struct gkr_u32buf gkr_u32buf;
+typedef struct gkr_knuckles gkr_knuckles;
+int gkr_u32_upload(gkr_ctx* ctx, const uint32_t* vals, uint64_t n, gkr_u32buf** out);
+void gkr_u32_free(gkr_u32buf* b);
+int gkr_table_from_u32(gkr_ctx* ctx, const gkr_u32buf* v, int negate, gkr_table** out);
+int gkr_table_gather(gkr_ctx* ctx, const gkr_table* src, const gkr_u32buf* idx, gkr_table** out);
+int gkr_table_lincomb(gkr_ctx* ctx, uint32_t n_terms, gkr_table* const* src, const uint64_t* coefs, const uint64_t* src_off,
+                      const uint64_t* dst_off, const uint64_t* len, uint64_t out_len, gkr_table** out);
+int gkr_poly_eval(gkr_ctx* ctx, const gkr_table* poly, const uint64_t x[4], uint64_t out[4]);
+int gkr_poly_div_by_linear(gkr_ctx* ctx, const gkr_table* poly, const uint64_t pt[4], gkr_table** quotient, uint64_t rem[4]);
+int gkr_knuckles_create(gkr_ctx* ctx, uint32_t num_vars, const uint64_t k[4], gkr_knuckles** out);
+void gkr_knuckles_free(gkr_knuckles* key);
+int gkr_knuckles_compute_t(gkr_ctx* ctx, const gkr_knuckles* key, const gkr_table* poly, const uint64_t* point, uint32_t n_point,
+                           gkr_table** t_out, uint64_t opening[4]);
+
 /* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
  * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */
 int gkr_transcript_new(const uint8_t* label, size_t label_len, gkr_transcript** out);

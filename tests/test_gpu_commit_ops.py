@@ -1,0 +1,97 @@
+"""GPU parity for the commitment-side algebra vs the oracle restatement."""
+import random
+
+import numpy as np
+import pytest
+
+import gkr_msm_b200 as g
+from oracle.pyref import commitments as OC
+from oracle.pyref import curves as CV
+from oracle.pyref import sumcheck as S
+from oracle.pyref.field import P
+from tests.test_gpu_msm import aff_to_limbs, rand_g1, res_to_point
+from tests.util import from_limbs, to_limb1, to_limbs
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bucket_sums_running_sum_and_msm_nonaff(ctx):
+    """pushforward.rs:398-429, 504-524, 598-604 on a miniature instance: digits -> bucket sums -> d commitment ==
+    commit(d table) (the reference's own commented-out assertion :527-530), then msm_nonaff(buckets, eq_d)."""
+    rng = random.Random(1)
+    x_size, d_log = 64, 3
+    bases = [rand_g1(rng) for _ in range(x_size)]
+    digits = [rng.randrange(1 << d_log) for _ in range(x_size)]
+    srs = g.Srs(ctx, aff_to_limbs(bases))
+    bk = srs.bucket_sums(np.arange(x_size), digits, 1 << d_log)
+    want = OC.bucket_sums(bases, range(x_size), digits, 1 << d_log)
+    got = [res_to_point(r) for r in bk.download_affine()]
+    assert got == want
+    d_comm = res_to_point(bk.weighted_sum())
+    assert d_comm == OC.running_sum_commit(want)
+    assert d_comm == CV.g1_msm(bases, digits)  # == KzgProvingKey::commit(d)
+    dtab = g.U32Buf(ctx, digits).to_field()
+    assert from_limbs(dtab.download()) == digits
+    assert res_to_point(srs.msm(dtab)) == d_comm
+    # second phase: msm_nonaff over the bucket bases with eq_d as scalars
+    r_d = [rng.randrange(P) for _ in range(d_log)]
+    eq_d = S.eq_poly_sequence_last(r_d)
+    got2 = res_to_point(bk.msm(ctx.eq_table(to_limbs(r_d))))
+    assert got2 == CV.g1_msm([b for b in want], eq_d)
+    # == commit(d_pull) with d_pull[x] = eq_d[digit[x]]  (pushforward.rs:606-609)
+    d_pull = ctx.gather(ctx.eq_table(to_limbs(r_d)), g.U32Buf(ctx, digits))
+    assert from_limbs(d_pull.download()) == [eq_d[d] for d in digits]
+    assert res_to_point(srs.msm(d_pull)) == got2
+    # access counts are negated counts
+    ac = [0] * (1 << d_log)
+    for d in digits:
+        ac[d] += 1
+    assert from_limbs(g.U32Buf(ctx, ac).to_field(negate=True).download()) == [(-c) % P for c in ac]
+    with pytest.raises(g.GkrError):
+        srs.bucket_sums([0, 1], [0, 99], 8)
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 64, 1000, 5000])
+def test_poly_eval_and_div_by_linear(ctx, n):
+    rng = random.Random(n)
+    poly = [rng.randrange(P) for _ in range(n)]
+    x = rng.randrange(P)
+    tab = ctx.upload(to_limbs(poly))
+    assert from_limbs(ctx.poly_eval(tab, to_limb1(x)).reshape(1, 4))[0] == OC.ev(poly, x)
+    q, rem = ctx.div_by_linear(tab, to_limb1(x))
+    oq, orem = OC.div_by_linear(poly, x)
+    assert from_limbs(rem.reshape(1, 4))[0] == orem
+    assert (from_limbs(q.download()) if n > 1 else []) == oq
+
+
+@pytest.mark.parametrize("num_vars,plen", [(1, 2), (3, 8), (5, 20), (8, 256)])
+def test_knuckles_compute_t(ctx, num_vars, plen):
+    rng = random.Random(num_vars)
+    k = 2
+    inv = OC.knuckles_inverses(num_vars, k)
+    poly = [rng.randrange(P) for _ in range(plen)]
+    point = [rng.randrange(P) for _ in range(num_vars)]
+    key = g.Knuckles(ctx, num_vars, to_limb1(k))
+    t, opening = key.compute_t(ctx.upload(to_limbs(poly)), to_limbs(point))
+    ot, oopen = OC.compute_t(num_vars, inv, poly, point)
+    assert from_limbs(opening.reshape(1, 4))[0] == oopen
+    assert from_limbs(t.download()) == ot
+    # knuckles.rs:326-340: the opening is the multilinear evaluation of the (zero-padded) table
+    padded = poly + [0] * ((1 << num_vars) - plen)
+    assert oopen == S.evaluate_poly(padded, point)
+
+
+def test_lincomb_slices(ctx):
+    rng = random.Random(4)
+    a = [rng.randrange(P) for _ in range(16)]
+    b = [rng.randrange(P) for _ in range(8)]
+    ca, cb = rng.randrange(P), rng.randrange(P)
+    ta, tb = ctx.upload(to_limbs(a)), ctx.upload(to_limbs(b))
+    # zero-extended lambda*t + p  (opening.rs:65-75)
+    got = from_limbs(ctx.lincomb([(ta, to_limb1(ca), 0, 0, 16), (tb, to_limb1(1), 0, 0, 8)], 16).download())
+    assert got == [(ca * a[i] + (b[i] if i < 8 else 0)) % P for i in range(16)]
+    # strided accumulation like combined_witness (pippenger.rs:209-223): rows 0 and 2 of a 4x4 matrix into one row
+    got = from_limbs(ctx.lincomb([(ta, to_limb1(ca), 0, 0, 4), (ta, to_limb1(cb), 8, 0, 4)], 4).download())
+    assert got == [(ca * a[i] + cb * a[8 + i]) % P for i in range(4)]
+    with pytest.raises(g.GkrError):
+        ctx.lincomb([(tb, to_limb1(1), 4, 0, 8)], 8)
