@@ -746,3 +746,16 @@ class Knuckles:
                 self.free()
         except Exception:
             pass
+
+
+def _ctx_upload_vecvec_flat(self, flat, lens, row_pad, col_pad, row_logsize, col_logsize) -> "VecVec":
+    """VecVecPolynomial::new from rows stored back to back (`flat`: (sum lens, 4) limbs, `lens`: row lengths)."""
+    flat = np.ascontiguousarray(flat, dtype=np.uint64).reshape(-1, 4)
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    rp, cp = _limbs(row_pad).reshape(4), _limbs(col_pad).reshape(4)
+    h = _vp()
+    self.check(self.lib.gkr_vecvec_upload(self.h, _ptr(flat), _ptr(lens), lens.shape[0], _ptr(rp), _ptr(cp), row_logsize, col_logsize, C.byref(h)))
+    return VecVec(self, h)
+
+
+Context.upload_vecvec_flat = _ctx_upload_vecvec_flat

@@ -13,7 +13,24 @@
 #define GKR_MAX_POLYS 16        // max tables per sumcheck object (triangle L1 has 12 inputs + eq)
 #define GKR_MAX_DEG 4           // max number of accumulated evaluation points per round
 #define GKR_REDUCE_THREADS 128  // block size of the sumcheck round kernels
-#define GKR_MAX_BLOCKS 4096     // upper bound on the grid of a round kernel (partials scratch)
+#define GKR_MAX_BLOCKS 1024     // upper bound on the grid of a round kernel (one partial per block and accumulator)
+#define GKR_RESULT_SLOTS 64     // live sumcheck objects per context
+
+// Result channel of one sumcheck object, in pinned host memory mapped into the device address space.  Every block of a
+// round kernel writes its partial sums here; the last block (device ticket) publishes `flag = seq`.  The host spins on
+// the flag (no stream synchronisation, no memcpy launch) and folds the <= GKR_MAX_BLOCKS partials itself.
+struct GkrSlot {
+    volatile uint32_t flag;
+    uint32_t pad_[7];
+    Fr part[GKR_MAX_BLOCKS * GKR_MAX_DEG];
+};
+
+struct RoundOut {  // kernel-side view of a slot
+    Fr* part;
+    uint32_t* flag;
+    unsigned int* ticket;
+    uint32_t seq;
+};
 
 struct gkr_ctx {
     int device = 0;
@@ -21,10 +38,22 @@ struct gkr_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
-    Fr* partials = nullptr;         // [GKR_MAX_BLOCKS * GKR_MAX_DEG] device scratch
+    Fr* partials = nullptr;         // [GKR_MAX_BLOCKS * GKR_MAX_DEG] device scratch (device-side two-stage reductions)
     unsigned int* ticket = nullptr; // device counter for the last-block pattern
-    Fr* result_host = nullptr;      // pinned + mapped: round sums land here without a memcpy launch
+    Fr* result_host = nullptr;      // pinned + mapped scratch for one-shot reductions (gate sums)
     Fr* result_dev = nullptr;       // device alias of result_host
+    GkrSlot* slots_host = nullptr;  // [GKR_RESULT_SLOTS] pinned + mapped result channels
+    GkrSlot* slots_dev = nullptr;
+    unsigned int* slot_tickets = nullptr;  // [GKR_RESULT_SLOTS] device
+    uint32_t slot_seq[GKR_RESULT_SLOTS] = {0};
+    RoundOut round_out(int slot) {  // next launch on this slot
+        RoundOut o;
+        o.part = slots_dev[slot].part;
+        o.flag = (uint32_t*)&slots_dev[slot].flag;
+        o.ticket = slot_tickets + slot;
+        o.seq = ++slot_seq[slot];
+        return o;
+    }
     // optional per-launch timing (bench.py's roofline leg): CUDA events on the launching stream
     bool timing = false;
     struct TimedLaunch {
@@ -121,6 +150,9 @@ static inline gkr::FrH fr_to_host(const Fr& a) {
     return r;
 }
 
+// host side: wait for the launch `seq` on `slot` and fold its per-block partials (n_acc accumulators per block)
+int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out);
+
 #ifdef __CUDACC__
 // Sum `acc[0..N)` over all threads of the grid.  Field addition is associative and commutative and every
 // partial is canonical, so the result is bit-identical to the reference's sequential / rayon sum whatever
@@ -147,6 +179,28 @@ __device__ __forceinline__ void block_reduce_fr(Fr* acc, Fr* smem /* [N * warps]
         }
     }
     __syncthreads();
+}
+
+// Block-level sums go straight to the host-mapped slot; the last block to take a ticket publishes the sequence number.
+template <int N>
+__device__ __forceinline__ void grid_reduce_to_host(Fr* acc, Fr* smem, const RoundOut& o) {
+    block_reduce_fr<N>(acc, smem);
+    if (threadIdx.x == 0) {
+        const unsigned int n_blocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+        for (int s = 0; s < N; s++) o.part[(size_t)bid * N + s] = acc[s];
+        __threadfence_system();
+        bool last = true;
+        if (n_blocks > 1) {
+            unsigned int tk = atomicAdd(o.ticket, 1u);
+            last = (tk == n_blocks - 1);
+            if (last) *o.ticket = 0;
+        }
+        if (last) {
+            __threadfence_system();
+            *(volatile uint32_t*)o.flag = o.seq;
+        }
+    }
 }
 
 template <int N>

@@ -28,32 +28,76 @@ struct Deg2Block {
     int gate;
     int in_idx[6];
     int out_off;
+    int own_mask;  // bit k: this block writes the folded table in_idx[k] (each table has exactly one owner)
 };
 
-struct Deg2EvalArgs {
-    const Fr* const* tabs;     // [P] flat data of the current round
+// One round of a Deg2 object: FOLD the previous round's tables with the challenge (unless this is round 0), write the
+// new tables, evaluate the gate stack at 1 and "2" on the fresh pairs, weight by eq, and add the closed-form padding sum.
+struct Deg2RoundArgs {
+    const Fr* const* in;       // [P] round b-1 tables when fold != 0, else the current tables
+    Fr* const* out;            // [P] round b tables (written when fold != 0)
     const Deg2Block* blocks;   // [gridDim.y]
     const Fr* gammas;          // [n_outs], gammas[0] == 1
-    const uint32_t* pair_off;  // [nrows + 1] row offsets in PAIRS; nullptr: one dense row
+    const uint32_t* off_old;   // element offsets of round b-1 [nrows + 1] (fold only)
+    const uint32_t* pair_off;  // PAIR offsets of round b [nrows + 1]; nullptr: one dense row
     uint32_t nrows;
-    const Fr* eq;              // eq table of this round (row-local part)
+    const Fr* eq;              // eq table of round b (row-local part)
     const Fr* rowcoef;         // [nrows] or nullptr
-    uint64_t n_pairs;
-    Fr* partials;
-    unsigned int* ticket;
-    Fr* result;                // 2 values: S1, S2
+    uint64_t n_pairs;          // pairs of round b
+    int fold;
+    Fr t;
+    const Fr* row_pads;        // [P]
+    const Fr* pt;              // row variables of this round's eq table, for the padding term
+    uint32_t n_pt;
+    int do_pad;                // ragged objects only
+    RoundOut o;                // 3 accumulators: S1, S2, T
 };
 
 template <int G>
-__device__ __forceinline__ void deg2_block_eval(const Deg2EvalArgs& A, const Deg2Block& blk, uint64_t q, const Fr& w, Fr* acc) {
+__device__ __forceinline__ void deg2_block_round(const Deg2RoundArgs& A, const Deg2Block& blk, uint64_t q, uint32_t row, uint64_t idx,
+                                                 const Fr& w, Fr* acc) {
     constexpr int NI = MoGate<G>::N_INS, NO = MoGate<G>::N_OUTS;
     Fr a1[NI], a2[NI];
+    uint64_t old_base = 0, half_old = 0;
+    if (A.fold) {
+        if (A.pair_off) {
+            old_base = A.off_old[row];
+            half_old = (A.off_old[row + 1] - old_base) >> 1;
+        } else {
+            half_old = 2 * A.n_pairs;  // dense: the old table has 4 * n_pairs entries
+        }
+    }
 #pragma unroll
     for (int j = 0; j < NI; j++) {
-        const Fr* src = A.tabs[blk.in_idx[j]] + 2 * q;
-        Fr p0 = src[0], p1 = src[1];
+        const int tj = blk.in_idx[j];
+        Fr p0, p1;
+        if (A.fold) {
+            const Fr* src = A.in[tj] + old_base;
+            const uint64_t i0 = 2 * idx, i1 = 2 * idx + 1;  // positions of the two new elements inside the row
+            if (i0 < half_old) {
+                Fr e0 = src[2 * i0], e1 = src[2 * i0 + 1];
+                p0 = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+            } else {
+                p0 = A.row_pads[tj];
+            }
+            if (i1 < half_old) {
+                Fr e0 = src[2 * i1], e1 = src[2 * i1 + 1];
+                p1 = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+            } else {
+                p1 = A.row_pads[tj];  // odd half re-padded with row_pad (vecvec.rs:432-436)
+            }
+            if ((blk.own_mask >> j) & 1) {
+                Fr* dst = A.out[tj] + 2 * q;
+                dst[0] = p0;
+                dst[1] = p1;
+            }
+        } else {
+            const Fr* src = A.in[tj] + 2 * q;
+            p0 = src[0];
+            p1 = src[1];
+        }
         a1[j] = p1;
-        a2[j] = fr_sub(fr_dbl(p1), p0);
+        a2[j] = fr_sub(fr_dbl(p1), p0);  // the "2-1" value 2 p(1) - p(0) of make_21, never stored
     }
     Fr o1[NO], o2[NO];
     MoGate<G>::eval(a1, o1);
@@ -77,80 +121,69 @@ __device__ __forceinline__ void deg2_block_eval(const Deg2EvalArgs& A, const Deg
     acc[1] = fr_add(acc[1], fr_mul(g2, w));
 }
 
-// grid = (x: pairs, y: gate blocks).  All blocks of all y reduce into the same two sums.
-__global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_eval_kernel(const __grid_constant__ Deg2EvalArgs A) {
-    __shared__ Fr smem[2 * (GKR_REDUCE_THREADS / 32)];
-    Fr acc[2] = {fr_zero(), fr_zero()};
+// grid = (x: pairs, y: gate blocks).  All blocks reduce into the same three sums.
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __grid_constant__ Deg2RoundArgs A) {
+    __shared__ Fr smem[3 * (GKR_REDUCE_THREADS / 32)];
+    Fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
     const Deg2Block blk = A.blocks[blockIdx.y];
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < A.n_pairs; q += stride) {
         Fr w;
+        uint32_t row = 0;
+        uint64_t idx = q;
         if (A.pair_off) {
-            uint32_t lo = 0, hi = A.nrows;  // largest r with pair_off[r] <= q  (empty rows repeat an offset)
+            uint32_t lo = 0, hi = A.nrows;  // largest r with pair_off[r] <= q (empty rows repeat an offset)
             while (hi - lo > 1) {
                 uint32_t mid = (lo + hi) >> 1;
                 if ((uint64_t)A.pair_off[mid] <= q) lo = mid; else hi = mid;
             }
-            // rows of length zero share their offset with the next row: step to the last row starting at <= q
-            w = fr_mul(A.eq[q - A.pair_off[lo]], A.rowcoef[lo]);
+            row = lo;
+            idx = q - A.pair_off[lo];
+            w = fr_mul(A.eq[idx], A.rowcoef[lo]);
         } else {
             w = A.eq[q];
         }
         switch (blk.gate) {
-            case GATE_AFF_L1: deg2_block_eval<GATE_AFF_L1>(A, blk, q, w, acc); break;
-            case GATE_AFF_L2: deg2_block_eval<GATE_AFF_L2>(A, blk, q, w, acc); break;
-            case GATE_AFF_L3: deg2_block_eval<GATE_AFF_L3>(A, blk, q, w, acc); break;
-            case GATE_PRJ_L1: deg2_block_eval<GATE_PRJ_L1>(A, blk, q, w, acc); break;
-            case GATE_PRJ_L2: deg2_block_eval<GATE_PRJ_L2>(A, blk, q, w, acc); break;
-            case GATE_PRJ_L3: deg2_block_eval<GATE_PRJ_L3>(A, blk, q, w, acc); break;
-            case GATE_BITCHECK: deg2_block_eval<GATE_BITCHECK>(A, blk, q, w, acc); break;
-            case GATE_LOGUP_LAYER: deg2_block_eval<GATE_LOGUP_LAYER>(A, blk, q, w, acc); break;
-            case GATE_ADD_INVERSES: deg2_block_eval<GATE_ADD_INVERSES>(A, blk, q, w, acc); break;
+            case GATE_AFF_L1: deg2_block_round<GATE_AFF_L1>(A, blk, q, row, idx, w, acc); break;
+            case GATE_AFF_L2: deg2_block_round<GATE_AFF_L2>(A, blk, q, row, idx, w, acc); break;
+            case GATE_AFF_L3: deg2_block_round<GATE_AFF_L3>(A, blk, q, row, idx, w, acc); break;
+            case GATE_PRJ_L1: deg2_block_round<GATE_PRJ_L1>(A, blk, q, row, idx, w, acc); break;
+            case GATE_PRJ_L2: deg2_block_round<GATE_PRJ_L2>(A, blk, q, row, idx, w, acc); break;
+            case GATE_PRJ_L3: deg2_block_round<GATE_PRJ_L3>(A, blk, q, row, idx, w, acc); break;
+            case GATE_BITCHECK: deg2_block_round<GATE_BITCHECK>(A, blk, q, row, idx, w, acc); break;
+            case GATE_LOGUP_LAYER: deg2_block_round<GATE_LOGUP_LAYER>(A, blk, q, row, idx, w, acc); break;
+            case GATE_ADD_INVERSES: deg2_block_round<GATE_ADD_INVERSES>(A, blk, q, row, idx, w, acc); break;
             default: break;
         }
     }
-    grid_reduce_fr<2>(acc, smem, A.partials, A.ticket, A.result);
-}
-
-// T = sum_rows rowcoef[row] * (1 - eq_sum(pt, len_row / 2)): the closed form of src/utils.rs:265-291 per row
-struct Deg2PadArgs {
-    const uint32_t* pair_off;
-    uint32_t nrows;
-    const Fr* rowcoef;
-    const Fr* pt;  // the row variables of this round's eq table (n_pt of them), pt[0] <-> most significant bit
-    uint32_t n_pt;
-    Fr* partials;
-    unsigned int* ticket;
-    Fr* result;
-};
-
-__global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_pad_kernel(const __grid_constant__ Deg2PadArgs A) {
-    __shared__ Fr smem[GKR_REDUCE_THREADS / 32];
-    Fr acc[1] = {fr_zero()};
-    const Fr one = fr_one();
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < A.nrows; r += gridDim.x * blockDim.x) {
-        uint64_t k = A.pair_off[r + 1] - A.pair_off[r];
-        Fr s;  // eq_sum(pt, k)
-        if (k >= ((uint64_t)1 << A.n_pt)) {
-            s = one;
-        } else {
-            Fr mult = one;
-            s = fr_zero();
-            for (uint32_t i = 0; i < A.n_pt; i++) {
-                uint32_t bit = (uint32_t)(k >> (A.n_pt - i - 1)) & 1u;
-                Fr p = A.pt[i];
-                if (bit) {
-                    Fr nm = fr_mul(mult, p);
-                    s = fr_add(s, fr_sub(mult, nm));
-                    mult = nm;
-                } else {
-                    mult = fr_mul(mult, fr_sub(one, p));
+    // T = sum_rows rowcoef[row] * (1 - eq_sum(pt, len_row / 2)): closed form of src/utils.rs:265-291 per row
+    // (vecvec_eq.rs:344-369), computed once by the y == 0 slice of the grid
+    if (A.do_pad && blockIdx.y == 0) {
+        const Fr one = fr_one();
+        for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.nrows; r += stride) {
+            uint64_t k = A.pair_off[r + 1] - A.pair_off[r];
+            Fr s;
+            if (k >= ((uint64_t)1 << A.n_pt)) {
+                s = one;
+            } else {
+                Fr mult = one;
+                s = fr_zero();
+                for (uint32_t i = 0; i < A.n_pt; i++) {
+                    uint32_t bit = (uint32_t)(k >> (A.n_pt - i - 1)) & 1u;
+                    Fr p = A.pt[i];
+                    if (bit) {
+                        Fr nm = fr_mul(mult, p);
+                        s = fr_add(s, fr_sub(mult, nm));
+                        mult = nm;
+                    } else {
+                        mult = fr_mul(mult, fr_sub(one, p));
+                    }
                 }
             }
+            acc[2] = fr_add(acc[2], fr_mul(A.rowcoef[r], fr_sub(one, s)));
         }
-        acc[0] = fr_add(acc[0], fr_mul(A.rowcoef[r], fr_sub(one, s)));
     }
-    grid_reduce_fr<1>(acc, smem, A.partials, A.ticket, A.result);
+    grid_reduce_to_host<3>(acc, smem, A.o);
 }
 
 // ragged fold (VecVecPolynomial::bind_21): grid.y = table
@@ -266,6 +299,7 @@ static std::vector<Deg2Block> expand_blocks(const gkr::GateStack& gs) {
                 for (int x : idx) b.in_idx[c++] = in_off + x;
                 for (; c < 6; c++) b.in_idx[c] = 0;
                 b.out_off = out_off + ooff;
+                b.own_mask = 0;
                 out.push_back(b);
             };
             switch (gs.gate[p]) {
@@ -293,6 +327,17 @@ static std::vector<Deg2Block> expand_blocks(const gkr::GateStack& gs) {
             in_off += ni;
             out_off += no;
         }
+    }
+    // every table is folded and written by exactly one block: the first that reads it
+    std::vector<char> owned(in_off, 0);
+    for (auto& b : out) {
+        int ni = 0, no = 0;
+        gkr::base_gate_io(b.gate, &ni, &no);
+        for (int k = 0; k < ni; k++)
+            if (!owned[b.in_idx[k]]) {
+                owned[b.in_idx[k]] = 1;
+                b.own_mask |= 1 << k;
+            }
     }
     return out;
 }
@@ -341,7 +386,7 @@ class Deg2SO : public gkr_so {
     // data
     Fr* slab[2] = {nullptr, nullptr};
     const Fr** d_tabs[3] = {nullptr, nullptr, nullptr};  // device pointer arrays: [0] inputs, [1]/[2] ping-pong
-    std::vector<const Fr*> h_cur;
+    std::vector<const Fr*> h_sets[3];  // host copies of the three pointer arrays
     int cur_set = 0;
     Deg2Block* d_blocks = nullptr;
     int n_blocks = 0;
@@ -370,49 +415,51 @@ class Deg2SO : public gkr_so {
         if (slot >= 0) gkr_result_slot_release(ctx, slot);
     }
 
-    Fr* res_dev() const { return ctx->result_dev + (size_t)slot * GKR_MAX_DEG; }
-    Fr* res_host() const { return ctx->result_host + (size_t)slot * GKR_MAX_DEG; }
     uint32_t binding_idx() const { return n_vars - 1 - round_idx; }
+    uint32_t pending_blocks = 0;
 
-    int launch_eval() {
-        const uint64_t n_pairs = totals[round_idx] / 2;
-        Deg2EvalArgs a;
-        a.tabs = d_tabs[cur_set];
+    // launches the round kernel for round `b` (= round_idx at call time); with fold_t != nullptr it first folds round b-1
+    int launch_round(uint32_t b, const gkr::FrH* fold_t) {
+        const uint64_t n_pairs = totals[b] / 2;
+        Deg2RoundArgs a;
+        int dst_set = cur_set;
+        if (fold_t) {
+            dst_set = (cur_set == 1) ? 2 : 1;
+            a.in = d_tabs[cur_set];
+            a.out = (Fr* const*)d_tabs[dst_set];
+            a.off_old = d_off + (size_t)(b - 1) * (nrows + 1);
+            a.fold = 1;
+            a.t = fr_from_host(*fold_t);
+        } else {
+            a.in = d_tabs[cur_set];
+            a.out = nullptr;
+            a.off_old = nullptr;
+            a.fold = 0;
+            a.t = fr_from_host(gkr::frh::ZERO);
+        }
         a.blocks = d_blocks;
         a.gammas = d_gammas;
-        a.pair_off = is_vecvec ? d_poff + (size_t)round_idx * (nrows + 1) : nullptr;
+        a.pair_off = is_vecvec ? d_poff + (size_t)b * (nrows + 1) : nullptr;
         a.nrows = nrows;
-        a.eq = d_eq + eq_off[round_idx];
+        a.eq = d_eq + eq_off[b];
         a.rowcoef = d_rowcoef;
         a.n_pairs = n_pairs;
-        a.partials = ctx->partials;
-        a.ticket = ctx->ticket;
-        a.result = res_dev();
-        if (n_pairs > 0) {
-            uint64_t want = (n_pairs + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
-            uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->num_sms * 3, GKR_MAX_BLOCKS / 2) / n_blocks);
-            dim3 grid((unsigned)std::max<uint64_t>(1, std::min(want, cap)), (unsigned)n_blocks);
-            deg2_eval_kernel<<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(a);
-            ctx->launches++;
-            GKR_CUDA_OK(ctx, cudaGetLastError());
-        } else {
-            GKR_CUDA_OK(ctx, cudaMemsetAsync(res_dev(), 0, 2 * sizeof(Fr), ctx->stream));
-        }
-        if (is_vecvec) {
-            Deg2PadArgs p;
-            p.pair_off = d_poff + (size_t)round_idx * (nrows + 1);
-            p.nrows = nrows;
-            p.rowcoef = d_rowcoef;
-            p.pt = d_pt_row;
-            p.n_pt = m_row - round_idx;  // row variables still in the eq table of this round
-            p.partials = ctx->partials;
-            p.ticket = ctx->ticket;
-            p.result = res_dev() + 2;
-            unsigned grid = (unsigned)std::max<uint32_t>(1, std::min<uint32_t>((nrows + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS, 256));
-            deg2_pad_kernel<<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(p);
-            ctx->launches++;
-            GKR_CUDA_OK(ctx, cudaGetLastError());
-        }
+        a.row_pads = d_pads;
+        a.pt = d_pt_row;
+        a.n_pt = m_row >= b ? m_row - b : 0;
+        a.do_pad = is_vecvec ? 1 : 0;
+        a.o = ctx->round_out(slot);
+        uint64_t work = std::max<uint64_t>(n_pairs, is_vecvec ? nrows : 1);
+        uint64_t want = (work + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
+        uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->num_sms * 3, GKR_MAX_BLOCKS) / n_blocks);
+        dim3 grid((unsigned)std::max<uint64_t>(1, std::min(want, cap)), (unsigned)n_blocks);
+        unsigned threads = GKR_REDUCE_THREADS;
+        if (grid.x == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (work + 31) / 32 * 32));
+        pending_blocks = grid.x * grid.y;
+        deg2_round_kernel<<<grid, threads, 0, ctx->stream>>>(a);
+        ctx->launches++;
+        GKR_CUDA_OK(ctx, cudaGetLastError());
+        cur_set = dst_set;
         return GKR_OK;
     }
 
@@ -422,23 +469,20 @@ class Deg2SO : public gkr_so {
         if (cached) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly called twice in a round");  // dense_eq.rs:109-111
         using namespace gkr::frh;
         if (!sums_pending) {
-            int rc = launch_eval();
+            int rc = launch_round(round_idx, nullptr);
             if (rc) return rc;
         }
-        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        gkr::FrH r[3];
+        int rcw = gkr_slot_wait(ctx, slot, pending_blocks, 3, r);
+        if (rcw) return rcw;
         sums_pending = false;
-        const Fr* r = res_host();
-        gkr::FrH s1 = fr_to_host(r[0]), s2 = fr_to_host(r[1]);
-        gkr::FrH padterm;
+        gkr::FrH padterm = ZERO;
         if (is_vecvec) {
-            padterm = mul(padG, fr_to_host(r[2]));
+            padterm = mul(padG, r[2]);
             if (has_col_tail) padterm = add(padterm, mul(colpadG, col_tail));
-        } else {
-            // trailing_sum = 1 - sum_{idx < len/2} eq[idx]   (dense_eq.rs:141); tables are full here, so it is zero
-            padterm = ZERO;
-        }
-        gkr::FrH total1 = mul(add(s1, padterm), multiplier);
-        gkr::FrH total2 = mul(add(s2, padterm), multiplier);
+        }  // dense object: tables are full, trailing_sum (dense_eq.rs:141) is zero
+        gkr::FrH total1 = mul(add(r[0], padterm), multiplier);
+        gkr::FrH total2 = mul(add(r[1], padterm), multiplier);
         const uint32_t b = binding_idx();
         from12(total1, total2, point[b], eq0_inv[b], claim_, evals);
         cached = true;
@@ -447,8 +491,9 @@ class Deg2SO : public gkr_so {
         return GKR_OK;
     }
 
+    // plain fold of the current round into the next layout (last round of the dense object: nothing left to evaluate)
     int fold_to_next(const gkr::FrH& t) {
-        const uint32_t b = round_idx;  // folding round b -> b + 1
+        const uint32_t b = round_idx;
         int dst_set = (cur_set == 1) ? 2 : 1;
         VvFoldArgs f;
         f.in = d_tabs[cur_set];
@@ -479,17 +524,18 @@ class Deg2SO : public gkr_so {
         gkr::FrH new_claim = interpolate_eval(evals, 4, t);
         gkr::FrH new_mult = mul(multiplier, eq1(point[b], t));
         if (is_vecvec && round_idx + 1 == n_sparse) return bind_into_dense(t, new_claim, new_mult);
-        int rc = fold_to_next(t);
+        int rc;
+        if (round_idx + 1 < n_sparse) {
+            rc = launch_round(round_idx + 1, &t);  // fused: fold round b, evaluate round b+1
+            sums_pending = true;
+        } else {
+            rc = fold_to_next(t);
+        }
         if (rc) return rc;
         multiplier = new_mult;
         claim_ = new_claim;
         cached = false;
         round_idx++;
-        if (round_idx < n_sparse) {
-            rc = launch_eval();
-            if (rc) return rc;
-            sums_pending = true;
-        }
         return GKR_OK;
     }
 
@@ -499,13 +545,11 @@ class Deg2SO : public gkr_so {
         if (dense) return dense->final_evals(out);
         if (is_vecvec) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: sparse stage has no final evals (vecvec_eq.rs:390-393)");
         if (round_idx != n_sparse) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: can only be called after the last round");
-        std::vector<const Fr*> ptrs(P);
-        GKR_CUDA_OK(ctx, cudaMemcpyAsync(ptrs.data(), d_tabs[cur_set], sizeof(Fr*) * P, cudaMemcpyDeviceToHost, ctx->stream));
+        const std::vector<const Fr*>& ptrs = h_sets[cur_set];
+        Fr* stage = ctx->slots_host[slot].part;  // pinned staging: P async copies, one synchronisation
+        for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&stage[j], ptrs[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
         GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        std::vector<Fr> v(P);
-        for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&v[j], ptrs[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = 0; j < P; j++) out[j] = fr_to_host(v[j]);
+        for (int j = 0; j < P; j++) out[j] = fr_to_host(stage[j]);
         return GKR_OK;
     }
 
@@ -670,6 +714,9 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     }
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[1], p1.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[2], p2.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
+    h_sets[0] = inputs;
+    h_sets[1] = p1;
+    h_sets[2] = p2;
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
     cur_set = 0;
     multiplier = ONE;

@@ -20,9 +20,7 @@ struct DenseRoundArgs {
     uint64_t n_items;  // MODE 0/1: number of pairs evaluated; MODE 2: number of elements
     Fr t;
     GateConsts consts;
-    Fr* partials;
-    unsigned int* ticket;
-    Fr* result;
+    RoundOut o;
 };
 
 // MODE 0: evaluate pairs (2i, 2i+1) of `in`                      (first round: nothing to fold yet)
@@ -74,7 +72,7 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const _
             }
         }
     }
-    grid_reduce_fr<NACC>(acc, smem, A.partials, A.ticket, A.result);
+    grid_reduce_to_host<NACC>(acc, smem, A.o);
 }
 
 // out[j][i] = in[j][2i] + t (in[j][2i+1] - in[j][2i])   -- used for the last round (one pair -> one value)
@@ -122,7 +120,7 @@ static int dispatch_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t param
 }
 
 template <class SO, int MODE>
-static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args) {
+static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t* n_blocks_out) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int b = 0;
@@ -132,9 +130,13 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args) {
     uint64_t want = (args.n_items + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
     uint64_t cap = std::min<uint64_t>((uint64_t)ctx->num_sms * blocks_per_sm, GKR_MAX_BLOCKS);
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+    // small rounds: one block no wider than the work, so the shuffle/shared-memory reduction stays shallow
+    unsigned threads = GKR_REDUCE_THREADS;
+    if (grid == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (args.n_items + 31) / 32 * 32));
+    *n_blocks_out = grid;
     {
         GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : (MODE == 1 ? GKR_K_DENSE_FOLD_EVAL : GKR_K_DENSE_SUM), args.n_items);
-        dense_round_kernel<SO, MODE><<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(args);
+        dense_round_kernel<SO, MODE><<<grid, threads, 0, ctx->stream>>>(args);
     }
     ctx->launches++;
     GKR_CUDA_OK(ctx, cudaGetLastError());
@@ -170,6 +172,7 @@ class DenseSO : public gkr_so {
     Fr* buf[2][GKR_MAX_POLYS];
     int next_buf = 0;
     bool sums_pending = false;  // a launched kernel will deliver the sums of the current round
+    uint32_t pending_blocks = 0;
     bool cached = false;
     gkr::FrH evals[GKR_MAX_DEG + 1];
     int slot = -1;
@@ -179,14 +182,9 @@ class DenseSO : public gkr_so {
         if (slot >= 0) gkr_result_slot_release(ctx, slot);
     }
 
-    Fr* result_dev() const { return ctx->result_dev + (size_t)slot * GKR_MAX_DEG; }
-    Fr* result_host() const { return ctx->result_host + (size_t)slot * GKR_MAX_DEG; }
-
     void fill_common(DenseRoundArgs& a) {
         a.consts = consts;
-        a.partials = ctx->partials;
-        a.ticket = ctx->ticket;
-        a.result = result_dev();
+        a.o = ctx->round_out(slot);
     }
 
     int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
@@ -198,14 +196,13 @@ class DenseSO : public gkr_so {
                 a.n_items = (uint64_t)1 << (num_vars - round_idx - 1);
                 fill_common(a);
                 int rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
-                    return launch_dense_round<decltype(so), 0>(ctx, a);
+                    return launch_dense_round<decltype(so), 0>(ctx, a, &pending_blocks);
                 });
                 if (rc) return rc;
             }
-            GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+            int rcw = gkr_slot_wait(ctx, slot, pending_blocks, DEG, evals + 1);
+            if (rcw) return rcw;
             sums_pending = false;
-            const Fr* r = result_host();
-            for (int s = 0; s < DEG; s++) evals[s + 1] = fr_to_host(r[s]);
             evals[0] = gkr::frh::sub(claim_, evals[1]);  // sumcheck.rs:325
             cached = true;
         }
@@ -235,7 +232,7 @@ class DenseSO : public gkr_so {
         if (new_len >= 2) {
             a.n_items = new_len >> 1;
             int rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
-                return launch_dense_round<decltype(so), 1>(ctx, a);
+                return launch_dense_round<decltype(so), 1>(ctx, a, &pending_blocks);
             });
             if (rc) return rc;
             sums_pending = true;
@@ -255,12 +252,10 @@ class DenseSO : public gkr_so {
 
     int final_evals(gkr::FrH* out) override {
         if (round_idx != num_vars) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: can only be called after the last round");
-        for (int j = 0; j < P; j++) {
-            Fr v;
-            GKR_CUDA_OK(ctx, cudaMemcpyAsync(&v, cur[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-            GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-            out[j] = fr_to_host(v);
-        }
+        Fr* stage = ctx->slots_host[slot].part;  // pinned staging: P async copies, one synchronisation
+        for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&stage[j], cur[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        for (int j = 0; j < P; j++) out[j] = fr_to_host(stage[j]);
         return GKR_OK;
     }
 
@@ -331,15 +326,10 @@ int gkr_dense_gate_sum_impl(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_p
     a.n_items = tables[0]->n;
     int slot = gkr_result_slot_acquire(ctx);
     if (slot < 0) return ctx->fail(GKR_ERR_UNSUPPORTED, "no free result slot");
-    a.partials = ctx->partials;
-    a.ticket = ctx->ticket;
-    a.result = ctx->result_dev + (size_t)slot * GKR_MAX_DEG;
-    rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) { return launch_dense_round<decltype(so), 2>(ctx, a); });
-    if (rc == GKR_OK) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
-        else *out = fr_to_host(ctx->result_host[(size_t)slot * GKR_MAX_DEG]);
-    }
+    a.o = ctx->round_out(slot);
+    uint32_t nb = 0;
+    rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) { return launch_dense_round<decltype(so), 2>(ctx, a, &nb); });
+    if (rc == GKR_OK) rc = gkr_slot_wait(ctx, slot, nb, 1, out);
     gkr_result_slot_release(ctx, slot);
     return rc;
 }

@@ -5,8 +5,6 @@
 #include <mutex>
 #include "common.cuh"
 
-#define GKR_RESULT_SLOTS 256
-
 static std::mutex g_slot_mutex;
 struct SlotPool {
     std::vector<int> free_list;
@@ -32,6 +30,31 @@ void gkr_result_slot_release(gkr_ctx* ctx, int slot) {
     std::lock_guard<std::mutex> lk(g_slot_mutex);
     SlotPool* p = pool_of(ctx);
     if (p) p->free_list.push_back(slot);
+}
+
+// Spin on the slot's flag (written by the last block into mapped host memory) and fold the per-block partials.
+// Every ~64k spins the stream is queried so that a faulted or vanished kernel turns into an error, never a hang.
+int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out) {
+    GkrSlot* s = &ctx->slots_host[slot];
+    const uint32_t seq = ctx->slot_seq[slot];
+    uint64_t spins = 0;
+    while (s->flag != seq) {
+        if ((++spins & 0xffff) == 0) {
+            cudaError_t q = cudaStreamQuery(ctx->stream);
+            if (q == cudaSuccess) {
+                if (s->flag == seq) break;
+                return ctx->fail(GKR_ERR_CUDA, "round kernel finished without publishing its result");
+            }
+            if (q != cudaErrorNotReady) return ctx->fail(GKR_ERR_CUDA, std::string("round kernel failed: ") + cudaGetErrorString(q));
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    for (int a = 0; a < n_acc; a++) {
+        gkr::FrH acc = gkr::frh::ZERO;
+        for (uint32_t b = 0; b < n_blocks; b++) acc = gkr::frh::add(acc, fr_to_host(s->part[(size_t)b * n_acc + a]));
+        out[a] = acc;
+    }
+    return GKR_OK;
 }
 
 extern "C" int gkr_version(void) { return 1; }
@@ -67,10 +90,15 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     if ((e = cudaMemset(ctx->ticket, 0, sizeof(unsigned int))) != cudaSuccess) return bail(e);
     if ((e = cudaHostAlloc(&ctx->result_host, sizeof(Fr) * GKR_RESULT_SLOTS * GKR_MAX_DEG, cudaHostAllocMapped)) != cudaSuccess) return bail(e);
     if ((e = cudaHostGetDevicePointer(&ctx->result_dev, ctx->result_host, 0)) != cudaSuccess) return bail(e);
+    if ((e = cudaHostAlloc(&ctx->slots_host, sizeof(GkrSlot) * GKR_RESULT_SLOTS, cudaHostAllocMapped)) != cudaSuccess) return bail(e);
+    if ((e = cudaHostGetDevicePointer(&ctx->slots_dev, ctx->slots_host, 0)) != cudaSuccess) return bail(e);
+    for (int i = 0; i < GKR_RESULT_SLOTS; i++) ctx->slots_host[i].flag = 0;
+    if ((e = cudaMalloc(&ctx->slot_tickets, sizeof(unsigned int) * GKR_RESULT_SLOTS)) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->slot_tickets, 0, sizeof(unsigned int) * GKR_RESULT_SLOTS)) != cudaSuccess) return bail(e);
     {
         std::lock_guard<std::mutex> lk(g_slot_mutex);
         SlotPool* p = new SlotPool();
-        for (int i = GKR_RESULT_SLOTS - 1; i >= 0; i--) p->free_list.push_back(i);
+        for (int i = GKR_RESULT_SLOTS - 1; i >= 0; i--) p->free_list.push_back(i);  // indices into ctx->slots_*
         g_pools.push_back({ctx, p});
     }
     *out = ctx;
@@ -93,6 +121,8 @@ extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
     if (ctx->partials) cudaFree(ctx->partials);
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->result_host) cudaFreeHost(ctx->result_host);
+    if (ctx->slots_host) cudaFreeHost(ctx->slots_host);
+    if (ctx->slot_tickets) cudaFree(ctx->slot_tickets);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -38,11 +38,7 @@ def main():
     polys = []
     for j, (rp, cp) in enumerate([(0, 0), (1, 1), (0, 0)]):
         flat = ctx.synth(100 + j, total).download() if j < 2 else np.tile(g.MONT_ONE, (total, 1))
-        h = g._vp()
-        rpl, cpl = to_limb1(rp), to_limb1(cp)
-        ctx.check(ctx.lib.gkr_vecvec_upload(ctx.h, flat.ctypes.data_as(g._vp), lens.ctypes.data_as(g._vp), nrows, rpl.ctypes.data_as(g._vp),
-                                            cpl.ctypes.data_as(g._vp), a.x, col_log, g.C.byref(h)))
-        polys.append(g.VecVec(ctx, h))
+        polys.append(ctx.upload_vecvec_flat(flat, lens, to_limb1(rp), to_limb1(cp), a.x, col_log))
     num_vars = a.x + col_log
     res = []
     for rep in range(a.reps + 1):
