@@ -60,6 +60,7 @@ def _sig(lib):
     f("gkr_ctx_launch_count", C.c_uint64, _vp)
     f("gkr_ctx_stream", _vp, _vp)
     f("gkr_ctx_timing_enable", C.c_int, _vp, C.c_int)
+    f("gkr_ctx_set_fast_fold", C.c_int, _vp, C.c_int)
     f("gkr_ctx_timing_read", C.c_int, _vp, _vp, _vp, _vp, C.c_int)
     f("gkr_bench_modmul", C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
     f("gkr_table_upload", C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp))
@@ -161,6 +162,9 @@ class Context:
     @property
     def stream(self) -> int:
         return int(self.lib.gkr_ctx_stream(self.h) or 0)
+
+    def set_fast_fold(self, on: bool = True):
+        self.check(self.lib.gkr_ctx_set_fast_fold(self.h, 1 if on else 0))
 
     def timing_enable(self, on: bool = True):
         self.check(self.lib.gkr_ctx_timing_enable(self.h, 1 if on else 0))

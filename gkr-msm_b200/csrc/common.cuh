@@ -38,6 +38,7 @@ struct gkr_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    bool no_fast_fold = false;      // test hook (GKR_NO_FAST_FOLD=1): always fold with the full Montgomery product
     Fr* partials = nullptr;         // [GKR_MAX_BLOCKS * GKR_MAX_DEG] device scratch (device-side two-stage reductions)
     unsigned int* ticket = nullptr; // device counter for the last-block pattern
     Fr* result_host = nullptr;      // pinned + mapped scratch for one-shot reductions (gate sums)

@@ -18,7 +18,8 @@ struct DenseRoundArgs {
     const Fr* in[GKR_MAX_POLYS];
     Fr* out[GKR_MAX_POLYS];
     uint64_t n_items;  // MODE 0/1: number of pairs evaluated; MODE 2: number of elements
-    Fr t;
+    Fr t;              // challenge, Montgomery form (general fold)
+    uint32_t t128[4];  // challenge as a plain 128-bit integer (FAST fold)
     GateConsts consts;
     RoundOut o;
 };
@@ -26,14 +27,23 @@ struct DenseRoundArgs {
 // MODE 0: evaluate pairs (2i, 2i+1) of `in`                      (first round: nothing to fold yet)
 // MODE 1: fold quads (4i..4i+3) of `in` into `out` (2i, 2i+1), then evaluate that fresh pair
 // MODE 2: plain sum of f over all elements (claim_hint computation), one accumulator
-template <class SO, int MODE>
+//
+// Integer-pipe economy (this kernel is bound by the 32x32->64 multiplier, not by HBM: DESIGN.md section 3):
+//   * FAST folds: a Fiat-Shamir challenge of transcript.challenge(128) is a 128-bit integer, so
+//     e0 + t (e1 - e0) is a 4x8-limb product plus a 4-round Montgomery reduction (fr_fold128, 56 wide
+//     multiply-adds instead of 112).  The folded table then carries a factor 2^-128 per fast fold; every gate
+//     on this path is homogeneous in the tables, so the round sums come out scaled by a known power of it
+//     and the host multiplies it away (DenseSO::unscale_*): the round polynomials stay bit-exact.
+//   * the last multiplication of every gate evaluation is accumulated UNREDUCED (FrWide, 64 instead of 112)
+//     and each thread reduces its accumulators once.
+template <class SO, int MODE, bool FAST>
 __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const __grid_constant__ DenseRoundArgs A) {
     constexpr int P = SO::P;
     constexpr int NACC = (MODE == 2) ? 1 : SO::DEG;
     __shared__ Fr smem[NACC * (GKR_REDUCE_THREADS / 32)];
-    Fr acc[NACC];
+    FrWide wacc[NACC];
 #pragma unroll
-    for (int s = 0; s < NACC; s++) acc[s] = fr_zero();
+    for (int s = 0; s < NACC; s++) frw_zero(wacc[s]);
 
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_items; i += stride) {
@@ -41,7 +51,7 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const _
         if (MODE == 2) {
 #pragma unroll
             for (int j = 0; j < P; j++) a[j] = A.in[j][i];
-            acc[0] = fr_add(acc[0], SO::eval(a, A.consts));
+            SO::mac(wacc[0], a, A.consts);
         } else {
             Fr d[P];
 #pragma unroll
@@ -50,8 +60,13 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const _
                 if (MODE == 1) {
                     const Fr* src = A.in[j] + 4 * i;
                     Fr e0 = src[0], e1 = src[1], e2 = src[2], e3 = src[3];
-                    lo = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
-                    hi = fr_add(e2, fr_mul(A.t, fr_sub(e3, e2)));
+                    if (FAST) {
+                        lo = fr_fold128(e0, fr_sub(e1, e0), A.t128);
+                        hi = fr_fold128(e2, fr_sub(e3, e2), A.t128);
+                    } else {
+                        lo = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+                        hi = fr_add(e2, fr_mul(A.t, fr_sub(e3, e2)));
+                    }
                     Fr* dst = A.out[j] + 2 * i;
                     dst[0] = lo;
                     dst[1] = hi;
@@ -63,15 +78,18 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const _
                 a[j] = hi;
                 d[j] = fr_sub(hi, lo);
             }
-            acc[0] = fr_add(acc[0], SO::eval(a, A.consts));
+            SO::mac(wacc[0], a, A.consts);
 #pragma unroll
             for (int s = 1; s < SO::DEG; s++) {
 #pragma unroll
                 for (int j = 0; j < P; j++) a[j] = fr_add(a[j], d[j]);
-                acc[s] = fr_add(acc[s], SO::eval(a, A.consts));
+                SO::mac(wacc[s], a, A.consts);
             }
         }
     }
+    Fr acc[NACC];
+#pragma unroll
+    for (int s = 0; s < NACC; s++) acc[s] = frw_reduce(wacc[s]);
     grid_reduce_to_host<NACC>(acc, smem, A.o);
 }
 
@@ -119,12 +137,12 @@ static int dispatch_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t param
     return ctx->fail(GKR_ERR_ARG, "unknown so_kind");
 }
 
-template <class SO, int MODE>
+template <class SO, int MODE, bool FAST = false>
 static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t* n_blocks_out) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int b = 0;
-        GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_kernel<SO, MODE>, GKR_REDUCE_THREADS, 0));
+        GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_kernel<SO, MODE, FAST>, GKR_REDUCE_THREADS, 0));
         blocks_per_sm = std::max(b, 1);
     }
     uint64_t want = (args.n_items + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
@@ -136,7 +154,7 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
     *n_blocks_out = grid;
     {
         GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : (MODE == 1 ? GKR_K_DENSE_FOLD_EVAL : GKR_K_DENSE_SUM), args.n_items);
-        dense_round_kernel<SO, MODE><<<grid, threads, 0, ctx->stream>>>(args);
+        dense_round_kernel<SO, MODE, FAST><<<grid, threads, 0, ctx->stream>>>(args);
     }
     ctx->launches++;
     GKR_CUDA_OK(ctx, cudaGetLastError());
@@ -144,7 +162,8 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
 }
 
 struct DenseSoInfo {
-    int P, DEG;
+    int P, DEG, HDEG, N_OUTS;
+    int gamma_shift[GKR_MAX_GATE_CONSTS];
 };
 
 static int dense_so_info(gkr_ctx* ctx, int so_kind, int gate, uint32_t param, DenseSoInfo* info) {
@@ -152,6 +171,9 @@ static int dense_so_info(gkr_ctx* ctx, int so_kind, int gate, uint32_t param, De
         using SO = decltype(so);
         info->P = SO::P;
         info->DEG = SO::DEG;
+        info->HDEG = SO::HDEG;
+        info->N_OUTS = SO::N_OUTS;
+        for (int i = 0; i < GKR_MAX_GATE_CONSTS; i++) info->gamma_shift[i] = i < SO::N_OUTS ? SO::gamma_shift(i) : 0;
         return (int)GKR_OK;
     });
 }
@@ -159,12 +181,27 @@ static int dense_so_info(gkr_ctx* ctx, int so_kind, int gate, uint32_t param, De
 int gkr_result_slot_acquire(gkr_ctx* ctx);
 void gkr_result_slot_release(gkr_ctx* ctx, int slot);
 
+// 2^128 and 2^-128 in Montgomery form (host side of the FAST folds)
+static const gkr::FrH& pow128_m() {
+    static const gkr::FrH v = gkr::frh::mul(gkr::FrH{{0, 0, 1, 0}}, gkr::frh::R2);
+    return v;
+}
+static const gkr::FrH& inv128_m() {
+    static const gkr::FrH v = gkr::frh::inverse(pow128_m());
+    return v;
+}
+
 class DenseSO : public gkr_so {
    public:
     int so_kind, gate;
     uint32_t gate_param;
-    GateConsts consts;
+    GateConsts consts;                      // device view for the CURRENT scale of the tables
+    gkr::FrH base_consts[GKR_MAX_GATE_CONSTS];  // the caller's gate constants
+    DenseSoInfo info;
     int P = 0, DEG = 0;
+    // FAST folds leave the tables scaled by sigma = 2^(-128 fast_folds); sums come out scaled by sigma^HDEG
+    uint32_t fast_folds = 0;
+    gkr::FrH sigma = gkr::frh::ONE, unscale_sum = gkr::frh::ONE, unscale_val = gkr::frh::ONE;
     uint32_t num_vars = 0, round_idx = 0;
     gkr::FrH claim_;
     const Fr* cur[GKR_MAX_POLYS];  // current tables (round 0: the caller's tables, untouched)
@@ -187,6 +224,18 @@ class DenseSO : public gkr_so {
         a.o = ctx->round_out(slot);
     }
 
+    // gate constants for tables scaled by sigma: gamma^i * sigma^gamma_shift(i)   (gates.cuh, gamma_eval_scaled)
+    void rescale_consts() {
+        for (int i = 0; i < GKR_MAX_GATE_CONSTS; i++) {
+            gkr::FrH g = base_consts[i];
+            if (i < info.N_OUTS && info.gamma_shift[i] > 0) {
+                if (i == 0) g = gkr::frh::ONE;  // output 0 has coefficient one in the reference (sumcheck.rs:724-731)
+                for (int k = 0; k < info.gamma_shift[i]; k++) g = gkr::frh::mul(g, sigma);
+            }
+            consts.g[i] = fr_from_host(g);
+        }
+    }
+
     int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
         if (round_idx >= num_vars) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly: the protocol has already ended");
         if (!cached) {
@@ -202,6 +251,8 @@ class DenseSO : public gkr_so {
             }
             int rcw = gkr_slot_wait(ctx, slot, pending_blocks, DEG, evals + 1);
             if (rcw) return rcw;
+            if (fast_folds)
+                for (int s = 1; s <= DEG; s++) evals[s] = gkr::frh::mul(evals[s], unscale_sum);
             sums_pending = false;
             evals[0] = gkr::frh::sub(claim_, evals[1]);  // sumcheck.rs:325
             cached = true;
@@ -228,11 +279,27 @@ class DenseSO : public gkr_so {
         DenseRoundArgs a;
         for (int j = 0; j < P; j++) { a.in[j] = cur[j]; a.out[j] = buf[next_buf][j]; }
         a.t = fr_from_host(t);
+        // transcript.challenge(128) is a 128-bit integer: fold with fr_fold128 when the gate is homogeneous
+        const gkr::FrH t_plain = gkr::frh::mul(t, gkr::FrH{{1, 0, 0, 0}});
+        const bool fast = info.HDEG > 0 && new_len >= 2 && t_plain.v[2] == 0 && t_plain.v[3] == 0 && !ctx->no_fast_fold;
+        if (fast) {
+            a.t128[0] = (uint32_t)t_plain.v[0]; a.t128[1] = (uint32_t)(t_plain.v[0] >> 32);
+            a.t128[2] = (uint32_t)t_plain.v[1]; a.t128[3] = (uint32_t)(t_plain.v[1] >> 32);
+            fast_folds++;
+            sigma = gkr::frh::mul(sigma, inv128_m());
+            unscale_val = gkr::frh::mul(unscale_val, pow128_m());
+            for (int k = 0; k < info.HDEG; k++) unscale_sum = gkr::frh::mul(unscale_sum, pow128_m());
+            rescale_consts();
+        }
         fill_common(a);
         if (new_len >= 2) {
             a.n_items = new_len >> 1;
             int rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
-                return launch_dense_round<decltype(so), 1>(ctx, a, &pending_blocks);
+                using SO = decltype(so);
+                if constexpr (SO::HDEG > 0) {
+                    if (fast) return launch_dense_round<SO, 1, true>(ctx, a, &pending_blocks);
+                }
+                return launch_dense_round<SO, 1, false>(ctx, a, &pending_blocks);
             });
             if (rc) return rc;
             sums_pending = true;
@@ -255,7 +322,10 @@ class DenseSO : public gkr_so {
         Fr* stage = ctx->slots_host[slot].part;  // pinned staging: P async copies, one synchronisation
         for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&stage[j], cur[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
         GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = 0; j < P; j++) out[j] = fr_to_host(stage[j]);
+        for (int j = 0; j < P; j++) {
+            out[j] = fr_to_host(stage[j]);
+            if (fast_folds) out[j] = gkr::frh::mul(out[j], unscale_val);
+        }
         return GKR_OK;
     }
 
@@ -297,6 +367,9 @@ int gkr_make_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, 
     so->gate_param = gate_param;
     rc = fill_consts(ctx, consts, n_consts, &so->consts);
     if (rc) { delete so; return rc; }
+    for (uint32_t i = 0; i < GKR_MAX_GATE_CONSTS; i++) so->base_consts[i] = i < n_consts ? consts[i] : gkr::frh::ZERO;
+    so->info = info;
+    so->rescale_consts();
     so->P = info.P;
     so->DEG = info.DEG;
     so->num_vars = num_vars;
@@ -318,6 +391,7 @@ int gkr_dense_gate_sum_impl(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_p
     DenseRoundArgs a;
     rc = fill_consts(ctx, consts, n_consts, &a.consts);
     if (rc) return rc;
+    if (info.gamma_shift[0] > 0) a.consts.g[0] = fr_from_host(gkr::frh::ONE);  // gamma_eval_scaled reads g[0]
     for (uint32_t j = 0; j < n_polys; j++) {
         if (!tables[j] || tables[j]->n != tables[0]->n) return ctx->fail(GKR_ERR_ARG, "tables must have equal length");
         a.in[j] = tables[j]->d;

@@ -77,6 +77,43 @@ __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) {
     return r;
 }
 __device__ __forceinline__ Fr fr_dbl(const Fr& a) { return fr_add(a, a); }
+
+// ---- lazy reduction --------------------------------------------------------------------------------
+// FrWide: a 544-bit accumulator of UNREDUCED 512-bit products.  Montgomery reduction is linear, so a thread sums the
+// last multiplication of every gate evaluation here (64 wide multiply-adds instead of 112) and reduces once at the
+// end: sum_i REDC(x_i y_i) == REDC(sum_i x_i y_i) (mod r), bit-exact after canonicalisation.
+struct FrWide {
+    uint32_t l[17];
+};
+__device__ __forceinline__ void frw_zero(FrWide& w) {
+#pragma unroll
+    for (int i = 0; i < 17; i++) w.l[i] = 0;
+}
+__device__ __forceinline__ void frw_mac(FrWide& w, const Fr& a, const Fr& b) { fr_mac_wide_asm(w.l, a.l, b.l); }
+// canonical Montgomery reduction of the accumulator: w = L + H 2^256 + T 2^512  ->  L R^-1 + H + T R  (mod r)
+__device__ __forceinline__ Fr frw_reduce(const FrWide& w) {
+    Fr lo, hi, one_plain, top, r2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { lo.l[i] = w.l[i]; hi.l[i] = w.l[8 + i]; one_plain.l[i] = 0; top.l[i] = 0; }
+    one_plain.l[0] = 1;
+    top.l[0] = w.l[16];
+    // R^2 mod r = 0x0748d9d99f59ff1105d314967254398f2b6cedcb87925c23c999e990f3f29c6d
+    r2.l[0] = 0xf3f29c6du; r2.l[1] = 0xc999e990u; r2.l[2] = 0x87925c23u; r2.l[3] = 0x2b6cedcbu;
+    r2.l[4] = 0x7254398fu; r2.l[5] = 0x05d31496u; r2.l[6] = 0x9f59ff11u; r2.l[7] = 0x0748d9d9u;
+    Fr a = fr_mul(lo, one_plain);  // L R^-1: the CIOS bound only needs L * 1 < r R
+    Fr b;
+    fr_reduce2_asm(b.l, hi.l);     // H < 2^256 < 3 r
+    Fr c = fr_mul(top, r2);        // T * R^2 * R^-1
+    return fr_add(fr_add(a, b), c);
+}
+// (c + t * a) * 2^-128 mod r for a 128-bit t (4 plain limbs): the sumcheck fold e0 + t (e1 - e0) by a Fiat-Shamir
+// challenge of transcript.challenge(128), at half the multiplier work of a Montgomery product.  The result carries
+// an extra factor 2^-128 which the host tracks (DenseSO::fast_folds).
+__device__ __forceinline__ Fr fr_fold128(const Fr& c, const Fr& a, const uint32_t* t) {
+    Fr r;
+    fr_fold128_asm(r.l, c.l, a.l, t);
+    return r;
+}
 __device__ __forceinline__ Fr fr_neg(const Fr& a) { return fr_sub(fr_zero(), a); }
 
 // a = -5 on Bandersnatch: mul_by_a(x) = -(4x + x)   (src/utils.rs:40-43)

@@ -1,6 +1,7 @@
 // Context, device tables and table builders (eq tables, synthetic inputs).
 //   eq tables: eq_poly_sequence_from_multiplier / eq_poly_sequence_last  src/utils.rs:222-262,
 //              EqPoly::evals src/cleanup/protocols/verifier_polys.rs:31-33
+#include <cstdlib>
 #include <algorithm>
 #include <mutex>
 #include "common.cuh"
@@ -76,6 +77,7 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e);
     ctx->num_sms = prop.multiProcessorCount;
+    { const char* nf = getenv("GKR_NO_FAST_FOLD"); ctx->no_fast_fold = nf && nf[0] == '1'; }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
     {
         // stream-ordered allocator with an unbounded release threshold: after warm-up a table / ping-pong slab
@@ -323,6 +325,12 @@ extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, con
 }
 
 // ---- per-launch timing (used only by bench.py's roofline leg) ----------------------------------------------
+extern "C" int gkr_ctx_set_fast_fold(gkr_ctx* ctx, int on) {
+    if (!ctx) return GKR_ERR_ARG;
+    ctx->no_fast_fold = on == 0;
+    return GKR_OK;
+}
+
 extern "C" int gkr_ctx_timing_enable(gkr_ctx* ctx, int on) {
     if (!ctx) return GKR_ERR_ARG;
     ctx->timing = on != 0;

@@ -190,3 +190,42 @@ def test_large_synthetic_sumcheck_properties(ctx):
         cur = S.evaluate_univar(coeffs, t)
     fe = from_limbs(so.final_evals())
     assert fe[0] * fe[1] % P * fe[2] % P == cur
+
+
+@pytest.mark.parametrize("kind", ["prod3", "folded4", "logup", "add_inverses"])
+def test_fast_fold_equals_montgomery_fold_at_scale(ctx, kind):
+    """The 128-bit-challenge fold (fr_fold128 + host-side rescaling) and the plain Montgomery fold must give
+    identical round polynomials and final evaluations -- checked at 2^18, beyond the big-int oracle's reach."""
+    nv = 18
+    rng = random.Random(4242)
+    n = 1 << nv
+    if kind == "prod3":
+        so_kind, gate, param, consts, ntab = g.SO_PLAIN, g.GATE_PROD3, 0, None, 3
+    elif kind == "folded4":
+        so_kind, gate, param, ntab = g.SO_PLAIN, g.GATE_FOLDED_PROD, 4, 8
+        consts = to_limbs([rng.randrange(P) for _ in range(4)])
+    elif kind == "logup":
+        so_kind, gate, param, ntab = g.SO_EQ_GAMMA, g.GATE_LOGUP_LAYER, 0, 5
+        consts = to_limbs([1, rng.randrange(P)])
+    else:
+        so_kind, gate, param, ntab = g.SO_EQ_GAMMA, g.GATE_ADD_INVERSES, 0, 3
+        consts = to_limbs([1, rng.randrange(P)])
+    tabs = [ctx.synth(500 + j, n) for j in range(ntab)]
+    claim = ctx.gate_sum(so_kind, gate, tabs, gate_param=param, consts=consts)
+    chals = [rand_chal128(rng) for _ in range(nv)]
+    chals[5] = rng.randrange(P)  # one full-width challenge in the middle: mixed fast / general folds
+    runs = []
+    for fast in (True, False):
+        ctx.set_fast_fold(fast)
+        so = ctx.dense_so(so_kind, gate, tabs, nv, claim, gate_param=param, consts=consts)
+        evs = []
+        for r in range(nv):
+            evs.append(so.unipoly().copy())
+            so.bind(to_limb1(chals[r]))
+        runs.append((evs, so.final_evals().copy(), so.claim.copy()))
+        so.destroy()
+    ctx.set_fast_fold(True)
+    for a, b in zip(runs[0][0], runs[1][0]):
+        assert np.array_equal(a, b)
+    assert np.array_equal(runs[0][1], runs[1][1])
+    assert np.array_equal(runs[0][2], runs[1][2])
