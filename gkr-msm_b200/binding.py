@@ -61,6 +61,7 @@ def _sig(lib):
     f("gkr_ctx_stream", _vp, _vp)
     f("gkr_ctx_timing_enable", C.c_int, _vp, C.c_int)
     f("gkr_ctx_set_fast_fold", C.c_int, _vp, C.c_int)
+    f("gkr_ctx_host_stats", C.c_int, _vp, _vp, C.c_int)
     f("gkr_ctx_timing_read", C.c_int, _vp, _vp, _vp, _vp, C.c_int)
     f("gkr_bench_modmul", C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
     f("gkr_table_upload", C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp))
@@ -163,6 +164,12 @@ class Context:
     def stream(self) -> int:
         return int(self.lib.gkr_ctx_stream(self.h) or 0)
 
+    def host_stats(self, reset: bool = True):
+        """(ns in round-kernel launch calls, ns waiting for round results, waits, kernels launched)"""
+        out = np.zeros(4, np.uint64)
+        self.check(self.lib.gkr_ctx_host_stats(self.h, _ptr(out), 1 if reset else 0))
+        return tuple(int(x) for x in out)
+
     def set_fast_fold(self, on: bool = True):
         self.check(self.lib.gkr_ctx_set_fast_fold(self.h, 1 if on else 0))
 
@@ -193,6 +200,11 @@ class Context:
         t = Table(self, h)
         t._keep = keep
         return t
+
+    def alloc(self, n: int) -> "Table":
+        h = _vp()
+        self.check(self.lib.gkr_table_alloc(self.h, n, C.byref(h)))
+        return Table(self, h)
 
     def synth(self, seed: int, n: int, first_index: int = 0) -> "Table":
         h = _vp()

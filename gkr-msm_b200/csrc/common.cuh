@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <ctime>
 #include <string>
 #include <vector>
 #include "../../include/gkr_msm_b200.h"
@@ -38,6 +39,7 @@ struct gkr_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    uint64_t ns_launch = 0, ns_wait = 0, n_waits = 0;  // host-side latency accounting (gkr_ctx_host_stats)
     bool no_fast_fold = false;      // test hook (GKR_NO_FAST_FOLD=1): always fold with the full Montgomery product
     Fr* partials = nullptr;         // [GKR_MAX_BLOCKS * GKR_MAX_DEG] device scratch (device-side two-stage reductions)
     unsigned int* ticket = nullptr; // device counter for the last-block pattern
@@ -100,11 +102,18 @@ struct gkr_vecvec {
 // kernel ids reported by gkr_ctx_timing_read
 enum GkrKernelId { GKR_K_DENSE_EVAL = 0, GKR_K_DENSE_FOLD_EVAL = 1, GKR_K_DENSE_SUM = 2, GKR_K_DENSE_FOLD = 3 };
 
+static inline uint64_t gkr_now_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
 struct GkrLaunchTimer {
     gkr_ctx* ctx;
     bool on;
+    uint64_t t0;
     gkr_ctx::TimedLaunch t;
-    GkrLaunchTimer(gkr_ctx* c, int kernel_id, uint64_t n_items) : ctx(c), on(c->timing) {
+    GkrLaunchTimer(gkr_ctx* c, int kernel_id, uint64_t n_items) : ctx(c), on(c->timing), t0(gkr_now_ns()) {
         if (!on) return;
         t.kernel_id = kernel_id;
         t.n_items = n_items;
@@ -113,6 +122,7 @@ struct GkrLaunchTimer {
         cudaEventRecord(t.start, ctx->stream);
     }
     ~GkrLaunchTimer() {
+        ctx->ns_launch += gkr_now_ns() - t0;
         if (!on) return;
         cudaEventRecord(t.stop, ctx->stream);
         ctx->timed.push_back(t);

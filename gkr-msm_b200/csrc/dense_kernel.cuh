@@ -1,0 +1,125 @@
+// The round kernel of DenseSumcheckObjectSO (shared by dense_sumcheck.cu and the kernel lab, kernel_lab.cu).
+#pragma once
+#include "common.cuh"
+#include "gates.cuh"
+
+struct DenseRoundArgs {
+    const Fr* in[GKR_MAX_POLYS];
+    Fr* out[GKR_MAX_POLYS];
+    uint64_t n_items;  // MODE 0/1: number of pairs evaluated; MODE 2: number of elements
+    Fr t;              // challenge, Montgomery form (general fold)
+    uint32_t t128[4];  // challenge as a plain 128-bit integer (FAST fold)
+    GateConsts consts;
+    RoundOut o;
+};
+
+// MODE 0: evaluate pairs (2i, 2i+1) of `in`                      (first round: nothing to fold yet)
+// MODE 1: fold quads (4i..4i+3) of `in` into `out` (2i, 2i+1), then evaluate that fresh pair
+// MODE 2: plain sum of f over all elements (claim_hint computation), one accumulator
+//
+// Integer-pipe economy (this kernel is bound by the 32x32->64 multiplier, not by HBM: DESIGN.md section 3):
+//   * FAST folds: a Fiat-Shamir challenge of transcript.challenge(128) is a 128-bit integer, so
+//     e0 + t (e1 - e0) is a 4x8-limb product plus a 4-round Montgomery reduction (fr_fold128, 56 wide
+//     multiply-adds instead of 112).  The folded table then carries a factor 2^-128 per fast fold; every gate
+//     on this path is homogeneous in the tables, so the round sums come out scaled by a known power of it
+//     and the host multiplies it away (DenseSO::unscale_*): the round polynomials stay bit-exact.
+//   * the last multiplication of every gate evaluation is accumulated UNREDUCED (FrWide, 64 instead of 112)
+//     and each thread reduces its accumulators once.
+//
+// MINB: minimum resident blocks per SM (register cap).  ACC_SMEM: keep the NACC x 544-bit accumulators in shared
+// memory (limb-major, conflict-free) instead of registers -- 51 registers less for a degree-3 gate.
+template <int NACC, bool ACC_SMEM>
+struct WideAccs {
+    FrWide r[ACC_SMEM ? 1 : NACC];
+    uint32_t* sm;
+    __device__ __forceinline__ void init(uint32_t* smem_base) {
+        sm = smem_base + threadIdx.x;
+        if (ACC_SMEM) {
+#pragma unroll
+            for (int k = 0; k < NACC * 17; k++) sm[k * GKR_REDUCE_THREADS] = 0;
+        } else {
+#pragma unroll
+            for (int s = 0; s < NACC; s++) frw_zero(r[s]);
+        }
+    }
+    template <class SO>
+    __device__ __forceinline__ void mac(int s, const Fr* a, const GateConsts& c) {
+        if (ACC_SMEM) {
+            FrWide w;
+#pragma unroll
+            for (int k = 0; k < 17; k++) w.l[k] = sm[(s * 17 + k) * GKR_REDUCE_THREADS];
+            SO::mac(w, a, c);
+#pragma unroll
+            for (int k = 0; k < 17; k++) sm[(s * 17 + k) * GKR_REDUCE_THREADS] = w.l[k];
+        } else {
+            SO::mac(r[s], a, c);
+        }
+    }
+    __device__ __forceinline__ Fr reduce(int s) {
+        if (ACC_SMEM) {
+            FrWide w;
+#pragma unroll
+            for (int k = 0; k < 17; k++) w.l[k] = sm[(s * 17 + k) * GKR_REDUCE_THREADS];
+            return frw_reduce(w);
+        }
+        return frw_reduce(r[s]);
+    }
+};
+
+template <class SO, int MODE, bool FAST, int MINB = 3, bool ACC_SMEM = false>
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS, MINB) dense_round_kernel(const __grid_constant__ DenseRoundArgs A) {
+    constexpr int P = SO::P;
+    constexpr int NACC = (MODE == 2) ? 1 : SO::DEG;
+    __shared__ Fr smem[NACC * (GKR_REDUCE_THREADS / 32)];
+    __shared__ uint32_t acc_sm[ACC_SMEM ? NACC * 17 * GKR_REDUCE_THREADS : 1];
+    WideAccs<NACC, ACC_SMEM> W;
+    W.init(acc_sm);
+
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_items; i += stride) {
+        Fr a[P];
+        if (MODE == 2) {
+#pragma unroll
+            for (int j = 0; j < P; j++) a[j] = A.in[j][i];
+            W.template mac<SO>(0, a, A.consts);
+        } else {
+            Fr d[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                Fr lo, hi;
+                if (MODE == 1) {
+                    const Fr* src = A.in[j] + 4 * i;
+                    Fr e0 = src[0], e1 = src[1], e2 = src[2], e3 = src[3];
+                    if (FAST) {
+                        lo = fr_fold128(e0, fr_sub(e1, e0), A.t128);
+                        hi = fr_fold128(e2, fr_sub(e3, e2), A.t128);
+                    } else {
+                        lo = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+                        hi = fr_add(e2, fr_mul(A.t, fr_sub(e3, e2)));
+                    }
+                    Fr* dst = A.out[j] + 2 * i;
+                    dst[0] = lo;
+                    dst[1] = hi;
+                } else {
+                    const Fr* src = A.in[j] + 2 * i;
+                    lo = src[0];
+                    hi = src[1];
+                }
+                a[j] = hi;
+                d[j] = fr_sub(hi, lo);
+            }
+            W.template mac<SO>(0, a, A.consts);
+#pragma unroll
+            for (int s = 1; s < SO::DEG; s++) {
+#pragma unroll
+                for (int j = 0; j < P; j++) a[j] = fr_add(a[j], d[j]);
+                W.template mac<SO>(s, a, A.consts);
+            }
+        }
+    }
+    Fr acc[NACC];
+#pragma unroll
+    for (int s = 0; s < NACC; s++) acc[s] = W.reduce(s);
+    grid_reduce_to_host<NACC>(acc, smem, A.o);
+}
+

@@ -12,86 +12,8 @@
 #include <algorithm>
 #include "common.cuh"
 #include "gates.cuh"
+#include "dense_kernel.cuh"
 #include "so.hpp"
-
-struct DenseRoundArgs {
-    const Fr* in[GKR_MAX_POLYS];
-    Fr* out[GKR_MAX_POLYS];
-    uint64_t n_items;  // MODE 0/1: number of pairs evaluated; MODE 2: number of elements
-    Fr t;              // challenge, Montgomery form (general fold)
-    uint32_t t128[4];  // challenge as a plain 128-bit integer (FAST fold)
-    GateConsts consts;
-    RoundOut o;
-};
-
-// MODE 0: evaluate pairs (2i, 2i+1) of `in`                      (first round: nothing to fold yet)
-// MODE 1: fold quads (4i..4i+3) of `in` into `out` (2i, 2i+1), then evaluate that fresh pair
-// MODE 2: plain sum of f over all elements (claim_hint computation), one accumulator
-//
-// Integer-pipe economy (this kernel is bound by the 32x32->64 multiplier, not by HBM: DESIGN.md section 3):
-//   * FAST folds: a Fiat-Shamir challenge of transcript.challenge(128) is a 128-bit integer, so
-//     e0 + t (e1 - e0) is a 4x8-limb product plus a 4-round Montgomery reduction (fr_fold128, 56 wide
-//     multiply-adds instead of 112).  The folded table then carries a factor 2^-128 per fast fold; every gate
-//     on this path is homogeneous in the tables, so the round sums come out scaled by a known power of it
-//     and the host multiplies it away (DenseSO::unscale_*): the round polynomials stay bit-exact.
-//   * the last multiplication of every gate evaluation is accumulated UNREDUCED (FrWide, 64 instead of 112)
-//     and each thread reduces its accumulators once.
-template <class SO, int MODE, bool FAST>
-__global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_round_kernel(const __grid_constant__ DenseRoundArgs A) {
-    constexpr int P = SO::P;
-    constexpr int NACC = (MODE == 2) ? 1 : SO::DEG;
-    __shared__ Fr smem[NACC * (GKR_REDUCE_THREADS / 32)];
-    FrWide wacc[NACC];
-#pragma unroll
-    for (int s = 0; s < NACC; s++) frw_zero(wacc[s]);
-
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_items; i += stride) {
-        Fr a[P];
-        if (MODE == 2) {
-#pragma unroll
-            for (int j = 0; j < P; j++) a[j] = A.in[j][i];
-            SO::mac(wacc[0], a, A.consts);
-        } else {
-            Fr d[P];
-#pragma unroll
-            for (int j = 0; j < P; j++) {
-                Fr lo, hi;
-                if (MODE == 1) {
-                    const Fr* src = A.in[j] + 4 * i;
-                    Fr e0 = src[0], e1 = src[1], e2 = src[2], e3 = src[3];
-                    if (FAST) {
-                        lo = fr_fold128(e0, fr_sub(e1, e0), A.t128);
-                        hi = fr_fold128(e2, fr_sub(e3, e2), A.t128);
-                    } else {
-                        lo = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
-                        hi = fr_add(e2, fr_mul(A.t, fr_sub(e3, e2)));
-                    }
-                    Fr* dst = A.out[j] + 2 * i;
-                    dst[0] = lo;
-                    dst[1] = hi;
-                } else {
-                    const Fr* src = A.in[j] + 2 * i;
-                    lo = src[0];
-                    hi = src[1];
-                }
-                a[j] = hi;
-                d[j] = fr_sub(hi, lo);
-            }
-            SO::mac(wacc[0], a, A.consts);
-#pragma unroll
-            for (int s = 1; s < SO::DEG; s++) {
-#pragma unroll
-                for (int j = 0; j < P; j++) a[j] = fr_add(a[j], d[j]);
-                SO::mac(wacc[s], a, A.consts);
-            }
-        }
-    }
-    Fr acc[NACC];
-#pragma unroll
-    for (int s = 0; s < NACC; s++) acc[s] = frw_reduce(wacc[s]);
-    grid_reduce_to_host<NACC>(acc, smem, A.o);
-}
 
 // out[j][i] = in[j][2i] + t (in[j][2i+1] - in[j][2i])   -- used for the last round (one pair -> one value)
 __global__ void dense_fold_kernel(const __grid_constant__ DenseRoundArgs A, int n_polys) {

@@ -39,6 +39,7 @@ int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH
     GkrSlot* s = &ctx->slots_host[slot];
     const uint32_t seq = ctx->slot_seq[slot];
     uint64_t spins = 0;
+    const uint64_t t0 = gkr_now_ns();
     while (s->flag != seq) {
         if ((++spins & 0xffff) == 0) {
             cudaError_t q = cudaStreamQuery(ctx->stream);
@@ -50,6 +51,8 @@ int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH
         }
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    ctx->ns_wait += gkr_now_ns() - t0;
+    ctx->n_waits++;
     for (int a = 0; a < n_acc; a++) {
         gkr::FrH acc = gkr::frh::ZERO;
         for (uint32_t b = 0; b < n_blocks; b++) acc = gkr::frh::add(acc, fr_to_host(s->part[(size_t)b * n_acc + a]));
@@ -325,6 +328,13 @@ extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, con
 }
 
 // ---- per-launch timing (used only by bench.py's roofline leg) ----------------------------------------------
+extern "C" int gkr_ctx_host_stats(gkr_ctx* ctx, uint64_t out[4], int reset) {
+    if (!ctx || !out) return GKR_ERR_ARG;
+    out[0] = ctx->ns_launch; out[1] = ctx->ns_wait; out[2] = ctx->n_waits; out[3] = ctx->launches;
+    if (reset) ctx->ns_launch = ctx->ns_wait = ctx->n_waits = 0;
+    return GKR_OK;
+}
+
 extern "C" int gkr_ctx_set_fast_fold(gkr_ctx* ctx, int on) {
     if (!ctx) return GKR_ERR_ARG;
     ctx->no_fast_fold = on == 0;

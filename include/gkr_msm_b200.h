@@ -73,6 +73,9 @@ int gkr_ctx_timing_enable(gkr_ctx* ctx, int on);
 /* test hook: on = 0 makes DenseSumcheckObjectSO::bind always use the full Montgomery product instead of the
  * 128-bit-challenge fold (both are bit-exact; tests compare them at sizes the oracle cannot reach). Default on. */
 int gkr_ctx_set_fast_fold(gkr_ctx* ctx, int on);
+/* host-side latency accounting: out = {ns spent inside kernel-launch calls of the round kernels, ns spent waiting for
+ * round results, number of waits, kernels launched}; reset != 0 clears the first three. */
+int gkr_ctx_host_stats(gkr_ctx* ctx, uint64_t out[4], int reset);
 int gkr_ctx_timing_read(gkr_ctx* ctx, int* kernel_id, uint64_t* n_items, float* ms, int max_n);
 int gkr_bench_modmul(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* modmul_per_s);
 

@@ -18,6 +18,8 @@ reps = 20
 def timeit(make_so, rounds, label):
     ts, cs = [], []
     for r in range(reps + 3):
+        if r == 3:
+            ctx.host_stats(True)
         ctx.sync()
         t0 = time.perf_counter()
         so = make_so()
@@ -30,6 +32,8 @@ def timeit(make_so, rounds, label):
         if r >= 3:
             cs.append(t1 - t0)
             ts.append(t2 - t1)
+    nl, nw, waits, _ = ctx.host_stats(True)
+    print(f"{label:40s} launch-call {nl/1e3/max(waits,1):6.1f} us  wait {nw/1e3/max(waits,1):6.1f} us per round ({waits//reps} waits/prove)", flush=True)
     print(f"{label:40s} create {np.median(cs)*1e6:8.1f} us   prove {np.median(ts)*1e6:8.1f} us  = {np.median(ts)*1e6/rounds:6.1f} us/round", flush=True)
 
 

@@ -1,0 +1,33 @@
+#!/usr/bin/env python3
+"""Times the variants of the dense round kernel compiled into csrc/kernel_lab.cu (B200 only)."""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import gkr_msm_b200 as g  # noqa: E402
+
+ctx = g.Context(0)
+lib = ctx.lib
+lib.gkr_lab_dense_prod3.restype = C.c_int
+log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+n = 1 << log_n
+tabs = [ctx.synth(j, n) for j in range(3)]
+outs = [ctx.alloc(n // 2) for _ in range(3)]
+vp = C.c_void_p
+tin = (vp * 3)(*[t.h for t in tabs])
+tout = (vp * 3)(*[t.h for t in outs])
+names = {0: "regs, >=3 blocks/SM", 1: "regs, >=4 blocks/SM (spills)", 2: "smem accs, >=4 blocks/SM", 3: "smem accs, >=5 blocks/SM", 4: "regs, >=2 blocks/SM"}
+for mode in (0, 1):
+    bytes_ = (32 * 3 * n) if mode == 0 else (48 * 3 * n)
+    for variant in range(5):
+        for gm in (1, 2):
+            ms = C.c_float(0)
+            bps = C.c_int(0)
+            rc = lib.gkr_lab_dense_prod3(ctx.h, variant, mode, tin, tout, C.c_uint64(n), 10, gm, C.byref(ms), C.byref(bps))
+            if rc:
+                print("variant", variant, "failed", rc)
+                continue
+            print(f"mode {mode} ({'eval' if mode == 0 else 'fast fold+eval'}) 2^{log_n} variant {variant} [{names[variant]}] grid x{gm}: "
+                  f"{ms.value:.4f} ms  {bytes_ / ms.value / 1e6:.0f} GB/s  ({bps.value} blocks/SM)", flush=True)
