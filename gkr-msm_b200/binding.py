@@ -567,21 +567,28 @@ Context.map_vecvec = _ctx_map_vecvec
 
 
 # ---- commitments ------------------------------------------------------------------------------------------
+def _srs_sigs(lib):
+    if hasattr(lib.gkr_srs_upload, "_sig"):
+        return
+    lib.gkr_srs_upload.restype = C.c_int
+    lib.gkr_srs_upload.argtypes = [_vp, _vp, C.c_uint64, C.c_int, C.POINTER(_vp)]
+    lib.gkr_srs_len.restype = C.c_uint64
+    lib.gkr_srs_len.argtypes = [_vp]
+    lib.gkr_srs_free.restype = None
+    lib.gkr_srs_free.argtypes = [_vp]
+    lib.gkr_msm_g1.restype = C.c_int
+    lib.gkr_msm_g1.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]
+    lib.gkr_srs_mock_setup.restype = C.c_int
+    lib.gkr_srs_mock_setup.argtypes = [_vp, _vp, _vp, C.c_uint64, C.POINTER(_vp)]
+    lib.gkr_srs_upload._sig = True
+
+
 class Srs:
     """gkr_srs: G1 bases resident in HBM (affine (n, 12) or Jacobian (n, 18) uint64 Montgomery limbs)."""
 
     def __init__(self, ctx: Context, points, projective: bool = False):
         lib = ctx.lib
-        if not hasattr(lib.gkr_srs_upload, "_sig"):
-            lib.gkr_srs_upload.restype = C.c_int
-            lib.gkr_srs_upload.argtypes = [_vp, _vp, C.c_uint64, C.c_int, C.POINTER(_vp)]
-            lib.gkr_srs_len.restype = C.c_uint64
-            lib.gkr_srs_len.argtypes = [_vp]
-            lib.gkr_srs_free.restype = None
-            lib.gkr_srs_free.argtypes = [_vp]
-            lib.gkr_msm_g1.restype = C.c_int
-            lib.gkr_msm_g1.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]
-            lib.gkr_srs_upload._sig = True
+        _srs_sigs(lib)
         a = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 18 if projective else 12)
         h = _vp()
         ctx.check(lib.gkr_srs_upload(ctx.h, _ptr(a), a.shape[0], 1 if projective else 0, C.byref(h)))
@@ -639,6 +646,19 @@ def _srs_download_affine(self) -> np.ndarray:
     return out
 
 
+def _srs_mock_setup(ctx: Context, tau, g0_xy, n: int) -> "Srs":
+    """KzgProvingKey::mock_setup(tau, g0, _, n).ptau_1 (kzg.rs:84-97), generated on the device."""
+    lib = ctx.lib
+    _srs_sigs(lib)
+    t, g0 = _limbs(tau).reshape(4), _limbs(g0_xy).reshape(12)
+    h = _vp()
+    ctx.check(lib.gkr_srs_mock_setup(ctx.h, _ptr(t), _ptr(g0), n, C.byref(h)))
+    out = Srs.__new__(Srs)
+    out.ctx, out.h, out.n = ctx, h, n
+    return out
+
+
+Srs.mock_setup = staticmethod(_srs_mock_setup)
 Srs.bucket_sums = _srs_bucket_sums
 Srs.weighted_sum = _srs_weighted_sum
 Srs.download_affine = _srs_download_affine
@@ -703,7 +723,7 @@ def _ctx_lincomb(self, terms, out_len) -> Table:
     """terms: list of (table, coef_limbs, src_off, dst_off, length); out[dst_off+i] += coef*table[src_off+i]."""
     _poly_sigs(self.lib)
     k = len(terms)
-    arr = (_vp * max(k, 1))(*[t[0].h for t in terms])
+    arr = (_vp * max(k, 1))(*[(t[0].h if t[0] is not None else None) for t in terms])  # None = the all-ones table
     coefs = np.ascontiguousarray(np.stack([_limbs(t[1]).reshape(4) for t in terms]) if k else np.zeros((0, 4), np.uint64))
     so = np.array([t[2] for t in terms], dtype=np.uint64)
     do = np.array([t[3] for t in terms], dtype=np.uint64)

@@ -523,3 +523,75 @@ extern "C" int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t
     cudaFreeAsync(tmp, st);
     return GKR_OK;
 }
+
+// ---- KzgProvingKey::mock_setup  (src/commitments/kzg.rs:84-97) ------------------------------------------------
+// ptau_1[i] = tau^i * g0.  Fixed-base: T[j] = 2^j g0 (255 affine points), then every thread adds the T[j] selected by the
+// bits of tau^i with mixed additions and normalises its own point (one inversion: 1/ZZ = (ZZ / ZZZ)^2).
+__global__ void srs_doublings_kernel(G1Aff g0, G1X* T) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    G1X p;
+    p.X = g0.x; p.Y = g0.y; p.ZZ = fq_one(); p.ZZZ = fq_one();
+    if (g1a_is_inf(g0)) p = g1x_inf();
+    for (int j = 0; j < 255; j++) {
+        T[j] = p;
+        p = g1x_dbl(p);
+    }
+}
+__global__ void __launch_bounds__(128) srs_fixed_base_kernel(const G1Aff* T, Fr tau, uint64_t n, G1Aff* out) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        Fr s = fr_one(), b = tau;  // tau^i
+        for (uint64_t e = i; e; e >>= 1) {
+            if (e & 1) s = fr_mul(s, b);
+            b = fr_sqr(b);
+        }
+        Fr one_raw = fr_zero();
+        one_raw.l[0] = 1;
+        s = fr_mul(s, one_raw);  // leave Montgomery form
+        G1X acc = g1x_inf();
+        for (int j = 0; j < 255; j++)
+            if ((s.l[j >> 5] >> (j & 31)) & 1) g1x_madd(acc, T[j]);
+        G1Aff r;
+        if (g1x_is_inf(acc)) {
+            r.x = fq_zero(); r.y = fq_zero();
+        } else {
+            Fq iz3 = fq_inv(acc.ZZZ);
+            Fq iz2 = fq_sqr(fq_mul(acc.ZZ, iz3));
+            r.x = fq_mul(acc.X, iz2);
+            r.y = fq_mul(acc.Y, iz3);
+        }
+        out[i] = r;
+    }
+}
+
+extern "C" int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uint64_t* g0_xy, uint64_t n, gkr_srs** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!tau || !g0_xy || !out) return ctx->fail(GKR_ERR_ARG, "null argument");
+    gkr::FrH t = frh_from_limbs(tau);
+    if (!frh_canonical(t)) return ctx->fail(GKR_ERR_ARG, "tau not canonical");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    gkr_srs* s = new gkr_srs();
+    s->ctx = ctx;
+    s->n = n;
+    s->kind = 0;
+    G1X* Tx = nullptr;
+    G1Aff* Ta = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&s->d, std::max<size_t>(sizeof(G1Aff) * n, 16), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&Tx, sizeof(G1X) * 255, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&Ta, sizeof(G1Aff) * 255, st));
+    G1Aff g0;
+    std::memcpy(&g0, g0_xy, sizeof(G1Aff));
+    srs_doublings_kernel<<<1, 32, 0, st>>>(g0, Tx);
+    g1_to_affine_kernel<<<4, 64, 0, st>>>(Tx, 255, Ta);
+    if (n) {
+        unsigned g = (unsigned)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->num_sms * 8);
+        srs_fixed_base_kernel<<<g, 128, 0, st>>>(Ta, fr_from_host(t), n, (G1Aff*)s->d);
+    }
+    ctx->launches += 3;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(Tx, st);
+    cudaFreeAsync(Ta, st);
+    *out = s;
+    return GKR_OK;
+}

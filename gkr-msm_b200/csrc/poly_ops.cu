@@ -141,6 +141,10 @@ __global__ void lincomb_kernel(Fr* out, uint64_t n, const LinTerm* terms, int n_
         for (int k = 0; k < n_terms; k++) {
             const LinTerm t = terms[k];
             if (i >= t.dst_off && i - t.dst_off < t.len) {
+                if (!t.src) {  // constant term: the all-ones table times coef
+                    acc = fr_add(acc, t.coef);
+                    continue;
+                }
                 Fr v = t.src[i - t.dst_off];
                 acc = fr_add(acc, t.coef_is_one ? v : fr_mul(v, t.coef));
             }
@@ -150,16 +154,17 @@ __global__ void lincomb_kernel(Fr* out, uint64_t n, const LinTerm* terms, int n_
 }
 // out = zeros(out_len); out[dst_off_k + i] += coef_k * src_k[src_off_k + i], i < len_k.
 // Covers `x + gamma*y`, the zero-extended `lambda*t + p`, folded_witness and the strided combined_witness.
+// src_k == NULL stands for the all-ones table: constant shifts and pads (c_adj / d_adj, pushforward.rs:700-710).
 extern "C" int gkr_table_lincomb(gkr_ctx* ctx, uint32_t n_terms, gkr_table* const* src, const uint64_t* coefs, const uint64_t* src_off,
                                  const uint64_t* dst_off, const uint64_t* len, uint64_t out_len, gkr_table** out) {
     if (!ctx) return GKR_ERR_ARG;
     if (!out || (n_terms && (!src || !coefs || !src_off || !dst_off || !len))) return ctx->fail(GKR_ERR_ARG, "null argument");
     std::vector<LinTerm> terms(n_terms);
     for (uint32_t k = 0; k < n_terms; k++) {
-        if (!src[k] || src_off[k] + len[k] > src[k]->n || dst_off[k] + len[k] > out_len) return ctx->fail(GKR_ERR_ARG, "slice out of range");
+        if ((src[k] && src_off[k] + len[k] > src[k]->n) || dst_off[k] + len[k] > out_len) return ctx->fail(GKR_ERR_ARG, "slice out of range");
         gkr::FrH c = frh_from_limbs(coefs + 4 * k);
         if (!frh_canonical(c)) return ctx->fail(GKR_ERR_ARG, "coefficient not canonical");
-        terms[k].src = src[k]->d + src_off[k];
+        terms[k].src = src[k] ? src[k]->d + src_off[k] : nullptr;  // NULL source = the constant-one table
         terms[k].dst_off = dst_off[k];
         terms[k].len = len[k];
         terms[k].coef = fr_from_host(c);

@@ -188,6 +188,9 @@ int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, int project
 uint64_t gkr_srs_len(const gkr_srs* s);
 void gkr_srs_free(gkr_srs* s);
 int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
+/* KzgProvingKey::mock_setup(tau, g0, _, size).ptau_1  (kzg.rs:84-97): bases[i] = tau^i * g0 as affine points,
+ * generated on the device (fixed-base: sum of the 2^j g0 selected by the bits of tau^i). g0_xy: 12 u64, tau: Fr. */
+int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uint64_t* g0_xy, uint64_t n, gkr_srs** out);
 
 /* bucket accumulation of the c / d commitments: B[b] = sum_{k: bucket_idx[k] == b} bases[point_idx[k]]
  * (PushForwardState::new, pushforward.rs:398-429, 433-456; Pullback::bucketed_msm, src/pullback.rs:28-59).
@@ -204,7 +207,8 @@ int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
  * gkr_table_from_u32: F::from(v) per entry, negated for the access counts (pushforward.rs:479-500).
  * gkr_table_gather:   out[i] = src[idx[i]] (c_pull / d_pull, pushforward.rs:585-595).
  * gkr_table_lincomb:  out = 0; out[dst_off_k + i] += coef_k * src_k[src_off_k + i] -- p_0 + gamma p_1, combined_witness,
- *                     folded_witness (pippenger.rs:209-231, 274-279), p_lt = lambda t + p (opening.rs:65-75).
+ *                     folded_witness (pippenger.rs:209-231, 274-279), p_lt = lambda t + p (opening.rs:65-75).  A NULL
+ *                     src_k is the all-ones table (constant shifts and pads of c_adj / d_adj, pushforward.rs:700-710).
  * gkr_poly_eval / gkr_poly_div_by_linear: `ev`, `div_by_linear` (kzg.rs:73-81, 142-150).
  * gkr_knuckles_*: KnucklesProvingKey::new inverses and compute_t (knuckles.rs:65-81, 111-154). */
 typedef struct gkr_u32buf gkr_u32buf;

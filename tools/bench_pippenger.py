@@ -1,0 +1,84 @@
+#!/usr/bin/env python3
+"""Headline secondary benchmark: `examples/pippenger` end to end on one B200 -- benchutils::run_pippenger
+(src/cleanup/protocols/pippenger.rs:499-559: witness generation + phase-1 commitments + the whole proof), the span the
+reference's criterion bench times (benches/pippenger.rs:40-45).  Inputs are synthetic: on-curve Bandersnatch points in
+arithmetic progression, uniform `nbits`-bit scalars, the reference's own mock SRS (kzg.rs:84-97) generated on the device.
+
+  python tools/bench_pippenger.py --x-logsize 16 --d-logsize 8 --nbits 128 --clm 0 [--reps 3]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--x-logsize", type=int, default=16)
+    ap.add_argument("--d-logsize", type=int, default=8)
+    ap.add_argument("--nbits", type=int, default=128)
+    ap.add_argument("--clm", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--profile", action="store_true", help="print a per-phase breakdown of the last repetition")
+    args = ap.parse_args()
+
+    import gkr_msm_b200 as g
+    from gkr_msm_b200 import hostmath as H
+    from gkr_msm_b200 import pippenger as DPP
+    from gkr_msm_b200.fieldutil import R_MOD, to_limbs
+
+    rng = np.random.default_rng(args.seed)
+    xl, dl, nbits, clm = args.x_logsize, args.d_logsize, args.nbits, args.clm
+    cfg = DPP.pippenger_config(dl, xl, nbits, clm)
+    n = 1 << xl
+    t0 = time.perf_counter()
+    pts = H.te_points_arithmetic_progression(0x1234567 + args.seed, 0x9E3779B97F4A7C15, n)
+    points_xy = np.stack([to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])])
+    raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    nbytes = nbits // 8  # from_le_bytes_mod_order(&bytes[..num_bits / 8]), pippenger.rs:465-467
+    coefs = np.zeros((n, 4), np.uint64)
+    b = raw.view(np.uint8).reshape(n, 32).copy()
+    b[:, nbytes:] = 0
+    coefs[:] = b.view(np.uint64).reshape(n, 4)
+    r = [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(cfg["y_logsize"])]
+    t_inputs = time.perf_counter() - t0
+
+    ctx = g.Context(0)
+    t0 = time.perf_counter()
+    nv = xl + clm
+    tau = int.from_bytes(rng.bytes(32), "little") % R_MOD
+    kzg = DPP.KzgKey.mock_setup(ctx, tau, H.G1_GEN, 2 * (1 << nv) - 1)
+    key = DPP.KnucklesKey(ctx, kzg, nv, 2)
+    ctx.sync()
+    t_setup = time.perf_counter() - t0
+
+    times, proof_len, launches = [], 0, 0
+    for rep in range(args.reps):
+        tr = g.Transcript(b"fgstglsp")
+        l0 = ctx.launches
+        ctx.sync()
+        t0 = time.perf_counter()
+        dense_output, claims, pair = DPP.run_pippenger(ctx, tr, points_xy, coefs, cfg, r, key)
+        ctx.sync()
+        times.append(time.perf_counter() - t0)
+        launches = ctx.launches - l0
+        proof_len = len(tr.proof())
+    best = min(times)
+    print(json.dumps({
+        "bench": "run_pippenger (witness + commit + prove)", "x_logsize": xl, "d_logsize": dl, "nbits": nbits, "clm": clm,
+        "y_size": cfg["y_size"], "incidences": cfg["y_size"] << xl, "prove_ms_best": best * 1e3, "prove_ms_all": [t * 1e3 for t in times],
+        "proof_bytes": proof_len, "gpu_launches": launches, "input_generation_s": t_inputs, "srs_setup_s": t_setup,
+        "srs_points": 2 * (1 << nv) - 1}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
