@@ -12,6 +12,7 @@
 // Point arithmetic is integer-pipe (IMAD) bound: a mixed add is ~10 Fq multiplications of 12x12 32-bit limbs.
 #include <algorithm>
 #include "common.cuh"
+#include "host_g1.hpp"
 
 // q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 __device__ __constant__ uint32_t FQ_P[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -63,8 +64,9 @@ __device__ __noinline__ G1X g1x_dbl(const G1X& p) {
     return r;
 }
 
-// madd-2008-s: XYZZ += affine
-__device__ __noinline__ void g1x_madd(G1X& a, const G1Aff& b) {
+// madd-2008-s: XYZZ += affine.  The _i variants are inlined into the bucket-accumulation loops (the accumulator stays in
+// registers); the plain ones are out-of-line calls for the cold paths.
+__device__ __forceinline__ void g1x_madd_i(G1X& a, const G1Aff& b) {
     if (g1a_is_inf(b)) return;
     if (g1x_is_inf(a)) {
         a.X = b.x; a.Y = b.y; a.ZZ = fq_one(); a.ZZZ = fq_one();
@@ -95,8 +97,10 @@ __device__ __noinline__ void g1x_madd(G1X& a, const G1Aff& b) {
     a.ZZZ = fq_mul(a.ZZZ, PPP);
 }
 
+__device__ __noinline__ void g1x_madd(G1X& a, const G1Aff& b) { g1x_madd_i(a, b); }
+
 // add-2008-s: XYZZ += XYZZ
-__device__ __noinline__ void g1x_add(G1X& a, const G1X& b) {
+__device__ __forceinline__ void g1x_add_i(G1X& a, const G1X& b) {
     if (g1x_is_inf(b)) return;
     if (g1x_is_inf(a)) { a = b; return; }
     Fq U1 = fq_mul(a.X, b.ZZ);
@@ -119,6 +123,8 @@ __device__ __noinline__ void g1x_add(G1X& a, const G1X& b) {
     a.ZZ = fq_mul(fq_mul(a.ZZ, b.ZZ), PP);
     a.ZZZ = fq_mul(fq_mul(a.ZZZ, b.ZZZ), PPP);
 }
+
+__device__ __noinline__ void g1x_add(G1X& a, const G1X& b) { g1x_add_i(a, b); }
 
 // a^(q-2)
 __device__ Fq fq_inv(const Fq& a) {
@@ -190,73 +196,161 @@ __global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, in
     }
 }
 
-// KIND 0: affine bases, 1: Jacobian (X, Y, Z), 2: extended Jacobian (X, Y, ZZ, ZZZ) as produced by gkr_g1_bucket_sums
-template <int KIND>
-__global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts, const uint32_t* offsets,
-                                                              uint32_t n, int c, uint64_t total, int skip_zero, G1X* buckets) {
-    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < total; b += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t cnt = counts[b];
-        G1X acc = g1x_inf();
-        if (!(skip_zero && (b & ((1u << c) - 1)) == 0) && cnt) {
-            const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
-            for (uint32_t k = 0; k < cnt; k++) {
-                if (KIND == 2) {
-                    g1x_add(acc, ((const G1X*)bases)[idx[k]]);
-                } else if (KIND == 1) {
-                    // Jacobian (X, Y, Z) base: ZZ = Z^2, ZZZ = Z^3
-                    const Fq* p = (const Fq*)bases + (size_t)3 * idx[k];
-                    Fq Z = p[2];
-                    if (fq_is_zero(Z)) continue;
-                    G1X t;
-                    t.X = p[0]; t.Y = p[1]; t.ZZ = fq_sqr(Z); t.ZZZ = fq_mul(t.ZZ, Z);
-                    g1x_add(acc, t);
-                } else {
-                    G1Aff p = ((const G1Aff*)bases)[idx[k]];
-                    g1x_madd(acc, p);
-                }
-            }
+// ---- balanced bucket accumulation ----------------------------------------------------------------------------
+// Bucket sizes are data dependent (a degenerate top window, small-integer scalar tables, digit buckets of 2^(x-d) points):
+// one thread per bucket would serialise thousands of additions.  Buckets are therefore counting-sorted by size
+// (descending): buckets with >= MSM_CAP entries are summed by a whole block each (strided partial sums + shared-memory
+// tree), the rest by one thread each, and because neighbouring threads own buckets of equal size warps do not diverge.
+#define MSM_CAP 256
+
+__global__ void msm_bin_hist_kernel(const uint32_t* counts, uint64_t nbk, uint32_t* bins /* [MSM_CAP + 1] */) {
+    __shared__ uint32_t sh[MSM_CAP + 1];
+    for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbk; b += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t k = counts[b];
+        atomicAdd(&sh[k < MSM_CAP ? k : MSM_CAP], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x)
+        if (sh[i]) atomicAdd(&bins[i], sh[i]);
+}
+// descending exclusive offsets: bin MSM_CAP (heavy) first, empty buckets last
+__global__ void msm_bin_scan_kernel(const uint32_t* bins, uint32_t* bin_off) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    uint32_t acc = 0;
+    for (int k = MSM_CAP; k >= 0; k--) {
+        bin_off[k] = acc;
+        acc += bins[k];
+    }
+}
+__global__ void __launch_bounds__(256) msm_bin_scatter_kernel(const uint32_t* counts, uint64_t nbk, const uint32_t* bin_off, uint32_t* bin_cursor,
+                                                               uint32_t* order) {
+    __shared__ uint32_t sh_cnt[MSM_CAP + 1], sh_base[MSM_CAP + 1];
+    const uint64_t tiles = (nbk + blockDim.x - 1) / blockDim.x;
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x) sh_cnt[i] = 0;
+        __syncthreads();
+        const uint64_t b = tile * blockDim.x + threadIdx.x;
+        uint32_t k = 0, pos = 0;
+        if (b < nbk) {
+            k = counts[b];
+            if (k > MSM_CAP) k = MSM_CAP;
+            pos = atomicAdd(&sh_cnt[k], 1u);
         }
-        buckets[b] = acc;
+        __syncthreads();
+        for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x)
+            if (sh_cnt[i]) sh_base[i] = bin_off[i] + atomicAdd(&bin_cursor[i], sh_cnt[i]);
+        __syncthreads();
+        if (b < nbk) order[sh_base[k] + pos] = (uint32_t)b;
+        __syncthreads();
     }
 }
 
-// per window: sum_d d * B_d.  Thread k owns buckets [k*L, (k+1)*L); descending running sums give
-// tot = sum (d - lo + 1) B_d and run = sum B_d, so sum d*B_d = tot + (lo - 1) * run.
-__global__ void __launch_bounds__(256) msm_reduce_kernel(const G1X* buckets, int c, G1X* window_sums) {
+// KIND 0: affine bases, 1: Jacobian (X, Y, Z), 2: extended Jacobian (X, Y, ZZ, ZZZ) as produced by gkr_g1_bucket_sums
+template <int KIND>
+__device__ __forceinline__ void msm_add_base(G1X& acc, const void* bases, uint32_t i) {
+    if (KIND == 2) {
+        g1x_add_i(acc, ((const G1X*)bases)[i]);
+    } else if (KIND == 1) {
+        // Jacobian (X, Y, Z) base: ZZ = Z^2, ZZZ = Z^3
+        const Fq* p = (const Fq*)bases + (size_t)3 * i;
+        Fq Z = p[2];
+        if (fq_is_zero(Z)) return;
+        G1X t;
+        t.X = p[0]; t.Y = p[1]; t.ZZ = fq_sqr(Z); t.ZZZ = fq_mul(t.ZZ, Z);
+        g1x_add_i(acc, t);
+    } else {
+        G1Aff p = ((const G1Aff*)bases)[i];
+        g1x_madd_i(acc, p);
+    }
+}
+
+// light buckets (< MSM_CAP entries): one thread per bucket, in size order
+template <int KIND>
+__global__ void __launch_bounds__(128) msm_accumulate_light_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts,
+                                                                    const uint32_t* offsets, uint32_t n, int c, uint64_t total,
+                                                                    const uint32_t* order, const uint32_t* bins, G1X* buckets) {
+    const uint64_t n_heavy = bins[MSM_CAP];
+    for (uint64_t i = n_heavy + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = order[i];
+        const uint32_t cnt = counts[b];
+        G1X acc = g1x_inf();
+        const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
+        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, bases, idx[k]);
+        buckets[b] = acc;
+    }
+}
+// heavy buckets: one block per bucket
+template <int KIND>
+__global__ void __launch_bounds__(256) msm_accumulate_heavy_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts,
+                                                                    const uint32_t* offsets, uint32_t n, int c, const uint32_t* order,
+                                                                    const uint32_t* bins, G1X* buckets) {
     extern __shared__ unsigned char smem_raw[];
     G1X* sh = reinterpret_cast<G1X*>(smem_raw);
-    const uint32_t nb = 1u << c;
-    const G1X* B = buckets + ((size_t)blockIdx.x << c);
-    const uint32_t T = blockDim.x;
-    const uint32_t L = (nb + T - 1) / T;
-    const uint32_t lo = threadIdx.x * L;
-    uint32_t hi = lo + L;
-    if (hi > nb) hi = nb;
-    G1X run = g1x_inf(), tot = g1x_inf();
-    if (lo < nb) {
-        for (uint32_t d = hi; d-- > lo;) {
-            g1x_add(run, B[d]);
-            g1x_add(tot, run);
-        }
-        if (lo >= 2) {  // tot += (lo - 1) * run
-            uint32_t k = lo - 1;
-            G1X acc = g1x_inf(), base = run;
-            while (k) {
-                if (k & 1) g1x_add(acc, base);
-                base = g1x_dbl(base);
-                k >>= 1;
+    const uint32_t n_heavy = bins[MSM_CAP];
+    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        const uint32_t b = order[h];
+        const uint32_t cnt = counts[b];
+        const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
+        G1X acc = g1x_inf();
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, bases, idx[k]);
+        sh[threadIdx.x] = acc;
+        __syncthreads();
+        for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                G1X a = sh[threadIdx.x];
+                g1x_add(a, sh[threadIdx.x + s]);
+                sh[threadIdx.x] = a;
             }
-            g1x_add(tot, acc);
-        } else if (lo == 0) {
-            // tot counted (d + 1) * B_d for the segment starting at zero: remove one run
-            G1X neg = run;
-            neg.Y = fq_sub(fq_zero(), neg.Y);
-            g1x_add(tot, neg);
+            __syncthreads();
         }
+        if (threadIdx.x == 0) buckets[b] = sh[0];
+        __syncthreads();
     }
-    sh[threadIdx.x] = tot;
+}
+
+// per window: sum_d d * B_d.  A thread owns the segment [lo, lo + L) of one window; descending running sums give
+// tot = sum (d - lo + 1) B_d and run = sum B_d, so the segment contributes tot + (lo - 1) * run.
+__global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, int c, int seg_log, uint64_t n_threads, G1X* seg_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    const uint32_t segs = 1u << (c - seg_log);
+    const uint32_t w = (uint32_t)(t / segs), sgm = (uint32_t)(t % segs);
+    const G1X* B = buckets + ((size_t)w << c);
+    const uint32_t lo = sgm << seg_log, hi = lo + (1u << seg_log);
+    G1X run = g1x_inf(), tot = g1x_inf();
+    for (uint32_t d = hi; d-- > lo;) {
+        g1x_add(run, B[d]);
+        g1x_add(tot, run);
+    }
+    if (lo >= 2) {  // tot += (lo - 1) * run
+        uint32_t k = lo - 1;
+        G1X acc = g1x_inf(), base = run;
+        while (k) {
+            if (k & 1) g1x_add(acc, base);
+            k >>= 1;
+            if (k) base = g1x_dbl(base);
+        }
+        g1x_add(tot, acc);
+    } else if (lo == 0) {
+        // tot counted (d + 1) * B_d for the segment starting at zero: remove one run
+        G1X neg = run;
+        neg.Y = fq_sub(fq_zero(), neg.Y);
+        g1x_add(tot, neg);
+    }
+    seg_out[t] = tot;
+}
+// window_sums[w] = sum of the window's segment contributions (strided partial sums + shared-memory tree)
+__global__ void __launch_bounds__(256) msm_window_tree_kernel(const G1X* seg_out, uint32_t segs, G1X* window_sums) {
+    extern __shared__ unsigned char smem_raw[];
+    G1X* sh = reinterpret_cast<G1X*>(smem_raw);
+    const G1X* S = seg_out + (size_t)blockIdx.x * segs;
+    G1X acc = g1x_inf();
+    for (uint32_t k = threadIdx.x; k < segs; k += blockDim.x) g1x_add(acc, S[k]);
+    sh[threadIdx.x] = acc;
     __syncthreads();
-    for (uint32_t s = T >> 1; s > 0; s >>= 1) {
+    for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
         if (threadIdx.x < s) {
             G1X a = sh[threadIdx.x];
             g1x_add(a, sh[threadIdx.x + s]);
@@ -265,25 +359,6 @@ __global__ void __launch_bounds__(256) msm_reduce_kernel(const G1X* buckets, int
         __syncthreads();
     }
     if (threadIdx.x == 0) window_sums[blockIdx.x] = sh[0];
-}
-
-// Horner over the windows and normalisation to affine
-__global__ void msm_combine_kernel(const G1X* window_sums, int c, int n_windows, G1Aff* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1X acc = g1x_inf();
-    for (int w = n_windows - 1; w >= 0; w--) {
-        for (int k = 0; k < c; k++) acc = g1x_dbl(acc);
-        g1x_add(acc, window_sums[w]);
-    }
-    G1Aff r;
-    if (g1x_is_inf(acc)) {
-        r.x = fq_zero();
-        r.y = fq_zero();
-    } else {
-        r.x = fq_mul(acc.X, fq_inv(acc.ZZ));
-        r.y = fq_mul(acc.Y, fq_inv(acc.ZZZ));
-    }
-    *out = r;
 }
 
 // ---- host -------------------------------------------------------------------------------------------------
@@ -332,6 +407,60 @@ static int pick_window(uint64_t n) {
     return c;
 }
 
+// size-ordered bucket accumulation: counts/offsets [nbk], sorted [W][n] -> buckets [nbk].  `work` holds
+// order [nbk] followed by bins / bin_off / bin_cursor [3 * (MSM_CAP + 1)].
+static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint32_t* sorted, const uint32_t* counts, const uint32_t* offsets,
+                          uint32_t n, int c, uint64_t nbk, uint32_t* work, G1X* buckets) {
+    cudaStream_t st = ctx->stream;
+    uint32_t* order = work;
+    uint32_t* bins = work + nbk;
+    uint32_t* bin_off = bins + (MSM_CAP + 1);
+    uint32_t* bin_cursor = bin_off + (MSM_CAP + 1);
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(bins, 0, sizeof(uint32_t) * 3 * (MSM_CAP + 1), st));
+    unsigned gb = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk + 255) / 256, (uint64_t)ctx->num_sms * 4));
+    msm_bin_hist_kernel<<<gb, 256, 0, st>>>(counts, nbk, bins);
+    msm_bin_scan_kernel<<<1, 32, 0, st>>>(bins, bin_off);
+    msm_bin_scatter_kernel<<<gb, 256, 0, st>>>(counts, nbk, bin_off, bin_cursor, order);
+    unsigned gl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16));
+    unsigned gh = (unsigned)ctx->num_sms * 2;
+    const size_t shh = sizeof(G1X) * 256;
+    if (kind == 2) {
+        msm_accumulate_heavy_kernel<2><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, order, bins, buckets);
+        msm_accumulate_light_kernel<2><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets);
+    } else if (kind == 1) {
+        msm_accumulate_heavy_kernel<1><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, order, bins, buckets);
+        msm_accumulate_light_kernel<1><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets);
+    } else {
+        msm_accumulate_heavy_kernel<0><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, order, bins, buckets);
+        msm_accumulate_light_kernel<0><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets);
+    }
+    ctx->launches += 5;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    return GKR_OK;
+}
+
+// sum_w 2^(c w) sum_d d * buckets[w][d] as an affine point: segment running sums and the per-window tree on the device,
+// Horner over the W window sums and the inversion on the host (host_g1.hpp).
+static int msm_finish(gkr_ctx* ctx, const G1X* buckets, int c, int W, uint64_t* out_xy) {
+    cudaStream_t st = ctx->stream;
+    const int seg_log = c < 3 ? c : 3;
+    const uint32_t segs = 1u << (c - seg_log);
+    const uint64_t n_threads = (uint64_t)W * segs;
+    G1X* seg_out = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&seg_out, sizeof(G1X) * (n_threads + W), st));
+    G1X* wsums = seg_out + n_threads;
+    msm_segment_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out);
+    msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs, wsums);
+    ctx->launches += 2;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    std::vector<gkr::G1XH> h(W);
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(h.data(), wsums, sizeof(G1X) * W, cudaMemcpyDeviceToHost, st));
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    cudaFreeAsync(seg_out, st);
+    gkr::g1h::horner_windows(h.data(), c, W, out_xy);
+    return GKR_OK;
+}
+
 // <bases[first .. first+n), scalars>   scalars: device table of n Fr (Montgomery).  out_xy: affine result, 12 u64
 // (x then y, Montgomery form; all zero for the point at infinity).
 extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
@@ -349,42 +478,29 @@ extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, cons
     const int c = pick_window(n);
     const int W = (255 + c - 1) / c;
     const size_t nbk = (size_t)W << c;
-    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *offsets = nullptr, *cursor = nullptr;
-    G1X *buckets = nullptr, *wsums = nullptr;
-    G1Aff* d_out = nullptr;
+    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *work = nullptr;
+    G1X* buckets = nullptr;
     GKR_CUDA_OK(ctx, cudaMallocAsync(&digits, sizeof(uint32_t) * W * n, st));
     GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * W * n, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * nbk * 3, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * (MSM_CAP + 1)), st));
     offsets = counts + nbk;
     cursor = counts + 2 * nbk;
+    work = counts + 3 * nbk;
     GKR_CUDA_OK(ctx, cudaMallocAsync(&buckets, sizeof(G1X) * nbk, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&wsums, sizeof(G1X) * W, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_out, sizeof(G1Aff), st));
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
     msm_digits_kernel<<<g1, 256, 0, st>>>(scalars->d, (uint32_t)n, c, W, digits, counts);
     msm_scan_kernel<<<W, 1024, 0, st>>>(counts, offsets, c);
     msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, c, W, offsets, cursor, sorted);
-    unsigned g2 = (unsigned)std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16);
+    ctx->launches += 3;
     const void* bases = (const unsigned char*)srs->d + first * srs->stride();
-    if (srs->kind == 2) msm_accumulate_kernel<2><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, nbk, 1, buckets);
-    else if (srs->kind == 1) msm_accumulate_kernel<1><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, nbk, 1, buckets);
-    else msm_accumulate_kernel<0><<<g2, 128, 0, st>>>(bases, sorted, counts, offsets, (uint32_t)n, c, nbk, 1, buckets);
-    const int T = 256;
-    GKR_CUDA_OK(ctx, cudaFuncSetAttribute(msm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(G1X) * T)));
-    msm_reduce_kernel<<<W, T, sizeof(G1X) * T, st>>>(buckets, c, wsums);
-    msm_combine_kernel<<<1, 32, 0, st>>>(wsums, c, W, d_out);
-    ctx->launches += 6;
-    GKR_CUDA_OK(ctx, cudaGetLastError());
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, d_out, sizeof(G1Aff), cudaMemcpyDeviceToHost, st));
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, work, buckets);
+    if (rc == GKR_OK) rc = msm_finish(ctx, buckets, c, W, out_xy);
     cudaFreeAsync(digits, st);
     cudaFreeAsync(sorted, st);
     cudaFreeAsync(counts, st);
     cudaFreeAsync(buckets, st);
-    cudaFreeAsync(wsums, st);
-    cudaFreeAsync(d_out, st);
-    return GKR_OK;
+    return rc;
 }
 
 
@@ -433,11 +549,12 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
     GKR_CUDA_OK(ctx, cudaMallocAsync(&d_p, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
     GKR_CUDA_OK(ctx, cudaMallocAsync(&d_b, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
     GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * nbk * 3 + sizeof(int), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * (MSM_CAP + 1) + 1), st));
     uint32_t* offsets = counts + nbk;
     uint32_t* cursor = counts + 2 * nbk;
     d_bad = (int*)(counts + 3 * nbk);
-    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3 + sizeof(int), st));
+    uint32_t* work = counts + 3 * nbk + 1;
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nbk * 3 + 1), st));
     if (n) {
         GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_p, point_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
         GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_b, bucket_idx, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, st));
@@ -447,9 +564,10 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
         g1_scatter_kernel<<<g1, 256, 0, st>>>(d_b, d_p, (uint32_t)n, n_buckets, offsets, cursor, sorted);
         ctx->launches += 3;
     }
-    unsigned g2 = (unsigned)std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16);
-    msm_accumulate_kernel<0><<<g2, 128, 0, st>>>(srs->d, sorted, counts, offsets, (uint32_t)n, c, nbk, 0, (G1X*)res->d);
-    ctx->launches++;
+    {
+        int rc = msm_accumulate(ctx, srs->d, 0, sorted, counts, offsets, (uint32_t)n, c, nbk, work, (G1X*)res->d);
+        if (rc) return rc;
+    }
     int bad = 0;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));  // host index arrays may be released by the caller now
@@ -473,22 +591,8 @@ extern "C" int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, 
     cudaStream_t st = ctx->stream;
     int c = 0;
     while (((uint64_t)1 << c) < buckets->n) c++;
-    G1X* wsum = nullptr;
-    G1Aff* d_out = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&wsum, sizeof(G1X), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_out, sizeof(G1Aff), st));
-    const int T = 256;
-    GKR_CUDA_OK(ctx, cudaFuncSetAttribute(msm_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(G1X) * T)));
-    // buckets beyond n (up to the power of two) were written as infinity by the accumulate kernel
-    msm_reduce_kernel<<<1, T, sizeof(G1X) * T, st>>>((const G1X*)buckets->d, c, wsum);
-    msm_combine_kernel<<<1, 32, 0, st>>>(wsum, c, 1, d_out);
-    ctx->launches += 2;
-    GKR_CUDA_OK(ctx, cudaGetLastError());
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, d_out, sizeof(G1Aff), cudaMemcpyDeviceToHost, st));
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(wsum, st);
-    cudaFreeAsync(d_out, st);
-    return GKR_OK;
+    // buckets beyond n (up to the power of two) were written as infinity by the accumulate kernels
+    return msm_finish(ctx, (const G1X*)buckets->d, c, 1, out_xy);
 }
 
 // download bucket sums / any point set as affine (x, y) pairs (tests, and `c_comm`-style per-bucket inspection)
@@ -593,5 +697,15 @@ extern "C" int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uin
     cudaFreeAsync(Tx, st);
     cudaFreeAsync(Ta, st);
     *out = s;
+    return GKR_OK;
+}
+
+// test hook (no device needed): the host tail of an MSM -- Horner over `n_windows` extended-Jacobian window sums
+// (24 u64 each: X, Y, ZZ, ZZZ) with c doublings per window, normalised to affine.
+extern "C" int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_windows, uint64_t* out_xy) {
+    if (!window_sums || !out_xy || c < 0 || n_windows < 0) return GKR_ERR_ARG;
+    std::vector<gkr::G1XH> h(n_windows);
+    if (n_windows) std::memcpy(h.data(), window_sums, sizeof(gkr::G1XH) * n_windows);
+    gkr::g1h::horner_windows(h.data(), c, n_windows, out_xy);
     return GKR_OK;
 }

@@ -16,6 +16,8 @@ Claims are (point, evs) over python ints; tables, SRS and bucket sums never leav
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import binding as g
@@ -25,6 +27,24 @@ from .fieldutil import R_MOD, from_limbs, make_gamma_pows, to_limb1, to_limbs
 
 P = R_MOD
 ONE = None  # lincomb source standing for the all-ones table
+
+# optional span accounting (the reference prints a tracing span tree, examples/pippenger.rs:75-89): name -> seconds
+PROFILE = None
+
+
+class span:
+    def __init__(self, ctx, name):
+        self.ctx, self.name = ctx, name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.ctx.sync()
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        if PROFILE is not None:
+            self.ctx.sync()
+            PROFILE[self.name] = PROFILE.get(self.name, 0.0) + time.perf_counter() - self.t0
 
 
 def write_points(tr, pts):  # proof_transcript.rs:64-69; pts: (12,) limb arrays
@@ -115,6 +135,8 @@ class PushForwardState:
         self.ctx, self.key = ctx, key
         self.y_size, self.y_logsize, self.d_logsize, self.x_logsize, self.x_size, self.clm = y_size, y_logsize, d_logsize, x_logsize, x_size, clm
         nb = 1 << d_logsize
+        sp = span(ctx, "state: host bucketing (digits, counters, order)")
+        sp.__enter__()
         digits = scalar_digits(coefs_u64, y_size, d_logsize)
         counter = np.empty_like(digits)
         order = np.empty((y_size, x_size), np.uint32)
@@ -127,6 +149,9 @@ class PushForwardState:
             counter[y, o] = (ar - off[digits[y][o]]).astype(np.uint32)
             order[y], lens[y] = o, cnt
         self.digits, self.counter = digits, counter
+        sp.__exit__()
+        sp = span(ctx, "state: upload images / tables")
+        sp.__enter__()
         # image polynomials: row (y, digit) holds the coordinates of the points of that bucket in input order
         self.p_0, self.p_1 = ctx.upload(points_xy[0]), ctx.upload(points_xy[1])
         flat_order = order.reshape(-1)
@@ -144,6 +169,9 @@ class PushForwardState:
         ac_d = np.bincount(digits.reshape(-1), minlength=nb).astype(np.uint32)
         ac_c = np.bincount(counter.reshape(-1), minlength=x_size).astype(np.uint32)
         self.ac_d, self.ac_c = g.U32Buf(ctx, ac_d).to_field(negate=True), g.U32Buf(ctx, ac_c).to_field(negate=True)
+        sp.__exit__()
+        sp = span(ctx, "state: c/d bucket sums + running-sum commitments")
+        sp.__enter__()
         # c / d commitments: bucket sums over the SRS then running sums (pushforward.rs:398-456, 504-524)
         comm_mul = 1 << clm
         n_comms = -(-y_size // comm_mul)
@@ -159,8 +187,10 @@ class PushForwardState:
             self.c_buckets.append(cb)
             self.d_comm.append(db.weighted_sum())
             self.c_comm.append(cb.weighted_sum())
-        self.p_0_comm, self.p_1_comm = key.commit(self.p_0), key.commit(self.p_1)
-        self.ac_c_comm, self.ac_d_comm = key.commit(self.ac_c), key.commit(self.ac_d)
+        sp.__exit__()
+        with span(ctx, "state: 4 MSM commitments (p_0, p_1, ac_c, ac_d)"):
+            self.p_0_comm, self.p_1_comm = key.commit(self.p_0), key.commit(self.p_1)
+            self.ac_c_comm, self.ac_d_comm = key.commit(self.ac_c), key.commit(self.ac_d)
         self.c_pull = self.d_pull = None
 
     def second_phase(self, r):  # pushforward.rs:572-622
@@ -248,7 +278,8 @@ class LogupMainphase:
         return layers, (from_limbs(tmp[0].download())[0], from_limbs(tmp[1].download())[0])
 
     def prove(self, tr, claims, advice):  # logup_mainphase.rs:135-200
-        witness, (num, denom) = self.make_witness(advice)
+        with span(self.ctx, "logup: witness"):
+            witness, (num, denom) = self.make_witness(advice)
         assert denom != 0 and num == denom * claims % P
         tr.write_scalars(to_limbs([num, denom]))
         running = ([], [num, denom])
@@ -306,6 +337,8 @@ class PushforwardProtocol:
                 terms.append((ONE, L1(tau_s), 0, matrix_size, full - matrix_size))
             return ctx.lincomb(terms, full)
 
+        sp = span(ctx, "pushforward: table algebra")
+        sp.__enter__()
         c_adj, d_adj = adj(st.c_pull, st.c, tau_c), adj(st.d_pull, st.d, tau_d)
         c_pull_p = ctx.lincomb([(st.c_pull, L1(1), 0, 0, matrix_size)], full)
         d_pull_p = ctx.lincomb([(st.d_pull, L1(1), 0, 0, matrix_size)], full)
@@ -318,12 +351,16 @@ class PushforwardProtocol:
         suppression_total = 2 * (full - matrix_size) % P * H.inv(tau_s) % P if tau_s else 0
 
         m = xl + yl - 1
-        mainphase_claims = LogupMainphase(ctx, [m, m, xl, dl]).prove(tr, suppression_total,
-                                                                    [left, right, [st.ac_c, table_c], [st.ac_d, table_d]])
+        sp.__exit__()
+        with span(ctx, "pushforward: logup main phase"):
+            mainphase_claims = LogupMainphase(ctx, [m, m, xl, dl]).prove(tr, suppression_total,
+                                                                        [left, right, [st.ac_c, table_c], [st.ac_d, table_d]])
         assert len(mainphase_claims) == 3
         cd_claims, ac_c_claims, ac_d_claims = mainphase_claims
         cd_claims = DP.SplitAt(("HI", 0), 2).prove(tr, cd_claims)
         gammas = make_gamma_pows(gamma, 5)
+        sp = span(ctx, "pushforward: combined prod3 + frac sumcheck")
+        sp.__enter__()
         # p_folded = p_0 + gamma (p_1 - 1) + gamma^2 ; p_selector_prod[y, x] = eq_trunc(r_y)[y] * p_folded[x]  (:740-758)
         p_folded = ctx.lincomb([(st.p_0, L1(1), 0, 0, x_size), (st.p_1, L1(gammas[1]), 0, 0, x_size),
                                 (ONE, L1(gammas[2] - gammas[1]), 0, 0, x_size)], x_size)
@@ -355,6 +392,7 @@ class PushforwardProtocol:
         c_adj_ev, d_adj_ev, _ = from_limbs(frac.final_evals())
         prod3.destroy()
         frac.destroy()
+        sp.__exit__()
         adj_p_folded_ev = p_selector_prod_ev * H.inv(H.eq_trunc_evaluate(yl, y_size, r_y, output_point[:yl])) % P
         p_folded_ev = (adj_p_folded_ev + gamma) % P
         sel_ev = H.eq_sum(output_point[:yl], y_size)  # SelectorPoly::evaluate, verifier_polys.rs:68-71
@@ -398,9 +436,11 @@ class KnucklesOpening:
     def prove(self, tr, claim, advice):
         ctx, pk = self.ctx, self.key
         comm, point, ev_claim = claim
-        t, opening = pk.compute_t(advice, point)
+        with span(ctx, "knuckles: compute_t"):
+            t, opening = pk.compute_t(advice, point)
         assert from_limbs(opening)[0] == ev_claim
-        t_comm = pk.kzg.commit(t)
+        with span(ctx, "knuckles: commit t (MSM 2N-1)"):
+            t_comm = pk.kzg.commit(t)
         write_points(tr, [t_comm])
         x_l = tr.challenge(128)
         x = from_limbs(x_l)[0]
@@ -410,9 +450,11 @@ class KnucklesOpening:
         lam_l = tr.challenge(128)
         lam = from_limbs(lam_l)[0]
         p_lt = ctx.lincomb([(t, lam_l, 0, 0, len(t)), (advice, to_limb1(1), 0, 0, len(advice))], len(t))  # opening.rs:65-75
-        p_lt_x_proof, _ = pk.kzg.open(p_lt, x_l)
+        with span(ctx, "knuckles: open p_lt (div + MSM)"):
+            p_lt_x_proof, _ = pk.kzg.open(p_lt, x_l)
         write_points(tr, [p_lt_x_proof])
-        t_kx_proof, t_kx = pk.kzg.open(t, to_limb1(kx))
+        with span(ctx, "knuckles: open t (div + MSM)"):
+            t_kx_proof, t_kx = pk.kzg.open(t, to_limb1(kx))
         tr.write_scalars(t_kx.reshape(1, 4))
         write_points(tr, [t_kx_proof])
         fin = from_limbs(tr.challenge(128))[0]
@@ -430,7 +472,8 @@ class PippengerWG:
 
     def __init__(self, ctx, points_xy, coefs_u64, y_size, y_logsize, d_logsize, x_logsize, clm, key):
         self.beginning = PushForwardState(ctx, points_xy, coefs_u64, y_size, y_logsize, d_logsize, x_logsize, clm, key)
-        self.ending = DP.PippengerEndingWG(ctx, y_logsize, d_logsize, x_logsize, DP.GlueSplit.witness(ctx, self.beginning.image))
+        with span(ctx, "witness: bintree + triangle (EC-add maps)"):
+            self.ending = DP.PippengerEndingWG(ctx, y_logsize, d_logsize, x_logsize, DP.GlueSplit.witness(ctx, self.beginning.image))
 
 
 class Pippenger:
@@ -451,13 +494,18 @@ class Pippenger:
         write_points(tr, st.d_comm)
         for pt in (st.p_0_comm, st.p_1_comm, st.ac_c_comm, st.ac_d_comm):
             write_points(tr, [pt])
-        claims = self.ending.prove(tr, claims, state.ending)
+        with span(ctx, "prove: ending GKR (triangle + bintree sumchecks)"):
+            claims = self.ending.prove(tr, claims, state.ending)
         claims = DP.GlueSplit().prove(tr, claims)
-        st.second_phase(claims[0])
+        with span(ctx, "prove: second phase (pulls + msm_nonaff)"):
+            st.second_phase(claims[0])
         write_points(tr, st.c_pull_comm)
         write_points(tr, st.d_pull_comm)
-        fc = b.prove(tr, claims, st)
+        with span(ctx, "prove: pushforward"):
+            fc = b.prove(tr, claims, st)
         gamma = fc["gamma"]
+        sp = span(ctx, "prove: opening inputs (lincombs)")
+        sp.__enter__()
         # opening claims (pippenger.rs:166-205)
         matrix_pt, matrix_evs = fc["matrix"]
         p_folded_ev, c_pull_ev, d_pull_ev, c_ev, d_ev = matrix_evs
@@ -491,13 +539,16 @@ class Pippenger:
               ctx.lincomb([(st.ac_c, one, 0, 0, len(st.ac_c))], 1 << nv),
               ctx.lincomb([(st.ac_d, one, 0, 0, len(st.ac_d))], 1 << nv),
               combined_witness]
-        mo_point, mo_evs = MultiOpenReduction(ctx, nv, 4).prove(tr, oclaims, mw)
+        sp.__exit__()
+        with span(ctx, "prove: multiopen reduction"):
+            mo_point, mo_evs = MultiOpenReduction(ctx, nv, 4).prove(tr, oclaims, mw)
         q = from_limbs(tr.challenge(128))[0]
         qs = make_gamma_pows(q, 4)
         folded_comm = g1_lincomb(ctx, [qs[0], qs[0] * gamma % P, qs[1], qs[2], qs[3]],
                                  [st.p_0_comm, st.p_1_comm, st.ac_c_comm, st.ac_d_comm, combined_comm])
         folded_witness = ctx.lincomb([(mw[i], to_limb1(qs[i]), 0, 0, 1 << nv) for i in range(4)], 1 << nv)
-        return KnucklesOpening(ctx, self.key).prove(tr, (folded_comm, mo_point, H.gamma_rlc(q, mo_evs)), folded_witness)
+        with span(ctx, "prove: knuckles opening"):
+            return KnucklesOpening(ctx, self.key).prove(tr, (folded_comm, mo_point, H.gamma_rlc(q, mo_evs)), folded_witness)
 
 
 def pippenger_config(d_logsize, x_logsize, num_bits, clm):  # build_pippenger_data, pippenger.rs:462-497

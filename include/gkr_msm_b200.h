@@ -201,6 +201,9 @@ int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* point_i
                        uint32_t n_buckets, gkr_srs** out);
 int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t* out_xy);
 int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
+/* test hook, host only: the O(windows) tail of every MSM (Horner over the extended-Jacobian window sums X, Y, ZZ, ZZZ --
+ * 24 u64 each -- with c doublings per window, then one inversion to affine) runs on the CPU; see csrc/host_g1.hpp. */
+int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_windows, uint64_t* out_xy);
 
 /* ---- univariate / element-wise table algebra -----------------------------------------
  * gkr_u32buf: digit / counter arrays resident on the device.

@@ -98,3 +98,26 @@ def test_msm_linearity_large(ctx):
     # and against the oracle through the 16 distinct bases
     agg = [sum(sv[i] for i in range(j, n, 16)) % P for j in range(16)]
     assert ms == CV.g1_msm(base_pts, agg)
+
+
+@pytest.mark.parametrize("kind", ["equal", "small", "mixed"])
+def test_msm_skewed_buckets(ctx, kind):
+    """bucket sizes far from uniform (>= 256 entries: the block-per-bucket path; counting-sorted light buckets)"""
+    rng = random.Random(len(kind))
+    n = 3000
+    base_pts = [rand_g1(rng) for _ in range(16)]
+    pts = [base_pts[rng.randrange(16)] for _ in range(n)]
+    if kind == "equal":
+        s0 = rng.randrange(P)
+        sc = [s0] * n
+    elif kind == "small":
+        sc = [rng.randrange(4) for _ in range(n)]
+    else:
+        sc = [rng.randrange(P) if i % 3 else P - 1 for i in range(n)]
+    srs = g.Srs(ctx, aff_to_limbs(pts))
+    got = res_to_point(srs.msm(ctx.upload(to_limbs(sc))))
+    # group by base point: sum_j (sum of the scalars on base j) * base_j
+    tot = {}
+    for p, s in zip(pts, sc):
+        tot[p] = (tot.get(p, 0) + s) % P
+    assert got == CV.g1_msm(list(tot.keys()), list(tot.values()))

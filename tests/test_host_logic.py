@@ -55,3 +55,45 @@ def test_cpp_transcript_rejects_non_canonical_scalar():
     bad = np.array([[0xFFFFFFFFFFFFFFFF] * 4], dtype=np.uint64)
     with pytest.raises(g.GkrError):
         t.write_scalars(bad)
+
+
+def test_host_g1_horner_matches_group_law():
+    """the CPU tail of every MSM (csrc/host_g1.hpp): Horner over extended-Jacobian window sums + normalisation"""
+    import ctypes as C
+
+    from oracle.pyref import curves as CV
+    from oracle.pyref.field import FQ_MODULUS as Q
+    from oracle.pyref.field import fq_vec_from_mont_u64, fq_vec_to_mont_u64
+
+    lib = g.load_library()
+    lib.gkr_host_g1_horner.restype = C.c_int
+    lib.gkr_host_g1_horner.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rng = random.Random(7)
+    for c, n_windows in [(4, 1), (5, 3), (13, 20), (16, 16), (0, 1)]:
+        pts = [CV.g1_mul(rng.randrange(1, P), CV.G1_GEN) for _ in range(n_windows)]
+        if n_windows > 2:
+            pts[1] = None  # an empty window
+            pts[-1] = pts[0]
+        ws = np.zeros((n_windows, 24), np.uint64)
+        for i, pt in enumerate(pts):
+            if pt is None:
+                continue
+            z = rng.randrange(1, Q)
+            zz, zzz = z * z % Q, z * z * z % Q
+            ws[i] = fq_vec_to_mont_u64([pt[0] * zz % Q, pt[1] * zzz % Q, zz, zzz]).reshape(24)
+        out = np.zeros(12, np.uint64)
+        assert lib.gkr_host_g1_horner(ws.ctypes.data, c, n_windows, out.ctypes.data) == 0
+        want = None
+        for i, pt in enumerate(pts):
+            want = CV.g1_add(want, CV.g1_mul(1 << (c * i), pt) if pt is not None else None)
+        x, y = fq_vec_from_mont_u64(out.reshape(2, 6))
+        assert (None if (x, y) == (0, 0) else (x, y)) == want
+    # P + (-P) and doubling inside the Horner chain
+    pt = CV.g1_mul(5, CV.G1_GEN)
+    neg = (pt[0], Q - pt[1])
+    ws = np.zeros((2, 24), np.uint64)
+    ws[0] = fq_vec_to_mont_u64([neg[0], neg[1], 1, 1]).reshape(24)
+    ws[1] = fq_vec_to_mont_u64([CV.g1_mul(5 * pow(2, -1, P) % P, CV.G1_GEN)[0], CV.g1_mul(5 * pow(2, -1, P) % P, CV.G1_GEN)[1], 1, 1]).reshape(24)
+    out = np.ones(12, np.uint64)
+    assert lib.gkr_host_g1_horner(ws.ctypes.data, 1, 2, out.ctypes.data) == 0
+    assert not out.any()  # 2 * (5/2 G) - 5 G = infinity
