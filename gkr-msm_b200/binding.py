@@ -794,4 +794,37 @@ def _ctx_upload_vecvec_flat(self, flat, lens, row_pad, col_pad, row_logsize, col
     return VecVec(self, h)
 
 
+def _ctx_vecvec_gather(self, src, idx, lens, row_pad, col_pad, row_logsize, col_logsize) -> "VecVec":
+    """VecVecPolynomial::new over rows gathered on the device: row r = src[idx[..]] (src None: all ones)."""
+    lib = self.lib
+    if not hasattr(lib.gkr_vecvec_gather, "_sig"):
+        lib.gkr_vecvec_gather.restype = C.c_int
+        lib.gkr_vecvec_gather.argtypes = [_vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]
+        lib.gkr_vecvec_gather._sig = True
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    rp, cp = _limbs(row_pad).reshape(4), _limbs(col_pad).reshape(4)
+    h = _vp()
+    self.check(lib.gkr_vecvec_gather(self.h, src.h if src is not None else None, _ptr(idx), _ptr(lens), lens.shape[0], _ptr(rp), _ptr(cp),
+                                     row_logsize, col_logsize, C.byref(h)))
+    return VecVec(self, h)
+
+
 Context.upload_vecvec_flat = _ctx_upload_vecvec_flat
+Context.vecvec_gather = _ctx_vecvec_gather
+
+
+def pushforward_bucketize(coefs_u64, y_size: int, d_logsize: int):
+    """PushForwardState::new index bookkeeping (pushforward.rs:351-396) in the host library: returns
+    (digits[y][n], counter[y][n], order[y][n], lens[y][2^d]) as uint32 arrays."""
+    lib = load_library()
+    lib.gkr_pushforward_bucketize.restype = C.c_int
+    lib.gkr_pushforward_bucketize.argtypes = [_vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]
+    co = np.ascontiguousarray(coefs_u64, dtype=np.uint64).reshape(-1, 4)
+    n = co.shape[0]
+    digits, counter, order = (np.empty((y_size, n), np.uint32) for _ in range(3))
+    lens = np.empty((y_size, 1 << d_logsize), np.uint32)
+    rc = lib.gkr_pushforward_bucketize(_ptr(co), n, y_size, d_logsize, _ptr(digits), _ptr(counter), _ptr(order), _ptr(lens))
+    if rc:
+        raise GkrError(rc, "gkr_pushforward_bucketize: bad arguments")
+    return digits, counter, order, lens

@@ -149,3 +149,48 @@ extern "C" int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_ro
     }
     return GKR_OK;
 }
+
+// ---- PushForwardState::new, index bookkeeping (pushforward.rs:351-396) --------------------------------------------
+// digits[y][x] = (coef_x >> (y d)) & (2^d - 1); counter[y][x] = rank of x inside its bucket (input order);
+// order[y] = the x of row y sorted by digit (stable) = the bucket contents back to back; lens[y][b] = bucket sizes.
+// Pure host work (a counting sort per digit row, one thread per row) -- no field arithmetic, nothing for the device.
+#include <thread>
+extern "C" int gkr_pushforward_bucketize(const uint64_t* coefs, uint64_t n, uint32_t y_size, uint32_t d_logsize, uint32_t* digits,
+                                         uint32_t* counter, uint32_t* order, uint32_t* lens) {
+    if (!coefs || !digits || !counter || !order || !lens || d_logsize == 0 || d_logsize > 24 || (uint64_t)y_size * d_logsize > 256 ||
+        n >= ((uint64_t)1 << 32))
+        return GKR_ERR_ARG;
+    const uint32_t nb = 1u << d_logsize, mask = nb - 1;
+    auto do_row = [&](uint32_t y) {
+        uint32_t* dg = digits + (size_t)y * n;
+        uint32_t* ct = counter + (size_t)y * n;
+        uint32_t* od = order + (size_t)y * n;
+        uint32_t* ln = lens + (size_t)y * nb;
+        const uint32_t bit = y * d_logsize, limb = bit >> 6, sh = bit & 63;
+        std::vector<uint32_t> cnt(nb, 0), off(nb, 0);
+        for (uint64_t x = 0; x < n; x++) {
+            const uint64_t* c = coefs + 4 * x;
+            uint64_t v = c[limb] >> sh;
+            if (sh && sh + d_logsize > 64 && limb + 1 < 4) v |= c[limb + 1] << (64 - sh);
+            const uint32_t d = (uint32_t)v & mask;
+            dg[x] = d;
+            ct[x] = cnt[d]++;
+        }
+        uint32_t acc = 0;
+        for (uint32_t b = 0; b < nb; b++) {
+            ln[b] = cnt[b];
+            off[b] = acc;
+            acc += cnt[b];
+        }
+        for (uint64_t x = 0; x < n; x++) od[off[dg[x]] + ct[x]] = (uint32_t)x;
+    };
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = std::max(1u, std::min(hw ? hw : 4u, y_size));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&, t]() {
+            for (uint32_t y = t; y < y_size; y += nt) do_row(y);
+        });
+    for (auto& t : th) t.join();
+    return GKR_OK;
+}

@@ -916,6 +916,71 @@ extern "C" int gkr_vecvec_upload(gkr_ctx* ctx, const uint64_t* flat, const uint3
     return GKR_OK;
 }
 
+// VecVecPolynomial::new over rows gathered from a resident table: row r holds src[idx[..]] for its row_len[r] consecutive
+// entries of `idx` (src == NULL: the all-ones table), odd rows padded with row_pad.  This is how PushForwardState::new builds
+// the bucket images of the point coordinates (pushforward.rs:363-396) without moving the coordinates through the host.
+__global__ void vecvec_gather_kernel(Fr* out, const Fr* src, uint64_t src_n, const uint32_t* pidx, uint64_t total, Fr row_pad, int* bad) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = pidx[i];
+        Fr v;
+        if (k == 0xffffffffu) v = row_pad;
+        else if (!src) v = fr_one();
+        else if (k < src_n) v = src[k];
+        else { *bad = 1; v = fr_zero(); }
+        out[i] = v;
+    }
+}
+extern "C" int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, const uint32_t* row_len, uint32_t n_rows,
+                                 const uint64_t row_pad[4], const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!out || !row_pad || !col_pad || (n_rows && (!row_len || !idx))) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (col_logsize >= 32 || row_logsize >= 32 || n_rows > ((uint64_t)1 << col_logsize)) return ctx->fail(GKR_ERR_ARG, "too many rows for col_logsize");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    gkr_vecvec* v = new gkr_vecvec();
+    v->ctx = ctx;
+    v->row_pad = frh_from_limbs(row_pad);
+    v->col_pad = frh_from_limbs(col_pad);
+    v->row_logsize = row_logsize;
+    v->col_logsize = col_logsize;
+    v->row_len.resize(n_rows);
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        if (row_len[r] > ((uint64_t)1 << row_logsize)) { delete v; return ctx->fail(GKR_ERR_ARG, "row longer than 1 << row_logsize"); }
+        v->row_len[r] = (row_len[r] + 1) & ~1u;
+        total += v->row_len[r];
+    }
+    v->total = total;
+    std::vector<uint32_t> pidx(std::max<uint64_t>(total, 1));
+    uint64_t so = 0, dof = 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        if (row_len[r]) std::memcpy(pidx.data() + dof, idx + so, sizeof(uint32_t) * row_len[r]);
+        if (row_len[r] & 1) pidx[dof + row_len[r]] = 0xffffffffu;
+        so += row_len[r];
+        dof += v->row_len[r];
+    }
+    uint32_t* d_idx = nullptr;
+    cudaStream_t st = ctx->stream;
+    cudaError_t e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_idx, sizeof(uint32_t) * (std::max<uint64_t>(total, 1) + 1), st);
+    int* d_bad = (int*)(d_idx + std::max<uint64_t>(total, 1));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    if (e == cudaSuccess && total) e = cudaMemcpyAsync(d_idx, pidx.data(), sizeof(uint32_t) * total, cudaMemcpyHostToDevice, st);
+    int bad = 0;
+    if (e == cudaSuccess && total) {
+        unsigned g = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 8);
+        vecvec_gather_kernel<<<g, 256, 0, st>>>(v->d, src ? src->d : nullptr, src ? src->n : 0, d_idx, total, fr_from_host(v->row_pad), d_bad);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (d_idx) cudaFreeAsync(d_idx, st);
+    if (e != cudaSuccess) { gkr_vecvec_free(v); return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
+    if (bad) { gkr_vecvec_free(v); return ctx->fail(GKR_ERR_ARG, "gather index out of range"); }
+    *out = v;
+    return GKR_OK;
+}
+
 extern "C" uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v) { return v ? (uint32_t)v->row_len.size() : 0; }
 extern "C" uint64_t gkr_vecvec_total_len(const gkr_vecvec* v) { return v ? v->total : 0; }
 

@@ -201,7 +201,7 @@ __global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, in
 // one thread per bucket would serialise thousands of additions.  Buckets are therefore counting-sorted by size
 // (descending): buckets with >= MSM_CAP entries are summed by a whole block each (strided partial sums + shared-memory
 // tree), the rest by one thread each, and because neighbouring threads own buckets of equal size warps do not diverge.
-#define MSM_CAP 256
+#define MSM_CAP 32
 
 __global__ void msm_bin_hist_kernel(const uint32_t* counts, uint64_t nbk, uint32_t* bins /* [MSM_CAP + 1] */) {
     __shared__ uint32_t sh[MSM_CAP + 1];

@@ -137,17 +137,7 @@ class PushForwardState:
         nb = 1 << d_logsize
         sp = span(ctx, "state: host bucketing (digits, counters, order)")
         sp.__enter__()
-        digits = scalar_digits(coefs_u64, y_size, d_logsize)
-        counter = np.empty_like(digits)
-        order = np.empty((y_size, x_size), np.uint32)
-        lens = np.empty((y_size, nb), np.uint32)
-        ar = np.arange(x_size, dtype=np.int64)
-        for y in range(y_size):
-            o = np.argsort(digits[y], kind="stable")
-            cnt = np.bincount(digits[y], minlength=nb)
-            off = np.concatenate([[0], np.cumsum(cnt)[:-1]])
-            counter[y, o] = (ar - off[digits[y][o]]).astype(np.uint32)
-            order[y], lens[y] = o, cnt
+        digits, counter, order, lens = g.pushforward_bucketize(coefs_u64, y_size, d_logsize)
         self.digits, self.counter = digits, counter
         sp.__exit__()
         sp = span(ctx, "state: upload images / tables")
@@ -158,12 +148,10 @@ class PushForwardState:
         flat_lens = lens.reshape(-1)
         one = g.MONT_ONE
         zero = np.zeros(4, np.uint64)
-        ones_flat = np.broadcast_to(one, (flat_order.shape[0], 4))
-        self.image = [
-            ctx.upload_vecvec_flat(points_xy[0][flat_order], flat_lens, zero, zero, x_logsize, y_logsize + d_logsize),
-            ctx.upload_vecvec_flat(points_xy[1][flat_order], flat_lens, one, one, x_logsize, y_logsize + d_logsize),
-            ctx.upload_vecvec_flat(ones_flat, flat_lens, zero, zero, x_logsize, y_logsize + d_logsize),
-        ]
+        cl = y_logsize + d_logsize
+        self.image = [ctx.vecvec_gather(self.p_0, flat_order, flat_lens, zero, zero, x_logsize, cl),
+                      ctx.vecvec_gather(self.p_1, flat_order, flat_lens, one, one, x_logsize, cl),
+                      ctx.vecvec_gather(None, flat_order, flat_lens, zero, zero, x_logsize, cl)]
         self.d_idx, self.c_idx = g.U32Buf(ctx, digits.reshape(-1)), g.U32Buf(ctx, counter.reshape(-1))
         self.d, self.c = self.d_idx.to_field(), self.c_idx.to_field()
         ac_d = np.bincount(digits.reshape(-1), minlength=nb).astype(np.uint32)

@@ -141,6 +141,10 @@ void gkr_so_destroy(gkr_so* so);
 typedef struct gkr_vecvec gkr_vecvec;
 int gkr_vecvec_upload(gkr_ctx* ctx, const uint64_t* flat, const uint32_t* row_len, uint32_t n_rows, const uint64_t row_pad[4],
                       const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out);
+/* the same over rows gathered from a resident table: row r = src[idx[..]] for its row_len[r] consecutive entries of the
+ * host array `idx` (src == NULL: the all-ones table) -- the bucket images of PushForwardState::new (pushforward.rs:363-396). */
+int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, const uint32_t* row_len, uint32_t n_rows,
+                      const uint64_t row_pad[4], const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out);
 uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v);
 uint64_t gkr_vecvec_total_len(const gkr_vecvec* v); /* elements after even-padding */
 int gkr_vecvec_download(gkr_ctx* ctx, const gkr_vecvec* v, uint64_t* flat_out, uint32_t* row_len_out, uint64_t row_pad[4],
@@ -228,6 +232,12 @@ int gkr_knuckles_create(gkr_ctx* ctx, uint32_t num_vars, const uint64_t k[4], gk
 void gkr_knuckles_free(gkr_knuckles* key);
 int gkr_knuckles_compute_t(gkr_ctx* ctx, const gkr_knuckles* key, const gkr_table* poly, const uint64_t* point, uint32_t n_point,
                            gkr_table** t_out, uint64_t opening[4]);
+
+/* PushForwardState::new index bookkeeping (pushforward.rs:351-396), host only: digit / counter matrices ([y_size][n]), the
+ * stable digit order of every row (= bucket contents back to back) and the bucket sizes ([y_size][2^d]).  coefs: n x 4 plain
+ * little-endian u64 (the integer value of the Bandersnatch scalar, not Montgomery form). */
+int gkr_pushforward_bucketize(const uint64_t* coefs, uint64_t n, uint32_t y_size, uint32_t d_logsize, uint32_t* digits,
+                              uint32_t* counter, uint32_t* order, uint32_t* lens);
 
 /* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
  * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */

@@ -97,3 +97,25 @@ def test_host_g1_horner_matches_group_law():
     out = np.ones(12, np.uint64)
     assert lib.gkr_host_g1_horner(ws.ctypes.data, 1, 2, out.ctypes.data) == 0
     assert not out.any()  # 2 * (5/2 G) - 5 G = infinity
+
+
+def test_pushforward_bucketize_matches_reference_bookkeeping():
+    """digits / counters / buckets of PushForwardState::new (pushforward.rs:351-396) from the host library"""
+    rng = random.Random(11)
+    for d, y_size, nbits, n in [(3, 5, 15, 64), (8, 16, 128, 500), (10, 13, 128, 300), (7, 36, 252, 100), (8, 32, 253, 128)]:
+        coefs = [rng.randrange(1 << nbits) for _ in range(n)]
+        co = np.array([[(c >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for c in coefs], dtype=np.uint64)
+        digits, counter, order, lens = g.pushforward_bucketize(co, y_size, d)
+        for y in range(y_size):
+            want = [(c >> (y * d)) & ((1 << d) - 1) for c in coefs]
+            assert [int(v) for v in digits[y]] == want
+            buckets = [[] for _ in range(1 << d)]
+            cnt = []
+            for x, dg in enumerate(want):
+                cnt.append(len(buckets[dg]))
+                buckets[dg].append(x)
+            assert [int(v) for v in counter[y]] == cnt
+            assert [int(v) for v in order[y]] == [x for b in buckets for x in b]
+            assert [int(v) for v in lens[y]] == [len(b) for b in buckets]
+    with pytest.raises(g.GkrError):
+        g.pushforward_bucketize(np.zeros((4, 4), np.uint64), 40, 8)
