@@ -580,6 +580,10 @@ def _srs_sigs(lib):
     lib.gkr_msm_g1.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp]
     lib.gkr_srs_mock_setup.restype = C.c_int
     lib.gkr_srs_mock_setup.argtypes = [_vp, _vp, _vp, C.c_uint64, C.POINTER(_vp)]
+    lib.gkr_msm_g1_batch.restype = C.c_int
+    lib.gkr_msm_g1_batch.argtypes = [_vp, _vp, C.c_uint64, C.c_uint64, C.c_uint32, _vp, C.c_uint64, _vp]
+    lib.gkr_g1_weighted_bucket_sums.restype = C.c_int
+    lib.gkr_g1_weighted_bucket_sums.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp]
     lib.gkr_srs_upload._sig = True
 
 
@@ -599,6 +603,18 @@ class Srs:
         n = len(scalars) if n is None else n
         out = np.zeros(12, np.uint64)
         self.ctx.check(self.ctx.lib.gkr_msm_g1(self.ctx.h, self.h, first, scalars.h, n, _ptr(out)))
+        return out
+
+    def msm_batch(self, scalars: "Table", n: int, first: int, stride: int, count: int) -> np.ndarray:
+        """`count` MSMs with the same scalars over the base ranges [first + p * stride, + n): (count, 12) affine results."""
+        out = np.zeros((count, 12), np.uint64)
+        self.ctx.check(self.ctx.lib.gkr_msm_g1_batch(self.ctx.h, self.h, first, stride, count, scalars.h, n, _ptr(out)))
+        return out
+
+    def weighted_sums(self, group_log: int, count: int, first: int = 0) -> np.ndarray:
+        """running-sum commitments sum_i i * B[first + (k << group_log) + i] of `count` bucket groups: (count, 12)."""
+        out = np.zeros((count, 12), np.uint64)
+        self.ctx.check(self.ctx.lib.gkr_g1_weighted_bucket_sums(self.ctx.h, self.h, first, group_log, count, _ptr(out)))
         return out
 
     def free(self):

@@ -13,6 +13,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "host_g1.hpp"
+#include <thread>
 
 // q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 __device__ __constant__ uint32_t FQ_P[12] = {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
@@ -266,35 +267,43 @@ __device__ __forceinline__ void msm_add_base(G1X& acc, const void* bases, uint32
     }
 }
 
-// light buckets (< MSM_CAP entries): one thread per bucket, in size order
+// light buckets (< MSM_CAP entries): one thread per bucket, in size order.  `n_problems` independent MSMs that share the
+// scalars (hence the digit sort) but read bases shifted by p * problem_stride accumulate into buckets[p * total + b].
 template <int KIND>
 __global__ void __launch_bounds__(128) msm_accumulate_light_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts,
                                                                     const uint32_t* offsets, uint32_t n, int c, uint64_t total,
-                                                                    const uint32_t* order, const uint32_t* bins, G1X* buckets) {
+                                                                    const uint32_t* order, const uint32_t* bins, G1X* buckets,
+                                                                    uint32_t n_problems, uint32_t problem_stride) {
     const uint64_t n_heavy = bins[MSM_CAP];
-    for (uint64_t i = n_heavy + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t b = order[i];
+    const uint64_t n_light = total - n_heavy;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_light * n_problems; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)(i / n_light);
+        const uint32_t b = order[n_heavy + i % n_light];
         const uint32_t cnt = counts[b];
+        const uint32_t shift = p * problem_stride;
         G1X acc = g1x_inf();
         const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
-        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, bases, idx[k]);
-        buckets[b] = acc;
+        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, bases, idx[k] + shift);
+        buckets[(size_t)p * total + b] = acc;
     }
 }
 // heavy buckets: one block per bucket
 template <int KIND>
 __global__ void __launch_bounds__(256) msm_accumulate_heavy_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts,
-                                                                    const uint32_t* offsets, uint32_t n, int c, const uint32_t* order,
-                                                                    const uint32_t* bins, G1X* buckets) {
+                                                                    const uint32_t* offsets, uint32_t n, int c, uint64_t total,
+                                                                    const uint32_t* order, const uint32_t* bins, G1X* buckets,
+                                                                    uint32_t n_problems, uint32_t problem_stride) {
     extern __shared__ unsigned char smem_raw[];
     G1X* sh = reinterpret_cast<G1X*>(smem_raw);
     const uint32_t n_heavy = bins[MSM_CAP];
-    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
-        const uint32_t b = order[h];
+    for (uint64_t h = blockIdx.x; h < (uint64_t)n_heavy * n_problems; h += gridDim.x) {
+        const uint32_t p = (uint32_t)(h / n_heavy);
+        const uint32_t b = order[h % n_heavy];
         const uint32_t cnt = counts[b];
+        const uint32_t shift = p * problem_stride;
         const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
         G1X acc = g1x_inf();
-        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, bases, idx[k]);
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, bases, idx[k] + shift);
         sh[threadIdx.x] = acc;
         __syncthreads();
         for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
@@ -305,7 +314,7 @@ __global__ void __launch_bounds__(256) msm_accumulate_heavy_kernel(const void* b
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) buckets[b] = sh[0];
+        if (threadIdx.x == 0) buckets[(size_t)p * total + b] = sh[0];
         __syncthreads();
     }
 }
@@ -407,10 +416,10 @@ static int pick_window(uint64_t n) {
     return c;
 }
 
-// size-ordered bucket accumulation: counts/offsets [nbk], sorted [W][n] -> buckets [nbk].  `work` holds
+// size-ordered bucket accumulation: counts/offsets [nbk], sorted [W][n] -> buckets [n_problems][nbk].  `work` holds
 // order [nbk] followed by bins / bin_off / bin_cursor [3 * (MSM_CAP + 1)].
 static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint32_t* sorted, const uint32_t* counts, const uint32_t* offsets,
-                          uint32_t n, int c, uint64_t nbk, uint32_t* work, G1X* buckets) {
+                          uint32_t n, int c, uint64_t nbk, uint32_t* work, G1X* buckets, uint32_t n_problems = 1, uint32_t problem_stride = 0) {
     cudaStream_t st = ctx->stream;
     uint32_t* order = work;
     uint32_t* bins = work + nbk;
@@ -421,27 +430,22 @@ static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint3
     msm_bin_hist_kernel<<<gb, 256, 0, st>>>(counts, nbk, bins);
     msm_bin_scan_kernel<<<1, 32, 0, st>>>(bins, bin_off);
     msm_bin_scatter_kernel<<<gb, 256, 0, st>>>(counts, nbk, bin_off, bin_cursor, order);
-    unsigned gl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk + 127) / 128, (uint64_t)ctx->num_sms * 16));
+    unsigned gl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk * n_problems + 127) / 128, (uint64_t)ctx->num_sms * 16));
     unsigned gh = (unsigned)ctx->num_sms * 2;
     const size_t shh = sizeof(G1X) * 256;
-    if (kind == 2) {
-        msm_accumulate_heavy_kernel<2><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, order, bins, buckets);
-        msm_accumulate_light_kernel<2><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets);
-    } else if (kind == 1) {
-        msm_accumulate_heavy_kernel<1><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, order, bins, buckets);
-        msm_accumulate_light_kernel<1><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets);
-    } else {
-        msm_accumulate_heavy_kernel<0><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, order, bins, buckets);
-        msm_accumulate_light_kernel<0><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets);
-    }
+#define GKR_MSM_ACC(K)                                                                                                                       \
+    msm_accumulate_heavy_kernel<K><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets, n_problems, problem_stride); \
+    msm_accumulate_light_kernel<K><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets, n_problems, problem_stride);
+    if (kind == 2) { GKR_MSM_ACC(2) } else if (kind == 1) { GKR_MSM_ACC(1) } else { GKR_MSM_ACC(0) }
+#undef GKR_MSM_ACC
     ctx->launches += 5;
     GKR_CUDA_OK(ctx, cudaGetLastError());
     return GKR_OK;
 }
 
-// sum_w 2^(c w) sum_d d * buckets[w][d] as an affine point: segment running sums and the per-window tree on the device,
-// Horner over the W window sums and the inversion on the host (host_g1.hpp).
-static int msm_finish(gkr_ctx* ctx, const G1X* buckets, int c, int W, uint64_t* out_xy) {
+// window sums S_w = sum_d d * buckets[w][d] for W consecutive groups of 2^c buckets: segment running sums and the
+// per-group tree on the device, result (extended Jacobian) copied to the host.
+static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, std::vector<gkr::G1XH>& h) {
     cudaStream_t st = ctx->stream;
     const int seg_log = c < 3 ? c : 3;
     const uint32_t segs = 1u << (c - seg_log);
@@ -453,26 +457,41 @@ static int msm_finish(gkr_ctx* ctx, const G1X* buckets, int c, int W, uint64_t* 
     msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs, wsums);
     ctx->launches += 2;
     GKR_CUDA_OK(ctx, cudaGetLastError());
-    std::vector<gkr::G1XH> h(W);
+    h.resize(W);
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(h.data(), wsums, sizeof(G1X) * W, cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
     cudaFreeAsync(seg_out, st);
-    gkr::g1h::horner_windows(h.data(), c, W, out_xy);
     return GKR_OK;
 }
 
-// <bases[first .. first+n), scalars>   scalars: device table of n Fr (Montgomery).  out_xy: affine result, 12 u64
-// (x then y, Montgomery form; all zero for the point at infinity).
-extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
+// host tail for `n_problems` MSMs of W windows each (window sums back to back): Horner + inversion per problem
+// (host_g1.hpp), one thread per problem when there are several.
+static void msm_host_tail(const std::vector<gkr::G1XH>& h, int c, int W, uint32_t n_problems, uint64_t* out_xy) {
+    if (n_problems == 1) {
+        gkr::g1h::horner_windows(h.data(), c, W, out_xy);
+        return;
+    }
+    unsigned hw = std::thread::hardware_concurrency();
+    unsigned nt = std::max(1u, std::min(hw ? hw : 4u, n_problems));
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&, t]() {
+            for (uint32_t p = t; p < n_problems; p += nt) gkr::g1h::horner_windows(h.data() + (size_t)p * W, c, W, out_xy + 12 * (size_t)p);
+        });
+    for (auto& t : th) t.join();
+}
+
+static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems, const gkr_table* scalars,
+                       uint64_t n, uint64_t* out_xy) {
     if (!ctx) return GKR_ERR_ARG;
-    if (!srs || !scalars || !out_xy) return ctx->fail(GKR_ERR_ARG, "null argument");
-    if (first + n > srs->n) return ctx->fail(GKR_ERR_ARG, "Vector is too large.");  // kzg.rs:124
+    if (!srs || !scalars || !out_xy || n_problems == 0) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (first + (uint64_t)(n_problems - 1) * problem_stride + n > srs->n) return ctx->fail(GKR_ERR_ARG, "Vector is too large.");  // kzg.rs:124
     if (scalars->n < n) return ctx->fail(GKR_ERR_ARG, "fewer scalars than requested");
-    if (n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "MSM larger than 2^31 points");
+    if (srs->n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "MSM larger than 2^31 points");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (n == 0) {
-        std::memset(out_xy, 0, 96);
+        std::memset(out_xy, 0, 96 * (size_t)n_problems);
         return GKR_OK;
     }
     const int c = pick_window(n);
@@ -486,7 +505,7 @@ extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, cons
     offsets = counts + nbk;
     cursor = counts + 2 * nbk;
     work = counts + 3 * nbk;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&buckets, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&buckets, sizeof(G1X) * nbk * n_problems, st));
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
     msm_digits_kernel<<<g1, 256, 0, st>>>(scalars->d, (uint32_t)n, c, W, digits, counts);
@@ -494,13 +513,28 @@ extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, cons
     msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, c, W, offsets, cursor, sorted);
     ctx->launches += 3;
     const void* bases = (const unsigned char*)srs->d + first * srs->stride();
-    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, work, buckets);
-    if (rc == GKR_OK) rc = msm_finish(ctx, buckets, c, W, out_xy);
+    std::vector<gkr::G1XH> h;
+    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, work, buckets, n_problems, (uint32_t)problem_stride);
+    if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, c, (uint32_t)W * n_problems, h);
     cudaFreeAsync(digits, st);
     cudaFreeAsync(sorted, st);
     cudaFreeAsync(counts, st);
     cudaFreeAsync(buckets, st);
+    if (rc == GKR_OK) msm_host_tail(h, c, W, n_problems, out_xy);
     return rc;
+}
+
+// <bases[first .. first+n), scalars>   scalars: device table of n Fr (Montgomery).  out_xy: affine result, 12 u64
+// (x then y, Montgomery form; all zero for the point at infinity).
+extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
+    return msm_g1_impl(ctx, srs, first, 0, 1, scalars, n, out_xy);
+}
+// `n_problems` MSMs with the SAME scalars over the base ranges [first + p * problem_stride, + n): the c_pull / d_pull
+// commitments of PushForwardState::second_phase (one msm_nonaff per commitment chunk over that chunk's bucket sums with
+// eq_c / eq_d as scalars, pushforward.rs:598-604).  The digit sort is shared; out_xy: n_problems x 12 u64.
+extern "C" int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
+                                const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
+    return msm_g1_impl(ctx, srs, first, problem_stride, n_problems, scalars, n, out_xy);
 }
 
 
@@ -583,16 +617,29 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
     return GKR_OK;
 }
 
-// sum_{i=1}^{len-1} i * B[i]: the running-sum commitment of pushforward.rs:504-524 (== commit of the digit / counter table)
+// sum_{i=1}^{len-1} i * B[i]: the running-sum commitment of pushforward.rs:504-524 (== commit of the digit / counter table),
+// for `count` consecutive groups of 2^group_log buckets starting at bucket `first` (one group per commitment chunk).
+extern "C" int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t first, uint32_t group_log, uint32_t count,
+                                           uint64_t* out_xy) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!buckets || !out_xy || buckets->kind != 2 || count == 0 || group_log > 30) return ctx->fail(GKR_ERR_ARG, "expects bucket sums");
+    int cap_log = 0;
+    while (((uint64_t)1 << cap_log) < buckets->n) cap_log++;
+    if (first + ((uint64_t)count << group_log) > ((uint64_t)1 << cap_log)) return ctx->fail(GKR_ERR_ARG, "bucket range out of bounds");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    std::vector<gkr::G1XH> h;
+    // buckets beyond n (up to the power of two) were written as infinity by the accumulate kernels
+    int rc = msm_window_sums(ctx, (const G1X*)buckets->d + first, (int)group_log, count, h);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < count; k++) gkr::g1h::to_affine(h[k], out_xy + 12 * (size_t)k);
+    return GKR_OK;
+}
 extern "C" int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t* out_xy) {
     if (!ctx) return GKR_ERR_ARG;
-    if (!buckets || !out_xy || buckets->kind != 2) return ctx->fail(GKR_ERR_ARG, "expects bucket sums");
-    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
+    if (!buckets) return ctx->fail(GKR_ERR_ARG, "expects bucket sums");
     int c = 0;
     while (((uint64_t)1 << c) < buckets->n) c++;
-    // buckets beyond n (up to the power of two) were written as infinity by the accumulate kernels
-    return msm_finish(ctx, (const G1X*)buckets->d, c, 1, out_xy);
+    return gkr_g1_weighted_bucket_sums(ctx, buckets, 0, (uint32_t)c, 1, out_xy);
 }
 
 // download bucket sums / any point set as affine (x, y) pairs (tests, and `c_comm`-style per-bucket inspection)

@@ -16,8 +16,6 @@ Claims are (point, evs) over python ints; tables, SRS and bucket sums never leav
 """
 from __future__ import annotations
 
-import time
-
 import numpy as np
 
 from . import binding as g
@@ -28,23 +26,7 @@ from .fieldutil import R_MOD, from_limbs, make_gamma_pows, to_limb1, to_limbs
 P = R_MOD
 ONE = None  # lincomb source standing for the all-ones table
 
-# optional span accounting (the reference prints a tracing span tree, examples/pippenger.rs:75-89): name -> seconds
-PROFILE = None
-
-
-class span:
-    def __init__(self, ctx, name):
-        self.ctx, self.name = ctx, name
-
-    def __enter__(self):
-        if PROFILE is not None:
-            self.ctx.sync()
-            self.t0 = time.perf_counter()
-
-    def __exit__(self, *a):
-        if PROFILE is not None:
-            self.ctx.sync()
-            PROFILE[self.name] = PROFILE.get(self.name, 0.0) + time.perf_counter() - self.t0
+from .profiling import span  # noqa: E402
 
 
 def write_points(tr, pts):  # proof_transcript.rs:64-69; pts: (12,) limb arrays
@@ -161,20 +143,18 @@ class PushForwardState:
         sp = span(ctx, "state: c/d bucket sums + running-sum commitments")
         sp.__enter__()
         # c / d commitments: bucket sums over the SRS then running sums (pushforward.rs:398-456, 504-524)
+        # All commitment chunks go through ONE bucket accumulation: bucket id = (chunk << group_log) | digit.
         comm_mul = 1 << clm
         n_comms = -(-y_size // comm_mul)
-        self.c_buckets, self.d_buckets, self.c_comm, self.d_comm = [], [], [], []
-        for k in range(n_comms):
-            ys = range(k * comm_mul, min((k + 1) * comm_mul, y_size))
-            pidx = np.concatenate([np.arange(x_size, dtype=np.uint32) + np.uint32(x_size * (y % comm_mul)) for y in ys])
-            dd = np.concatenate([digits[y] for y in ys])
-            cc = np.concatenate([counter[y] for y in ys])
-            db = key.kzg.srs.bucket_sums(pidx, dd, nb)
-            cb = key.kzg.srs.bucket_sums(pidx, cc, int(cc.max()) + 1)
-            self.d_buckets.append(db)
-            self.c_buckets.append(cb)
-            self.d_comm.append(db.weighted_sum())
-            self.c_comm.append(cb.weighted_sum())
+        self.n_comms = n_comms
+        ys = np.arange(y_size, dtype=np.uint32)
+        pidx = (np.arange(x_size, dtype=np.uint32)[None, :] + (np.uint32(x_size) * (ys % comm_mul))[:, None]).reshape(-1)
+        chunk = (ys // comm_mul)[:, None]
+        self.c_log = max(int(counter.max()).bit_length(), 1)
+        self.d_all = key.kzg.srs.bucket_sums(pidx, (digits + (chunk << np.uint32(d_logsize))).reshape(-1), n_comms << d_logsize)
+        self.c_all = key.kzg.srs.bucket_sums(pidx, (counter + (chunk << np.uint32(self.c_log))).reshape(-1), n_comms << self.c_log)
+        self.d_comm = list(self.d_all.weighted_sums(d_logsize, n_comms))
+        self.c_comm = list(self.c_all.weighted_sums(self.c_log, n_comms))
         sp.__exit__()
         with span(ctx, "state: 4 MSM commitments (p_0, p_1, ac_c, ac_d)"):
             self.p_0_comm, self.p_1_comm = key.commit(self.p_0), key.commit(self.p_1)
@@ -189,8 +169,8 @@ class PushForwardState:
         self.eq_d, self.eq_c = ctx.eq_table(to_limbs(r[yl:yl + dl])), ctx.eq_table(to_limbs(r[yl + dl:]))
         self.c_pull, self.d_pull = ctx.gather(self.eq_c, self.c_idx), ctx.gather(self.eq_d, self.d_idx)
         # msm_nonaff over the bucket bases with eq as scalars (pushforward.rs:598-604) == commit(c_pull chunk)
-        self.c_pull_comm = [b.msm(self.eq_c, n=b.n) for b in self.c_buckets]
-        self.d_pull_comm = [b.msm(self.eq_d, n=b.n) for b in self.d_buckets]
+        self.c_pull_comm = list(self.c_all.msm_batch(self.eq_c, 1 << self.c_log, 0, 1 << self.c_log, self.n_comms))
+        self.d_pull_comm = list(self.d_all.msm_batch(self.eq_d, 1 << dl, 0, 1 << dl, self.n_comms))
 
 
 # ---------------------------------------------------------------- dense eq sumcheck ----------------------

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 from . import binding as g
 from .fieldutil import R_MOD, from_limbs, make_gamma_pows, to_limb1, to_limbs
+from .profiling import span
 
 P = R_MOD
 
@@ -58,8 +59,10 @@ class DenseDeg2Sumcheck:
         claim = evs[0]
         for i in range(1, len(evs)):
             claim = (claim + gp[i] * evs[i]) % P
-        so = self.ctx.deg2_dense_so(self.gate["parts"], tables, to_limbs(gp), to_limb1(claim), to_limbs(point))
-        _, out_point, fe = g.sumcheck_prove(tr, so, self.num_vars)
+        with span(self.ctx, "gkr: deg2 dense object setup"):
+            so = self.ctx.deg2_dense_so(self.gate["parts"], tables, to_limbs(gp), to_limb1(claim), to_limbs(point))
+        with span(self.ctx, "gkr: deg2 dense rounds"):
+            _, out_point, fe = g.sumcheck_prove(tr, so, self.num_vars)
         so.destroy()
         tr.write_scalars(fe)
         return (from_limbs(out_point), from_limbs(fe))
@@ -78,8 +81,10 @@ class VecVecDeg2Sumcheck:
         claim = evs[0]
         for i in range(1, len(evs)):
             claim = (claim + gp[i] * evs[i]) % P
-        so = self.ctx.deg2_vecvec_so(self.gate["gid"], polys, to_limbs(gp), to_limb1(claim), to_limbs(point), self.nvv)
-        _, out_point, fe = g.sumcheck_prove(tr, so, self.num_vars)
+        with span(self.ctx, "gkr: deg2 vecvec object setup"):
+            so = self.ctx.deg2_vecvec_so(self.gate["gid"], polys, to_limbs(gp), to_limb1(claim), to_limbs(point), self.nvv)
+        with span(self.ctx, "gkr: deg2 vecvec rounds (sparse + dense tail)"):
+            _, out_point, fe = g.sumcheck_prove(tr, so, self.num_vars)
         so.destroy()
         fe = fe[:-1]  # poly_evs.pop(): the eq evaluation is not sent (vecvec_eq.rs:445)
         tr.write_scalars(fe)

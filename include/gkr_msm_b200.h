@@ -204,6 +204,14 @@ int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uint64_t* g0_x
 int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* point_idx, const uint32_t* bucket_idx, uint64_t n,
                        uint32_t n_buckets, gkr_srs** out);
 int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t* out_xy);
+/* batched forms for the commitment chunks of one proof (y_size / 2^clm of them): bucket ids (chunk << group_log) | bucket
+ * turn all chunks into ONE gkr_g1_bucket_sums call; gkr_g1_weighted_bucket_sums then returns `count` running-sum
+ * commitments (count x 12 u64), one per group of 2^group_log buckets starting at `first`; gkr_msm_g1_batch is `n_problems`
+ * MSMs with the same scalars over the base ranges [first + p * problem_stride, + n) (msm_nonaff per chunk, :598-604). */
+int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t first, uint32_t group_log, uint32_t count,
+                                uint64_t* out_xy);
+int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
+                     const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
 int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
 /* test hook, host only: the O(windows) tail of every MSM (Horner over the extended-Jacobian window sums X, Y, ZZ, ZZZ --
  * 24 u64 each -- with c doublings per window, then one inversion to affine) runs on the CPU; see csrc/host_g1.hpp. */

@@ -95,3 +95,32 @@ def test_lincomb_slices(ctx):
     assert got == [(ca * a[i] + cb * a[8 + i]) % P for i in range(4)]
     with pytest.raises(g.GkrError):
         ctx.lincomb([(tb, to_limb1(1), 4, 0, 8)], 8)
+
+
+def test_batched_bucket_commitments(ctx):
+    """all commitment chunks in one pass: combined bucket ids, grouped running sums, msm_nonaff per chunk (same scalars)"""
+    rng = random.Random(12)
+    x_size, d_log, chunks = 48, 3, 3
+    bases = [rand_g1(rng) for _ in range(x_size)]
+    srs = g.Srs(ctx, aff_to_limbs(bases))
+    digits = [[rng.randrange(1 << d_log) for _ in range(x_size)] for _ in range(chunks)]
+    digits[1] = [5] * x_size  # one heavy bucket, the others empty
+    pidx = np.tile(np.arange(x_size, dtype=np.uint32), chunks)
+    bidx = np.concatenate([np.array(digits[k], dtype=np.uint32) + (k << d_log) for k in range(chunks)])
+    allb = srs.bucket_sums(pidx, bidx, chunks << d_log)
+    want = [OC.bucket_sums(bases, range(x_size), digits[k], 1 << d_log) for k in range(chunks)]
+    got = [res_to_point(r) for r in allb.download_affine()]
+    assert got == [b for w in want for b in w]
+    comms = [res_to_point(r) for r in allb.weighted_sums(d_log, chunks)]
+    assert comms == [OC.running_sum_commit(w) for w in want]
+    assert comms == [CV.g1_msm(bases, digits[k]) for k in range(chunks)]
+    r_d = [rng.randrange(P) for _ in range(d_log)]
+    eq_d = S.eq_poly_sequence_last(r_d)
+    pulls = [res_to_point(r) for r in allb.msm_batch(ctx.eq_table(to_limbs(r_d)), 1 << d_log, 0, 1 << d_log, chunks)]
+    assert pulls == [CV.g1_msm(want[k], eq_d) for k in range(chunks)]
+    # a sub-range of the groups, and range checking
+    assert [res_to_point(r) for r in allb.weighted_sums(d_log, 2, first=1 << d_log)] == comms[1:]
+    with pytest.raises(g.GkrError):
+        allb.weighted_sums(d_log, chunks + 2)
+    with pytest.raises(g.GkrError):
+        allb.msm_batch(ctx.eq_table(to_limbs(r_d)), 1 << d_log, 0, 1 << d_log, chunks + 1)

@@ -34,6 +34,7 @@ def main():
     import gkr_msm_b200 as g
     from gkr_msm_b200 import hostmath as H
     from gkr_msm_b200 import pippenger as DPP
+    from gkr_msm_b200 import profiling as PR
     from gkr_msm_b200.fieldutil import R_MOD, to_limbs
 
     rng = np.random.default_rng(args.seed)
@@ -73,16 +74,16 @@ def main():
         launches = ctx.launches - l0
         proof_len = len(tr.proof())
     if args.profile:
-        DPP.PROFILE = {}
+        PR.PROFILE = {}
         tr = g.Transcript(b"fgstglsp")
         t0 = time.perf_counter()
         DPP.run_pippenger(ctx, tr, points_xy, coefs, cfg, r, key)
         ctx.sync()
         tot = time.perf_counter() - t0
-        for k, v in sorted(DPP.PROFILE.items(), key=lambda kv: -kv[1]):
+        for k, v in sorted(PR.PROFILE.items(), key=lambda kv: -kv[1]):
             print(f"  {v * 1e3:9.2f} ms  {k}", file=sys.stderr)
         print(f"  {tot * 1e3:9.2f} ms  total (with span syncs)", file=sys.stderr)
-        DPP.PROFILE = None
+        PR.PROFILE = None
     best = min(times)
     print(json.dumps({
         "bench": "run_pippenger (witness + commit + prove)", "x_logsize": xl, "d_logsize": dl, "nbits": nbits, "clm": clm,
