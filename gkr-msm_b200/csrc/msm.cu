@@ -200,47 +200,50 @@ __global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, in
 // ---- balanced bucket accumulation ----------------------------------------------------------------------------
 // Bucket sizes are data dependent (a degenerate top window, small-integer scalar tables, digit buckets of 2^(x-d) points):
 // one thread per bucket would serialise thousands of additions.  Buckets are therefore counting-sorted by size
-// (descending): buckets with >= MSM_CAP entries are summed by a whole block each (strided partial sums + shared-memory
-// tree), the rest by one thread each, and because neighbouring threads own buckets of equal size warps do not diverge.
-#define MSM_CAP 32
+// (descending) into three tiers: HUGE (>= MSM_HUGE entries) are summed by a whole block each, MEDIUM (>= cap) by one
+// warp each (strided partial sums + shared-memory tree), LIGHT (< cap) by one thread each -- and because neighbouring
+// threads own buckets of equal size, warps of the light tier do not diverge.  `cap` is chosen by the host from the
+// average bucket size and the number of buckets (enough threads to fill the machine either way).
+#define MSM_MAXCAP 1024
+#define MSM_HUGE 4096
+#define MSM_NBINS (MSM_MAXCAP + 2)  // bins 0..cap-1: exact light sizes; bin cap: medium; bin cap+1: huge
 
-__global__ void msm_bin_hist_kernel(const uint32_t* counts, uint64_t nbk, uint32_t* bins /* [MSM_CAP + 1] */) {
-    __shared__ uint32_t sh[MSM_CAP + 1];
-    for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x) sh[i] = 0;
+__device__ __forceinline__ uint32_t msm_bin_of(uint32_t cnt, uint32_t cap) { return cnt < cap ? cnt : (cnt < MSM_HUGE ? cap : cap + 1); }
+
+__global__ void msm_bin_hist_kernel(const uint32_t* counts, uint64_t nbk, uint32_t cap, uint32_t* bins /* [MSM_NBINS] */) {
+    __shared__ uint32_t sh[MSM_NBINS];
+    for (int i = threadIdx.x; i < MSM_NBINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbk; b += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t k = counts[b];
-        atomicAdd(&sh[k < MSM_CAP ? k : MSM_CAP], 1u);
-    }
+    for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbk; b += (uint64_t)gridDim.x * blockDim.x)
+        atomicAdd(&sh[msm_bin_of(counts[b], cap)], 1u);
     __syncthreads();
-    for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x)
+    for (int i = threadIdx.x; i < MSM_NBINS; i += blockDim.x)
         if (sh[i]) atomicAdd(&bins[i], sh[i]);
 }
-// descending exclusive offsets: bin MSM_CAP (heavy) first, empty buckets last
-__global__ void msm_bin_scan_kernel(const uint32_t* bins, uint32_t* bin_off) {
+// descending exclusive offsets: huge first, then medium, then light by decreasing size, empty buckets last
+__global__ void msm_bin_scan_kernel(const uint32_t* bins, uint32_t cap, uint32_t* bin_off) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     uint32_t acc = 0;
-    for (int k = MSM_CAP; k >= 0; k--) {
+    for (int k = (int)cap + 1; k >= 0; k--) {
         bin_off[k] = acc;
         acc += bins[k];
     }
 }
-__global__ void __launch_bounds__(256) msm_bin_scatter_kernel(const uint32_t* counts, uint64_t nbk, const uint32_t* bin_off, uint32_t* bin_cursor,
-                                                               uint32_t* order) {
-    __shared__ uint32_t sh_cnt[MSM_CAP + 1], sh_base[MSM_CAP + 1];
+__global__ void __launch_bounds__(256) msm_bin_scatter_kernel(const uint32_t* counts, uint64_t nbk, uint32_t cap, const uint32_t* bin_off,
+                                                               uint32_t* bin_cursor, uint32_t* order) {
+    __shared__ uint32_t sh_cnt[MSM_NBINS], sh_base[MSM_NBINS];
     const uint64_t tiles = (nbk + blockDim.x - 1) / blockDim.x;
     for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x) sh_cnt[i] = 0;
+        for (int i = threadIdx.x; i < MSM_NBINS; i += blockDim.x) sh_cnt[i] = 0;
         __syncthreads();
         const uint64_t b = tile * blockDim.x + threadIdx.x;
         uint32_t k = 0, pos = 0;
         if (b < nbk) {
-            k = counts[b];
-            if (k > MSM_CAP) k = MSM_CAP;
+            k = msm_bin_of(counts[b], cap);
             pos = atomicAdd(&sh_cnt[k], 1u);
         }
         __syncthreads();
-        for (int i = threadIdx.x; i <= MSM_CAP; i += blockDim.x)
+        for (int i = threadIdx.x; i < MSM_NBINS; i += blockDim.x)
             if (sh_cnt[i]) sh_base[i] = bin_off[i] + atomicAdd(&bin_cursor[i], sh_cnt[i]);
         __syncthreads();
         if (b < nbk) order[sh_base[k] + pos] = (uint32_t)b;
@@ -267,54 +270,83 @@ __device__ __forceinline__ void msm_add_base(G1X& acc, const void* bases, uint32
     }
 }
 
-// light buckets (< MSM_CAP entries): one thread per bucket, in size order.  `n_problems` independent MSMs that share the
-// scalars (hence the digit sort) but read bases shifted by p * problem_stride accumulate into buckets[p * total + b].
+struct MsmAccArgs {
+    const void* bases;
+    const uint32_t *sorted, *counts, *offsets, *order, *bins;
+    uint32_t n, cap;
+    int c;
+    uint64_t total;  // buckets per problem
+    G1X* buckets;
+    uint32_t n_problems, problem_stride;  // independent MSMs sharing the scalars: bases shifted by p * problem_stride
+};
+
+// light tier (< cap entries): one thread per bucket, in size order
 template <int KIND>
-__global__ void __launch_bounds__(128) msm_accumulate_light_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts,
-                                                                    const uint32_t* offsets, uint32_t n, int c, uint64_t total,
-                                                                    const uint32_t* order, const uint32_t* bins, G1X* buckets,
-                                                                    uint32_t n_problems, uint32_t problem_stride) {
-    const uint64_t n_heavy = bins[MSM_CAP];
-    const uint64_t n_light = total - n_heavy;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_light * n_problems; i += (uint64_t)gridDim.x * blockDim.x) {
+__global__ void __launch_bounds__(128) msm_accumulate_light_kernel(const __grid_constant__ MsmAccArgs A) {
+    const uint64_t n_heavy = (uint64_t)A.bins[A.cap] + A.bins[A.cap + 1];
+    const uint64_t n_light = A.total - n_heavy;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_light * A.n_problems; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t p = (uint32_t)(i / n_light);
-        const uint32_t b = order[n_heavy + i % n_light];
-        const uint32_t cnt = counts[b];
-        const uint32_t shift = p * problem_stride;
+        const uint32_t b = A.order[n_heavy + i % n_light];
+        const uint32_t cnt = A.counts[b];
+        const uint32_t shift = p * A.problem_stride;
         G1X acc = g1x_inf();
-        const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
-        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, bases, idx[k] + shift);
-        buckets[(size_t)p * total + b] = acc;
+        const uint32_t* idx = A.sorted + (size_t)(b >> A.c) * A.n + A.offsets[b];
+        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, A.bases, idx[k] + shift);
+        A.buckets[(size_t)p * A.total + b] = acc;
     }
 }
-// heavy buckets: one block per bucket
+// tree-sum the G partial sums of a group of G consecutive threads (G = 32: one warp, G = blockDim: the block)
+__device__ __forceinline__ void msm_group_tree(G1X* sh, uint32_t lane, uint32_t G, bool whole_block) {
+    for (uint32_t s = G >> 1; s > 0; s >>= 1) {
+        if (lane < s) {
+            G1X a = sh[lane];
+            g1x_add(a, sh[lane + s]);
+            sh[lane] = a;
+        }
+        if (whole_block) __syncthreads(); else __syncwarp();
+    }
+}
+// medium tier ([cap, MSM_HUGE) entries): one warp per bucket
 template <int KIND>
-__global__ void __launch_bounds__(256) msm_accumulate_heavy_kernel(const void* bases, const uint32_t* sorted, const uint32_t* counts,
-                                                                    const uint32_t* offsets, uint32_t n, int c, uint64_t total,
-                                                                    const uint32_t* order, const uint32_t* bins, G1X* buckets,
-                                                                    uint32_t n_problems, uint32_t problem_stride) {
+__global__ void __launch_bounds__(128) msm_accumulate_medium_kernel(const __grid_constant__ MsmAccArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    G1X* sh = reinterpret_cast<G1X*>(smem_raw) + warp * 32;
+    const uint32_t n_huge = A.bins[A.cap + 1], n_med = A.bins[A.cap];
+    for (uint64_t h = (uint64_t)blockIdx.x * wpb + warp; h < (uint64_t)n_med * A.n_problems; h += (uint64_t)gridDim.x * wpb) {
+        const uint32_t p = (uint32_t)(h / n_med);
+        const uint32_t b = A.order[n_huge + h % n_med];
+        const uint32_t cnt = A.counts[b];
+        const uint32_t shift = p * A.problem_stride;
+        const uint32_t* idx = A.sorted + (size_t)(b >> A.c) * A.n + A.offsets[b];
+        G1X acc = g1x_inf();
+        for (uint32_t k = lane; k < cnt; k += 32) msm_add_base<KIND>(acc, A.bases, idx[k] + shift);
+        sh[lane] = acc;
+        __syncwarp();
+        msm_group_tree(sh, lane, 32, false);
+        if (lane == 0) A.buckets[(size_t)p * A.total + b] = sh[0];
+        __syncwarp();
+    }
+}
+// huge tier: one block per bucket
+template <int KIND>
+__global__ void __launch_bounds__(256) msm_accumulate_huge_kernel(const __grid_constant__ MsmAccArgs A) {
     extern __shared__ unsigned char smem_raw[];
     G1X* sh = reinterpret_cast<G1X*>(smem_raw);
-    const uint32_t n_heavy = bins[MSM_CAP];
-    for (uint64_t h = blockIdx.x; h < (uint64_t)n_heavy * n_problems; h += gridDim.x) {
-        const uint32_t p = (uint32_t)(h / n_heavy);
-        const uint32_t b = order[h % n_heavy];
-        const uint32_t cnt = counts[b];
-        const uint32_t shift = p * problem_stride;
-        const uint32_t* idx = sorted + (size_t)(b >> c) * n + offsets[b];
+    const uint32_t n_huge = A.bins[A.cap + 1];
+    for (uint64_t h = blockIdx.x; h < (uint64_t)n_huge * A.n_problems; h += gridDim.x) {
+        const uint32_t p = (uint32_t)(h / n_huge);
+        const uint32_t b = A.order[h % n_huge];
+        const uint32_t cnt = A.counts[b];
+        const uint32_t shift = p * A.problem_stride;
+        const uint32_t* idx = A.sorted + (size_t)(b >> A.c) * A.n + A.offsets[b];
         G1X acc = g1x_inf();
-        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, bases, idx[k] + shift);
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, A.bases, idx[k] + shift);
         sh[threadIdx.x] = acc;
         __syncthreads();
-        for (uint32_t s = blockDim.x >> 1; s > 0; s >>= 1) {
-            if (threadIdx.x < s) {
-                G1X a = sh[threadIdx.x];
-                g1x_add(a, sh[threadIdx.x + s]);
-                sh[threadIdx.x] = a;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) buckets[(size_t)p * total + b] = sh[0];
+        msm_group_tree(sh, threadIdx.x, blockDim.x, true);
+        if (threadIdx.x == 0) A.buckets[(size_t)p * A.total + b] = sh[0];
         __syncthreads();
     }
 }
@@ -412,33 +444,46 @@ static int pick_window(uint64_t n) {
     while (((uint64_t)1 << lg) < n) lg++;
     int c = lg - 3;  // bucket work 2^c per window vs n additions per window
     if (c < 4) c = 4;
-    if (c > 16) c = 16;
+    if (c > 18) c = 18;
     return c;
 }
 
 // size-ordered bucket accumulation: counts/offsets [nbk], sorted [W][n] -> buckets [n_problems][nbk].  `work` holds
-// order [nbk] followed by bins / bin_off / bin_cursor [3 * (MSM_CAP + 1)].
+// order [nbk] followed by bins / bin_off / bin_cursor [3 * MSM_NBINS].  n_entries: total sorted entries (for the average).
 static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint32_t* sorted, const uint32_t* counts, const uint32_t* offsets,
-                          uint32_t n, int c, uint64_t nbk, uint32_t* work, G1X* buckets, uint32_t n_problems = 1, uint32_t problem_stride = 0) {
+                          uint32_t n, int c, uint64_t nbk, uint64_t n_entries, uint32_t* work, G1X* buckets, uint32_t n_problems = 1,
+                          uint32_t problem_stride = 0) {
     cudaStream_t st = ctx->stream;
     uint32_t* order = work;
     uint32_t* bins = work + nbk;
-    uint32_t* bin_off = bins + (MSM_CAP + 1);
-    uint32_t* bin_cursor = bin_off + (MSM_CAP + 1);
-    GKR_CUDA_OK(ctx, cudaMemsetAsync(bins, 0, sizeof(uint32_t) * 3 * (MSM_CAP + 1), st));
+    uint32_t* bin_off = bins + MSM_NBINS;
+    uint32_t* bin_cursor = bin_off + MSM_NBINS;
+    // light/medium threshold: with few buckets every bucket needs many threads; with many buckets one thread per bucket
+    // already fills the machine and only outliers (>= 4x the average) are worth a warp
+    uint32_t cap = 32;
+    if (nbk * n_problems >= 65536) {
+        uint64_t avg = n_entries / nbk;
+        cap = (uint32_t)std::min<uint64_t>(MSM_MAXCAP, std::max<uint64_t>(32, 4 * avg));
+    }
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(bins, 0, sizeof(uint32_t) * 3 * MSM_NBINS, st));
     unsigned gb = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk + 255) / 256, (uint64_t)ctx->num_sms * 4));
-    msm_bin_hist_kernel<<<gb, 256, 0, st>>>(counts, nbk, bins);
-    msm_bin_scan_kernel<<<1, 32, 0, st>>>(bins, bin_off);
-    msm_bin_scatter_kernel<<<gb, 256, 0, st>>>(counts, nbk, bin_off, bin_cursor, order);
+    msm_bin_hist_kernel<<<gb, 256, 0, st>>>(counts, nbk, cap, bins);
+    msm_bin_scan_kernel<<<1, 32, 0, st>>>(bins, cap, bin_off);
+    msm_bin_scatter_kernel<<<gb, 256, 0, st>>>(counts, nbk, cap, bin_off, bin_cursor, order);
+    MsmAccArgs A;
+    A.bases = bases; A.sorted = sorted; A.counts = counts; A.offsets = offsets; A.order = order; A.bins = bins;
+    A.n = n; A.cap = cap; A.c = c; A.total = nbk; A.buckets = buckets; A.n_problems = n_problems; A.problem_stride = problem_stride;
     unsigned gl = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk * n_problems + 127) / 128, (uint64_t)ctx->num_sms * 16));
+    unsigned gm = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbk * n_problems + 3) / 4, (uint64_t)ctx->num_sms * 8));
     unsigned gh = (unsigned)ctx->num_sms * 2;
-    const size_t shh = sizeof(G1X) * 256;
-#define GKR_MSM_ACC(K)                                                                                                                       \
-    msm_accumulate_heavy_kernel<K><<<gh, 256, shh, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets, n_problems, problem_stride); \
-    msm_accumulate_light_kernel<K><<<gl, 128, 0, st>>>(bases, sorted, counts, offsets, n, c, nbk, order, bins, buckets, n_problems, problem_stride);
+    const size_t sh_huge = sizeof(G1X) * 256, sh_med = sizeof(G1X) * 128;
+#define GKR_MSM_ACC(K)                                                   \
+    msm_accumulate_huge_kernel<K><<<gh, 256, sh_huge, st>>>(A);          \
+    msm_accumulate_medium_kernel<K><<<gm, 128, sh_med, st>>>(A);         \
+    msm_accumulate_light_kernel<K><<<gl, 128, 0, st>>>(A);
     if (kind == 2) { GKR_MSM_ACC(2) } else if (kind == 1) { GKR_MSM_ACC(1) } else { GKR_MSM_ACC(0) }
 #undef GKR_MSM_ACC
-    ctx->launches += 5;
+    ctx->launches += 6;
     GKR_CUDA_OK(ctx, cudaGetLastError());
     return GKR_OK;
 }
@@ -501,7 +546,7 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     G1X* buckets = nullptr;
     GKR_CUDA_OK(ctx, cudaMallocAsync(&digits, sizeof(uint32_t) * W * n, st));
     GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * W * n, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * (MSM_CAP + 1)), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS), st));
     offsets = counts + nbk;
     cursor = counts + 2 * nbk;
     work = counts + 3 * nbk;
@@ -514,7 +559,8 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     ctx->launches += 3;
     const void* bases = (const unsigned char*)srs->d + first * srs->stride();
     std::vector<gkr::G1XH> h;
-    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, work, buckets, n_problems, (uint32_t)problem_stride);
+    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, (uint64_t)W * n, work, buckets, n_problems,
+                            (uint32_t)problem_stride);
     if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, c, (uint32_t)W * n_problems, h);
     cudaFreeAsync(digits, st);
     cudaFreeAsync(sorted, st);
@@ -583,7 +629,7 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
     GKR_CUDA_OK(ctx, cudaMallocAsync(&d_p, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
     GKR_CUDA_OK(ctx, cudaMallocAsync(&d_b, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
     GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * (MSM_CAP + 1) + 1), st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS + 1), st));
     uint32_t* offsets = counts + nbk;
     uint32_t* cursor = counts + 2 * nbk;
     d_bad = (int*)(counts + 3 * nbk);
@@ -599,7 +645,7 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
         ctx->launches += 3;
     }
     {
-        int rc = msm_accumulate(ctx, srs->d, 0, sorted, counts, offsets, (uint32_t)n, c, nbk, work, (G1X*)res->d);
+        int rc = msm_accumulate(ctx, srs->d, 0, sorted, counts, offsets, (uint32_t)n, c, nbk, n, work, (G1X*)res->d);
         if (rc) return rc;
     }
     int bad = 0;
