@@ -66,7 +66,10 @@ struct WideAccs {
     }
 };
 
-template <class SO, int MODE, bool FAST, int MINB = 3, bool ACC_SMEM = false>
+// PF: software prefetch distance in grid-stride iterations -- every thread touches the cache lines of its iteration
+// i + PF * stride with prefetch.global.L2 (no registers, no shared memory), so the demand loads of that iteration
+// hit L2 instead of HBM and the long-scoreboard stalls of this low-occupancy kernel shrink.
+template <class SO, int MODE, bool FAST, int MINB = 3, bool ACC_SMEM = false, int PF = 0>
 __global__ void __launch_bounds__(GKR_REDUCE_THREADS, MINB) dense_round_kernel(const __grid_constant__ DenseRoundArgs A) {
     constexpr int P = SO::P;
     constexpr int NACC = (MODE == 2) ? 1 : SO::DEG;
@@ -78,6 +81,16 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS, MINB) dense_round_kernel(c
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < A.n_items; i += stride) {
         Fr a[P];
+        if (PF > 0 && MODE != 2) {
+            const uint64_t ip = i + (uint64_t)PF * stride;
+            if (ip < A.n_items) {
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const Fr* nxt = A.in[j] + (MODE == 1 ? 4 : 2) * ip;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+                }
+            }
+        }
         if (MODE == 2) {
 #pragma unroll
             for (int j = 0; j < P; j++) a[j] = A.in[j][i];

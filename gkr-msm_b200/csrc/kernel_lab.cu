@@ -6,9 +6,9 @@
 #include "gates.cuh"
 #include "dense_kernel.cuh"
 
-template <int MODE, bool FAST, int MINB, bool ACC_SMEM>
+template <int MODE, bool FAST, int MINB, bool ACC_SMEM, int PF = 0>
 static int lab_run(gkr_ctx* ctx, DenseRoundArgs& a, int iters, float* ms, int* blocks_per_sm, int grid_mult) {
-    auto kern = dense_round_kernel<SoProd3, MODE, FAST, MINB, ACC_SMEM>;
+    auto kern = dense_round_kernel<SoProd3, MODE, FAST, MINB, ACC_SMEM, PF>;
     int b = 0;
     GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, GKR_REDUCE_THREADS, 0));
     *blocks_per_sm = b;
@@ -50,6 +50,7 @@ extern "C" int gkr_lab_dense_prod3(gkr_ctx* ctx, int variant, int mode, gkr_tabl
     a.t = fr_from_host(gkr::frh::ONE);
     for (int i = 0; i < GKR_MAX_GATE_CONSTS; i++) a.consts.g[i] = fr_from_host(gkr::frh::ONE);
 #define LAB(M, F, B, S) return lab_run<M, F, B, S>(ctx, a, iters, ms, blocks_per_sm, grid_mult)
+#define LABP(M, F, B, S, PFD) return lab_run<M, F, B, S, PFD>(ctx, a, iters, ms, blocks_per_sm, grid_mult)
     if (mode == 0) {
         switch (variant) {
             case 0: LAB(0, false, 3, false);
@@ -57,6 +58,9 @@ extern "C" int gkr_lab_dense_prod3(gkr_ctx* ctx, int variant, int mode, gkr_tabl
             case 2: LAB(0, false, 4, true);
             case 3: LAB(0, false, 5, true);
             case 4: LAB(0, false, 2, false);
+            case 5: LABP(0, false, 3, false, 1);
+            case 6: LABP(0, false, 3, false, 2);
+            case 7: LABP(0, false, 3, false, 4);
         }
     } else {
         switch (variant) {
@@ -65,8 +69,12 @@ extern "C" int gkr_lab_dense_prod3(gkr_ctx* ctx, int variant, int mode, gkr_tabl
             case 2: LAB(1, true, 4, true);
             case 3: LAB(1, true, 5, true);
             case 4: LAB(1, true, 2, false);
+            case 5: LABP(1, true, 3, false, 1);
+            case 6: LABP(1, true, 3, false, 2);
+            case 7: LABP(1, true, 3, false, 4);
         }
     }
 #undef LAB
+#undef LABP
     return ctx->fail(GKR_ERR_ARG, "unknown lab variant");
 }

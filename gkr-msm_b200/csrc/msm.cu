@@ -439,13 +439,25 @@ extern "C" void gkr_srs_free(gkr_srs* s) {
     delete s;
 }
 
+// window width: minimise W * (n + 3 * 2^c) bucket additions (accumulate + running-sum reduce) over c, and avoid a
+// degenerate top window (255 - (W - 1) c < 7 bits would put n / 2^bits points into each of a handful of buckets)
 static int pick_window(uint64_t n) {
     int lg = 0;
     while (((uint64_t)1 << lg) < n) lg++;
-    int c = lg - 3;  // bucket work 2^c per window vs n additions per window
-    if (c < 4) c = 4;
-    if (c > 18) c = 18;
-    return c;
+    int best = 4;
+    double best_cost = 1e300;
+    for (int c = 4; c <= 18; c++) {
+        if (c > lg + 1 && c > 4) break;
+        const int W = (255 + c - 1) / c;
+        const int top_bits = 255 - (W - 1) * c;
+        double cost = (double)W * ((double)n + 3.0 * (double)((uint64_t)1 << c));
+        if (top_bits < 7 && n > 4096) cost += 4.0 * (double)n;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = c;
+        }
+    }
+    return best;
 }
 
 // size-ordered bucket accumulation: counts/offsets [nbk], sorted [W][n] -> buckets [n_problems][nbk].  `work` holds

@@ -18,10 +18,10 @@ outs = [ctx.alloc(n // 2) for _ in range(3)]
 vp = C.c_void_p
 tin = (vp * 3)(*[t.h for t in tabs])
 tout = (vp * 3)(*[t.h for t in outs])
-names = {0: "regs, >=3 blocks/SM", 1: "regs, >=4 blocks/SM (spills)", 2: "smem accs, >=4 blocks/SM", 3: "smem accs, >=5 blocks/SM", 4: "regs, >=2 blocks/SM"}
+names = {0: "regs, >=3 blocks/SM", 1: "regs, >=4 blocks/SM (spills)", 2: "smem accs, >=4 blocks/SM", 3: "smem accs, >=5 blocks/SM", 4: "regs, >=2 blocks/SM", 5: "regs, 3 blocks, L2 prefetch +1", 6: "regs, 3 blocks, L2 prefetch +2", 7: "regs, 3 blocks, L2 prefetch +4"}
 for mode in (0, 1):
     bytes_ = (32 * 3 * n) if mode == 0 else (48 * 3 * n)
-    for variant in range(5):
+    for variant in range(8):
         for gm in (1, 2):
             ms = C.c_float(0)
             bps = C.c_int(0)
