@@ -261,6 +261,22 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"oracle C port (OpenMP), full Prod3 sumcheck over 2^{args.ref_log_n} x 3 tables, median of {reps} runs ({sec:.3f} s each)"}
 
+    # ---- secondary: the whole `examples/pippenger` prover on BASELINE config[0] (x=16, d=8, 128 bit, clm 0) ------------
+    pip = None
+    if world == 1 and not args.no_pippenger:
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("bench_pippenger", os.path.join(ROOT, "tools", "bench_pippenger.py"))
+            bp = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(bp)
+            r = bp.run(argparse.Namespace(x_logsize=16, d_logsize=8, nbits=128, clm=0, reps=3, seed=7, profile=False), ctx=ctx)
+            pip = {"prove_ms": r["prove_ms_best"], "what": "benchutils::run_pippenger (witness + phase-1 commitments + proof), wall clock, "
+                   "inputs on the host, SRS resident", "config": "x_logsize 16, d_logsize 8, nbits 128, clm 0 (BASELINE config[0]: 2^20 "
+                   "point-digit incidences)", "proof_bytes": r["proof_bytes"], "gpu_launches": r["gpu_launches"],
+                   "prove_ms_all": r["prove_ms_all"]}
+        except Exception as e:  # pragma: no cover
+            pip = {"error": repr(e)}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -271,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"hypercube sharded by top index bits over {world} GPU(s)",
                    "l2": "inputs (1.5 GiB per GPU) larger than the 126 MB L2", "transcript": "merlin on host, one challenge per round"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "pippenger_prove": pip,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -287,6 +304,7 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pippenger", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

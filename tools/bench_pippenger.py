@@ -20,17 +20,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--x-logsize", type=int, default=16)
-    ap.add_argument("--d-logsize", type=int, default=8)
-    ap.add_argument("--nbits", type=int, default=128)
-    ap.add_argument("--clm", type=int, default=0)
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--seed", type=int, default=7)
-    ap.add_argument("--profile", action="store_true", help="print a per-phase breakdown of the last repetition")
-    args = ap.parse_args()
-
+def run(args, ctx=None):
     import gkr_msm_b200 as g
     from gkr_msm_b200 import hostmath as H
     from gkr_msm_b200 import pippenger as DPP
@@ -53,7 +43,7 @@ def main():
     r = [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(cfg["y_logsize"])]
     t_inputs = time.perf_counter() - t0
 
-    ctx = g.Context(0)
+    ctx = ctx or g.Context(0)
     t0 = time.perf_counter()
     nv = xl + clm
     tau = int.from_bytes(rng.bytes(32), "little") % R_MOD
@@ -85,11 +75,23 @@ def main():
         print(f"  {tot * 1e3:9.2f} ms  total (with span syncs)", file=sys.stderr)
         PR.PROFILE = None
     best = min(times)
-    print(json.dumps({
+    return ({
         "bench": "run_pippenger (witness + commit + prove)", "x_logsize": xl, "d_logsize": dl, "nbits": nbits, "clm": clm,
         "y_size": cfg["y_size"], "incidences": cfg["y_size"] << xl, "prove_ms_best": best * 1e3, "prove_ms_all": [t * 1e3 for t in times],
         "proof_bytes": proof_len, "gpu_launches": launches, "input_generation_s": t_inputs, "srs_setup_s": t_setup,
-        "srs_points": 2 * (1 << nv) - 1}), flush=True)
+        "srs_points": 2 * (1 << nv) - 1})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--x-logsize", type=int, default=16)
+    ap.add_argument("--d-logsize", type=int, default=8)
+    ap.add_argument("--nbits", type=int, default=128)
+    ap.add_argument("--clm", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--profile", action="store_true", help="print a per-phase breakdown of the last repetition")
+    print(json.dumps(run(ap.parse_args())), flush=True)
 
 
 if __name__ == "__main__":
