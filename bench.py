@@ -124,12 +124,21 @@ def cpu_port_run(log_n: int, reps: int, min_seconds: float = 0.0):
     return elem_rounds(log_n) / sec, sec, coracle.num_threads(), len(times)
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all the host threads it can, so the
+    variable is reset BEFORE the OpenMP runtime of the oracle library is loaded."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is a Rust crate
     (nightly + un-vendored git deps) that cannot be built in this image, so this arm times the oracle's C
     port of the same algorithm (oracle/c/gkr_oracle.c) on all host threads -- rank 0 only."""
     if rank != 0:
         return
+    use_all_host_threads()
     log_n = args.ref_log_n
     for _ in range(args.warmup):
         cpu_port_run(log_n, 1)
@@ -214,7 +223,11 @@ def run_ours(args, rank, world, local_rank):
         avg_ms = sum(dom) / len(dom)
         ach = alg_bytes / (avg_ms * 1e-3) / 1e9
         kernel_ms = sum(ms for (_, _, ms) in launches_timed) / args.steps
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 from the committed ncu --set full capture
+        # (profiles/r01_ncu_full_dense_round_prod3_fold_eval.csv): 1.610762 GB + 0.780815 GB per launch; other sizes: not captured
+        traffic = 1610762000 + 780814592 if log_n == 24 else None
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": "profiles/r01_ncu_full_dense_round_prod3_fold_eval.csv (ncu --set full, one launch)",
                     "kernel": "dense_round_kernel<SoProd3, fold+eval> (first fused round)", "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                     "share_of_kernel_time": avg_ms / kernel_ms if kernel_ms else None,
@@ -257,6 +270,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        use_all_host_threads()
         val, sec, threads, reps = cpu_port_run(args.ref_log_n, 3, min_seconds=10.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"oracle C port (OpenMP), full Prod3 sumcheck over 2^{args.ref_log_n} x 3 tables, median of {reps} runs ({sec:.3f} s each)"}

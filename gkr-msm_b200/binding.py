@@ -674,7 +674,24 @@ def _srs_mock_setup(ctx: Context, tau, g0_xy, n: int) -> "Srs":
     return out
 
 
+def _srs_bucket_sums_rows(self, idx: "U32Buf", x_logsize: int, clm: int, group_log: int) -> "Srs":
+    """bucket sums of a resident digit / counter matrix (rows of 2^x_logsize entries): incidence (y, x) adds
+    bases[x + 2^x_logsize * (y mod 2^clm)] to bucket ((y >> clm) << group_log) | idx[y][x]  (pushforward.rs:401-456)."""
+    lib = self.ctx.lib
+    if not hasattr(lib.gkr_g1_bucket_sums_rows, "_sig"):
+        lib.gkr_g1_bucket_sums_rows.restype = C.c_int
+        lib.gkr_g1_bucket_sums_rows.argtypes = [_vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(_vp)]
+        lib.gkr_g1_bucket_sums_rows._sig = True
+    h = _vp()
+    self.ctx.check(lib.gkr_g1_bucket_sums_rows(self.ctx.h, self.h, idx.h, x_logsize, clm, group_log, C.byref(h)))
+    rows = idx.n >> x_logsize
+    out = Srs.__new__(Srs)
+    out.ctx, out.h, out.n = self.ctx, h, (-(-rows // (1 << clm))) << group_log
+    return out
+
+
 Srs.mock_setup = staticmethod(_srs_mock_setup)
+Srs.bucket_sums_rows = _srs_bucket_sums_rows
 Srs.bucket_sums = _srs_bucket_sums
 Srs.weighted_sum = _srs_weighted_sum
 Srs.download_affine = _srs_download_affine
@@ -826,8 +843,27 @@ def _ctx_vecvec_gather(self, src, idx, lens, row_pad, col_pad, row_logsize, col_
     return VecVec(self, h)
 
 
+def _ctx_vecvec_gather_multi(self, srcs, idx, lens, row_pads, col_pads, row_logsize, col_logsize):
+    """several polynomials over the same gathered rows (one index upload): srcs[k] None = all ones."""
+    lib = self.lib
+    if not hasattr(lib.gkr_vecvec_gather_multi, "_sig"):
+        lib.gkr_vecvec_gather_multi.restype = C.c_int
+        lib.gkr_vecvec_gather_multi.argtypes = [_vp, C.POINTER(_vp), C.c_uint32, _vp, _vp, C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]
+        lib.gkr_vecvec_gather_multi._sig = True
+    k = len(srcs)
+    idx = np.ascontiguousarray(idx, dtype=np.uint32)
+    lens = np.ascontiguousarray(lens, dtype=np.uint32)
+    rp = np.ascontiguousarray(np.stack([_limbs(p).reshape(4) for p in row_pads]))
+    cp = np.ascontiguousarray(np.stack([_limbs(p).reshape(4) for p in col_pads]))
+    arr = (_vp * k)(*[(t.h if t is not None else None) for t in srcs])
+    out = (_vp * k)()
+    self.check(lib.gkr_vecvec_gather_multi(self.h, arr, k, _ptr(idx), _ptr(lens), lens.shape[0], _ptr(rp), _ptr(cp), row_logsize, col_logsize, out))
+    return [VecVec(self, _vp(out[i])) for i in range(k)]
+
+
 Context.upload_vecvec_flat = _ctx_upload_vecvec_flat
 Context.vecvec_gather = _ctx_vecvec_gather
+Context.vecvec_gather_multi = _ctx_vecvec_gather_multi
 
 
 def pushforward_bucketize(coefs_u64, y_size: int, d_logsize: int):

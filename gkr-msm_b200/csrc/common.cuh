@@ -89,6 +89,13 @@ struct gkr_table {
     bool owned = true;
 };
 
+// digit / counter arrays resident on the device (gkr_u32_upload)
+struct gkr_u32buf {
+    gkr_ctx* ctx = nullptr;
+    uint32_t* d = nullptr;
+    uint64_t n = 0;
+};
+
 // VecVecPolynomial<F> (src/cleanup/polys/vecvec.rs:149-160) in CSR form: rows back to back, every row even-length
 struct gkr_vecvec {
     gkr_ctx* ctx = nullptr;

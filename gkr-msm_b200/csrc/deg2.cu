@@ -930,55 +930,71 @@ __global__ void vecvec_gather_kernel(Fr* out, const Fr* src, uint64_t src_n, con
         out[i] = v;
     }
 }
-extern "C" int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, const uint32_t* row_len, uint32_t n_rows,
-                                 const uint64_t row_pad[4], const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out) {
+extern "C" int gkr_vecvec_gather_multi(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const uint32_t* idx, const uint32_t* row_len,
+                                       uint32_t n_rows, const uint64_t* row_pads, const uint64_t* col_pads, uint32_t row_logsize,
+                                       uint32_t col_logsize, gkr_vecvec** outs) {
     if (!ctx) return GKR_ERR_ARG;
-    if (!out || !row_pad || !col_pad || (n_rows && (!row_len || !idx))) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (!outs || !srcs || n_src == 0 || !row_pads || !col_pads || (n_rows && (!row_len || !idx))) return ctx->fail(GKR_ERR_ARG, "null argument");
     if (col_logsize >= 32 || row_logsize >= 32 || n_rows > ((uint64_t)1 << col_logsize)) return ctx->fail(GKR_ERR_ARG, "too many rows for col_logsize");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    gkr_vecvec* v = new gkr_vecvec();
-    v->ctx = ctx;
-    v->row_pad = frh_from_limbs(row_pad);
-    v->col_pad = frh_from_limbs(col_pad);
-    v->row_logsize = row_logsize;
-    v->col_logsize = col_logsize;
-    v->row_len.resize(n_rows);
+    std::vector<uint32_t> even(n_rows);
     uint64_t total = 0;
     for (uint32_t r = 0; r < n_rows; r++) {
-        if (row_len[r] > ((uint64_t)1 << row_logsize)) { delete v; return ctx->fail(GKR_ERR_ARG, "row longer than 1 << row_logsize"); }
-        v->row_len[r] = (row_len[r] + 1) & ~1u;
-        total += v->row_len[r];
+        if (row_len[r] > ((uint64_t)1 << row_logsize)) return ctx->fail(GKR_ERR_ARG, "row longer than 1 << row_logsize");
+        even[r] = (row_len[r] + 1) & ~1u;
+        total += even[r];
     }
-    v->total = total;
+    // padded gather index, built and uploaded once for all sources
     std::vector<uint32_t> pidx(std::max<uint64_t>(total, 1));
     uint64_t so = 0, dof = 0;
     for (uint32_t r = 0; r < n_rows; r++) {
         if (row_len[r]) std::memcpy(pidx.data() + dof, idx + so, sizeof(uint32_t) * row_len[r]);
         if (row_len[r] & 1) pidx[dof + row_len[r]] = 0xffffffffu;
         so += row_len[r];
-        dof += v->row_len[r];
+        dof += even[r];
     }
-    uint32_t* d_idx = nullptr;
     cudaStream_t st = ctx->stream;
-    cudaError_t e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), st);
-    if (e == cudaSuccess) e = cudaMallocAsync(&d_idx, sizeof(uint32_t) * (std::max<uint64_t>(total, 1) + 1), st);
+    uint32_t* d_idx = nullptr;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_idx, sizeof(uint32_t) * (std::max<uint64_t>(total, 1) + 1), st));
     int* d_bad = (int*)(d_idx + std::max<uint64_t>(total, 1));
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
     if (e == cudaSuccess && total) e = cudaMemcpyAsync(d_idx, pidx.data(), sizeof(uint32_t) * total, cudaMemcpyHostToDevice, st);
-    int bad = 0;
-    if (e == cudaSuccess && total) {
-        unsigned g = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 8);
-        vecvec_gather_kernel<<<g, 256, 0, st>>>(v->d, src ? src->d : nullptr, src ? src->n : 0, d_idx, total, fr_from_host(v->row_pad), d_bad);
-        ctx->launches++;
-        e = cudaGetLastError();
+    for (uint32_t k = 0; k < n_src; k++) outs[k] = nullptr;
+    for (uint32_t k = 0; k < n_src && e == cudaSuccess; k++) {
+        gkr_vecvec* v = new gkr_vecvec();
+        outs[k] = v;
+        v->ctx = ctx;
+        v->row_pad = frh_from_limbs(row_pads + 4 * k);
+        v->col_pad = frh_from_limbs(col_pads + 4 * k);
+        v->row_logsize = row_logsize;
+        v->col_logsize = col_logsize;
+        v->row_len = even;
+        v->total = total;
+        e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), st);
+        if (e == cudaSuccess && total) {
+            unsigned g = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 8);
+            vecvec_gather_kernel<<<g, 256, 0, st>>>(v->d, srcs[k] ? srcs[k]->d : nullptr, srcs[k] ? srcs[k]->n : 0, d_idx, total,
+                                                    fr_from_host(v->row_pad), d_bad);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
     }
+    int bad = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    if (d_idx) cudaFreeAsync(d_idx, st);
-    if (e != cudaSuccess) { gkr_vecvec_free(v); return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
-    if (bad) { gkr_vecvec_free(v); return ctx->fail(GKR_ERR_ARG, "gather index out of range"); }
-    *out = v;
+    cudaFreeAsync(d_idx, st);
+    if (e != cudaSuccess || bad) {
+        for (uint32_t k = 0; k < n_src; k++) {
+            gkr_vecvec_free(outs[k]);
+            outs[k] = nullptr;
+        }
+        return e != cudaSuccess ? ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)) : ctx->fail(GKR_ERR_ARG, "gather index out of range");
+    }
     return GKR_OK;
+}
+extern "C" int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, const uint32_t* row_len, uint32_t n_rows,
+                                 const uint64_t row_pad[4], const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out) {
+    return gkr_vecvec_gather_multi(ctx, &src, 1, idx, row_len, n_rows, row_pad, col_pad, row_logsize, col_logsize, out);
 }
 
 extern "C" uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v) { return v ? (uint32_t)v->row_len.size() : 0; }

@@ -675,6 +675,82 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
     return GKR_OK;
 }
 
+// ---- the same with the digit / counter matrix already on the device (PushForwardState::new) ------------------------------
+__device__ __forceinline__ uint32_t rows_bucket(const uint32_t* idx, uint64_t k, uint32_t xl, uint32_t clm, uint32_t group_log, uint32_t* pidx) {
+    const uint32_t y = (uint32_t)(k >> xl), x = (uint32_t)(k & (((uint64_t)1 << xl) - 1));
+    *pidx = x + ((y & ((1u << clm) - 1)) << xl);
+    return ((y >> clm) << group_log) | idx[k];
+}
+__global__ void g1_rows_hist_kernel(const uint32_t* idx, uint64_t n, uint32_t xl, uint32_t clm, uint32_t group_log, uint32_t* counts, int* bad) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        if (idx[k] >> group_log) { *bad = 1; continue; }
+        uint32_t p;
+        atomicAdd(&counts[rows_bucket(idx, k, xl, clm, group_log, &p)], 1u);
+    }
+}
+__global__ void g1_rows_scatter_kernel(const uint32_t* idx, uint64_t n, uint32_t xl, uint32_t clm, uint32_t group_log, const uint32_t* offsets,
+                                       uint32_t* cursor, uint32_t* sorted) {
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        if (idx[k] >> group_log) continue;
+        uint32_t p;
+        const uint32_t b = rows_bucket(idx, k, xl, clm, group_log, &p);
+        sorted[offsets[b] + atomicAdd(&cursor[b], 1u)] = p;
+    }
+}
+extern "C" int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const gkr_u32buf* idx, uint32_t x_logsize, uint32_t clm, uint32_t group_log,
+                                       gkr_srs** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!srs || !idx || !out || x_logsize > 30 || clm > 16 || group_log > 30) return ctx->fail(GKR_ERR_ARG, "bad argument");
+    if (srs->kind != 0) return ctx->fail(GKR_ERR_ARG, "bucket sums need affine bases");
+    const uint64_t n = idx->n, x_size = (uint64_t)1 << x_logsize;
+    if (n == 0 || n % x_size) return ctx->fail(GKR_ERR_ARG, "index matrix is not a whole number of rows");
+    if (n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many incidences");
+    const uint64_t rows = n / x_size;
+    if (x_size * std::min<uint64_t>(rows, (uint64_t)1 << clm) > srs->n) return ctx->fail(GKR_ERR_ARG, "point index out of range");
+    const uint64_t n_groups = (rows + ((uint64_t)1 << clm) - 1) >> clm;
+    const uint64_t n_buckets = n_groups << group_log;
+    if (n_buckets >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many buckets");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int c = 0;
+    while (((uint64_t)1 << c) < n_buckets) c++;
+    const size_t nbk = (size_t)1 << c;
+    uint32_t *sorted = nullptr, *counts = nullptr;
+    gkr_srs* res = new gkr_srs();
+    res->ctx = ctx;
+    res->n = n_buckets;
+    res->kind = 2;
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&res->d, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * n, st));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS + 1), st));
+    uint32_t* offsets = counts + nbk;
+    uint32_t* cursor = counts + 2 * nbk;
+    int* d_bad = (int*)(counts + 3 * nbk);
+    uint32_t* work = counts + 3 * nbk + 1;
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nbk * 3 + 1), st));
+    unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    g1_rows_hist_kernel<<<g1, 256, 0, st>>>(idx->d, n, x_logsize, clm, group_log, counts, d_bad);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, c);
+    g1_rows_scatter_kernel<<<g1, 256, 0, st>>>(idx->d, n, x_logsize, clm, group_log, offsets, cursor, sorted);
+    ctx->launches += 3;
+    int rc = msm_accumulate(ctx, srs->d, 0, sorted, counts, offsets, (uint32_t)n, c, nbk, n, work, (G1X*)res->d);
+    int bad = 0;
+    if (rc == GKR_OK) {
+        cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    cudaFreeAsync(sorted, st);
+    cudaFreeAsync(counts, st);
+    if (rc == GKR_OK && bad) rc = ctx->fail(GKR_ERR_ARG, "bucket index out of range");
+    if (rc) {
+        gkr_srs_free(res);
+        return rc;
+    }
+    *out = res;
+    return GKR_OK;
+}
+
 // sum_{i=1}^{len-1} i * B[i]: the running-sum commitment of pushforward.rs:504-524 (== commit of the digit / counter table),
 // for `count` consecutive groups of 2^group_log buckets starting at bucket `first` (one group per commitment chunk).
 extern "C" int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t first, uint32_t group_log, uint32_t count,

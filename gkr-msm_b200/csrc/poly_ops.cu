@@ -10,12 +10,6 @@
 #include <algorithm>
 #include "common.cuh"
 
-struct gkr_u32buf {
-    gkr_ctx* ctx = nullptr;
-    uint32_t* d = nullptr;
-    uint64_t n = 0;
-};
-
 // R^2 mod r (Montgomery form of a small integer v is mont_mul(v, R^2))
 __device__ __forceinline__ Fr fr_r2() {
     Fr r;

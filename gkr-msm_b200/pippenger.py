@@ -131,13 +131,14 @@ class PushForwardState:
         one = g.MONT_ONE
         zero = np.zeros(4, np.uint64)
         cl = y_logsize + d_logsize
-        self.image = [ctx.vecvec_gather(self.p_0, flat_order, flat_lens, zero, zero, x_logsize, cl),
-                      ctx.vecvec_gather(self.p_1, flat_order, flat_lens, one, one, x_logsize, cl),
-                      ctx.vecvec_gather(None, flat_order, flat_lens, zero, zero, x_logsize, cl)]
+        self.image = ctx.vecvec_gather_multi([self.p_0, self.p_1, None], flat_order, flat_lens, [zero, one, zero], [zero, one, zero],
+                                             x_logsize, cl)
         self.d_idx, self.c_idx = g.U32Buf(ctx, digits.reshape(-1)), g.U32Buf(ctx, counter.reshape(-1))
         self.d, self.c = self.d_idx.to_field(), self.c_idx.to_field()
-        ac_d = np.bincount(digits.reshape(-1), minlength=nb).astype(np.uint32)
-        ac_c = np.bincount(counter.reshape(-1), minlength=x_size).astype(np.uint32)
+        # access counts from the bucket sizes: ac_d[v] = #incidences with digit v; ac_c[v] = #buckets longer than v
+        ac_d = lens.sum(axis=0, dtype=np.uint64).astype(np.uint32)
+        len_hist = np.bincount(flat_lens, minlength=x_size + 1)[:x_size + 1]
+        ac_c = (flat_lens.shape[0] - np.cumsum(len_hist)[:x_size]).astype(np.uint32)
         self.ac_d, self.ac_c = g.U32Buf(ctx, ac_d).to_field(negate=True), g.U32Buf(ctx, ac_c).to_field(negate=True)
         sp.__exit__()
         sp = span(ctx, "state: c/d bucket sums + running-sum commitments")
@@ -147,12 +148,9 @@ class PushForwardState:
         comm_mul = 1 << clm
         n_comms = -(-y_size // comm_mul)
         self.n_comms = n_comms
-        ys = np.arange(y_size, dtype=np.uint32)
-        pidx = (np.arange(x_size, dtype=np.uint32)[None, :] + (np.uint32(x_size) * (ys % comm_mul))[:, None]).reshape(-1)
-        chunk = (ys // comm_mul)[:, None]
-        self.c_log = max(int(counter.max()).bit_length(), 1)
-        self.d_all = key.kzg.srs.bucket_sums(pidx, (digits + (chunk << np.uint32(d_logsize))).reshape(-1), n_comms << d_logsize)
-        self.c_all = key.kzg.srs.bucket_sums(pidx, (counter + (chunk << np.uint32(self.c_log))).reshape(-1), n_comms << self.c_log)
+        self.c_log = max((int(lens.max()) - 1).bit_length(), 1)  # counters run up to the longest bucket
+        self.d_all = key.kzg.srs.bucket_sums_rows(self.d_idx, x_logsize, clm, d_logsize)
+        self.c_all = key.kzg.srs.bucket_sums_rows(self.c_idx, x_logsize, clm, self.c_log)
         self.d_comm = list(self.d_all.weighted_sums(d_logsize, n_comms))
         self.c_comm = list(self.c_all.weighted_sums(self.c_log, n_comms))
         sp.__exit__()

@@ -30,6 +30,7 @@ typedef struct gkr_ctx gkr_ctx;               /* device context: stream, scratch
 typedef struct gkr_table gkr_table;           /* device-resident dense table (`Vec<Fr>`)                */
 typedef struct gkr_so gkr_so;                 /* a `Sumcheckable` object                                */
 typedef struct gkr_transcript gkr_transcript; /* host-side ProofTranscript2 (merlin)                    */
+typedef struct gkr_u32buf gkr_u32buf;         /* device-resident u32 array (digits, counters, indices)   */
 
 typedef enum gkr_status {
     GKR_OK = 0,
@@ -145,6 +146,11 @@ int gkr_vecvec_upload(gkr_ctx* ctx, const uint64_t* flat, const uint32_t* row_le
  * host array `idx` (src == NULL: the all-ones table) -- the bucket images of PushForwardState::new (pushforward.rs:363-396). */
 int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, const uint32_t* row_len, uint32_t n_rows,
                       const uint64_t row_pad[4], const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out);
+/* n_src polynomials over the same rows in one call (one index upload): srcs[k] may be NULL (all ones); row_pads / col_pads
+ * hold n_src x 4 u64; outs receives n_src handles. */
+int gkr_vecvec_gather_multi(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const uint32_t* idx, const uint32_t* row_len,
+                            uint32_t n_rows, const uint64_t* row_pads, const uint64_t* col_pads, uint32_t row_logsize,
+                            uint32_t col_logsize, gkr_vecvec** outs);
 uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v);
 uint64_t gkr_vecvec_total_len(const gkr_vecvec* v); /* elements after even-padding */
 int gkr_vecvec_download(gkr_ctx* ctx, const gkr_vecvec* v, uint64_t* flat_out, uint32_t* row_len_out, uint64_t row_pad[4],
@@ -203,6 +209,11 @@ int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uint64_t* g0_x
  * running-sum commitment of pushforward.rs:504-524.  gkr_g1_download_affine normalises points for inspection. */
 int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* point_idx, const uint32_t* bucket_idx, uint64_t n,
                        uint32_t n_buckets, gkr_srs** out);
+/* the same for the digit / counter matrices of PushForwardState::new resident on the device: idx holds rows of 2^x_logsize
+ * entries (row y, column x); incidence (y, x) adds bases[x + 2^x_logsize * (y mod 2^clm)] to bucket
+ * ((y >> clm) << group_log) | idx[y][x] (pushforward.rs:401-429 with the row merge of :433-456 folded in). */
+int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const gkr_u32buf* idx, uint32_t x_logsize, uint32_t clm, uint32_t group_log,
+                            gkr_srs** out);
 int gkr_g1_weighted_bucket_sum(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t* out_xy);
 /* batched forms for the commitment chunks of one proof (y_size / 2^clm of them): bucket ids (chunk << group_log) | bucket
  * turn all chunks into ONE gkr_g1_bucket_sums call; gkr_g1_weighted_bucket_sums then returns `count` running-sum
@@ -226,7 +237,6 @@ int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_windows, uint64
  *                     src_k is the all-ones table (constant shifts and pads of c_adj / d_adj, pushforward.rs:700-710).
  * gkr_poly_eval / gkr_poly_div_by_linear: `ev`, `div_by_linear` (kzg.rs:73-81, 142-150).
  * gkr_knuckles_*: KnucklesProvingKey::new inverses and compute_t (knuckles.rs:65-81, 111-154). */
-typedef struct gkr_u32buf gkr_u32buf;
 typedef struct gkr_knuckles gkr_knuckles;
 int gkr_u32_upload(gkr_ctx* ctx, const uint32_t* vals, uint64_t n, gkr_u32buf** out);
 void gkr_u32_free(gkr_u32buf* b);

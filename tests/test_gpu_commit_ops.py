@@ -124,3 +124,27 @@ def test_batched_bucket_commitments(ctx):
         allb.weighted_sums(d_log, chunks + 2)
     with pytest.raises(g.GkrError):
         allb.msm_batch(ctx.eq_table(to_limbs(r_d)), 1 << d_log, 0, 1 << d_log, chunks + 1)
+
+
+@pytest.mark.parametrize("clm", [0, 1, 2])
+def test_bucket_sums_rows_matches_host_index_route(ctx, clm):
+    """device-resident digit matrix -> bucket sums == the explicit (point index, bucket index) route, incl. a ragged last chunk"""
+    rng = random.Random(20 + clm)
+    xl, d_log, y_size = 4, 2, 5
+    x_size, cm = 1 << xl, 1 << clm
+    bases = [rand_g1(rng) for _ in range(x_size * cm)]
+    srs = g.Srs(ctx, aff_to_limbs(bases))
+    digits = np.array([[rng.randrange(1 << d_log) for _ in range(x_size)] for _ in range(y_size)], dtype=np.uint32)
+    got = srs.bucket_sums_rows(g.U32Buf(ctx, digits.reshape(-1)), xl, clm, d_log)
+    n_comms = -(-y_size // cm)
+    assert got.n == n_comms << d_log
+    pidx = np.concatenate([np.arange(x_size, dtype=np.uint32) + x_size * (y % cm) for y in range(y_size)])
+    bidx = np.concatenate([digits[y] + ((y // cm) << d_log) for y in range(y_size)])
+    want = srs.bucket_sums(pidx, bidx, n_comms << d_log)
+    assert np.array_equal(got.download_affine(), want.download_affine())
+    comms = [res_to_point(r) for r in got.weighted_sums(d_log, n_comms)]
+    for k in range(n_comms):
+        ys = range(k * cm, min((k + 1) * cm, y_size))
+        assert comms[k] == CV.g1_msm([bases[x + x_size * (y % cm)] for y in ys for x in range(x_size)], [int(digits[y][x]) for y in ys for x in range(x_size)])
+    with pytest.raises(g.GkrError):  # a digit that does not fit group_log bits
+        srs.bucket_sums_rows(g.U32Buf(ctx, digits.reshape(-1)), xl, clm, 1)
