@@ -71,3 +71,43 @@ def test_pippenger_device_vs_oracle(ctx, d, x, nbits, clm):
     # the pair returned by the prover satisfies the (mock-setup) pairing equation A == tau * B
     a, b = res_to_point(dpair[0]), res_to_point(dpair[1])
     okey.kzg.verify_pair((a, b))
+
+
+@pytest.mark.parametrize("d,x,nbits,clm", [(6, 12, 128, 0), (5, 10, 64, 2), (8, 16, 128, 0)])
+def test_pippenger_full_size_properties(ctx, d, x, nbits, clm):
+    """Sizes the python prover cannot reach (up to BASELINE config[0], x = 16): size-independent properties instead of a
+    byte comparison -- (1) the ORACLE VERIFIER accepts the device-made proof (every sumcheck round, every claim reduction,
+    the opening equation and the pairing check A == tau B of the mock setup), (2) the proved MSM result, recovered by the
+    verifier from the output tables, equals the true MSM, known in closed form because the synthetic points are the
+    arithmetic progression (k0 + i step) G:  sum_i c_i P_i = (sum_i c_i (k0 + i step)) G."""
+    rng = np.random.default_rng(1000 * d + x)
+    cfg = DPP.pippenger_config(d, x, nbits, clm)
+    n = 1 << x
+    k0, step = 0x1234567 + x, 0x9E3779B97F4A7C15
+    pts = H.te_points_arithmetic_progression(k0, step, n)
+    points_xy = np.stack([to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])])
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, nbits // 8:] = 0
+    coefs_u64 = raw.view(np.uint64).reshape(n, 4)
+    coefs = [int.from_bytes(raw[i].tobytes(), "little") for i in range(n)]
+    r = [int.from_bytes(rng.bytes(32), "little") % P for _ in range(cfg["y_logsize"])]
+    tau = int.from_bytes(rng.bytes(32), "little") % P
+    nv = x + clm
+    key = DPP.KnucklesKey(ctx, DPP.KzgKey.mock_setup(ctx, tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    tr = g.Transcript(b"fgstglsp")
+    ddense, dclaims, dpair = DPP.run_pippenger(ctx, tr, points_xy, coefs_u64, cfg, r, key)
+    proof = tr.proof()
+    okey = PP.KnucklesKey(PP.KzgKey(tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    dense_output = [from_limbs(t.download()) for t in ddense]
+    total = sum(c * (k0 + i * step) for i, c in enumerate(coefs)) % CV.TE_SUBGROUP_ORDER
+    expected = CV.te_to_affine(H.te_mul(total, CV.TE_GEN))
+    tv = ProofTranscript2.start_verifier(b"fgstglsp", proof)
+    got = PP.verify_pippenger(tv, cfg, dense_output, (list(dclaims[0]), list(dclaims[1])), okey, expected)
+    assert tv.ctr == len(proof) and got == expected
+    okey.kzg.verify_pair((res_to_point(dpair[0]), res_to_point(dpair[1])))
+    # a corrupted proof is rejected
+    bad = bytearray(proof)
+    bad[len(bad) // 3] ^= 4
+    with pytest.raises(AssertionError):
+        PP.verify_pippenger(ProofTranscript2.start_verifier(b"fgstglsp", bytes(bad)), cfg, dense_output,
+                            (list(dclaims[0]), list(dclaims[1])), okey, expected)
