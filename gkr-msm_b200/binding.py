@@ -880,3 +880,27 @@ def pushforward_bucketize(coefs_u64, y_size: int, d_logsize: int):
     if rc:
         raise GkrError(rc, "gkr_pushforward_bucketize: bad arguments")
     return digits, counter, order, lens
+
+
+FQ_MONT_ONE = np.array([0x760900000002FFFD, 0xEBF4000BC40C0002, 0x5F48985753C758BA, 0x77CE585370525745, 0x5C071A97A256EC6D,
+                        0x15F65EC3FA80E493], dtype=np.uint64)
+
+
+def g1_sum(points_xy) -> np.ndarray:
+    """Sum of a few affine G1 points ((n, 12) Montgomery limbs, all-zero = infinity) on the host (csrc/host_g1.hpp): the
+    combine step of an MSM split by point range over several GPUs -- G points, one inversion."""
+    lib = load_library()
+    lib.gkr_host_g1_horner.restype = C.c_int
+    lib.gkr_host_g1_horner.argtypes = [_vp, C.c_int, C.c_int, _vp]
+    pts = np.ascontiguousarray(points_xy, dtype=np.uint64).reshape(-1, 12)
+    ws = np.zeros((pts.shape[0], 24), np.uint64)
+    for i, p in enumerate(pts):
+        if p.any():
+            ws[i, :12] = p
+            ws[i, 12:18] = FQ_MONT_ONE
+            ws[i, 18:24] = FQ_MONT_ONE
+    out = np.zeros(12, np.uint64)
+    rc = lib.gkr_host_g1_horner(_ptr(ws), 0, pts.shape[0], _ptr(out))
+    if rc:
+        raise GkrError(rc, "gkr_host_g1_horner")
+    return out

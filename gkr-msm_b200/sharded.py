@@ -97,3 +97,15 @@ class ShardedProd3Sumcheck:
         for t in tabs:
             t.free()
         return out
+
+
+def sharded_commit(srs_slice: "g.Srs", scalars_slice: "g.Table", exchange) -> np.ndarray:
+    """KzgProvingKey::commit (src/commitments/kzg.rs:123-126) split by POINT RANGE over the ranks of one box (SURVEY 8e):
+    every rank commits its own slice of the SRS / coefficient vector on its GPU, the G affine partial results (96 bytes
+    each) are all-gathered through the shared-memory exchange and added on the host.  The group is commutative, so the
+    result is the same point -- and the same canonical limbs -- as the single-GPU commitment.  exchange None: one rank."""
+    local = srs_slice.msm(scalars_slice)
+    if exchange is None:
+        return local
+    allp = exchange.allgather(local.reshape(3, 4))
+    return g.g1_sum(allp.reshape(exchange.world, 12))

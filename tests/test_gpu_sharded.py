@@ -67,3 +67,56 @@ def test_two_rank_sharded_proof_equals_single_rank(ctx, world):
     chal = point[::-1].copy()  # the protocol returns the challenges reversed (sumcheck.rs:120)
     oev, ofe = coracle.dense_sumcheck(0, 10, host, n, ocl, chal)
     assert np.array_equal(ofe, fe)
+
+
+def _msm_worker(rank, world, port, n_local, tau_limbs, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    import gkr_msm_b200 as g
+    from gkr_msm_b200 import hostmath as H
+    from gkr_msm_b200.sharded import sharded_commit
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = g.Context(0)
+    name = f"/gkr_msm_test_{port}"
+    ex = g.Exchange(name, rank, world, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        ex = g.Exchange(name, rank, world, create=False)
+    dist.barrier()
+    # every rank regenerates the whole mock SRS and keeps its own point range (a real deployment loads only its range)
+    full = g.Srs.mock_setup(ctx, np.array(tau_limbs, dtype=np.uint64), H.g1_to_limbs(H.G1_GEN), n_local * world)
+    mine = g.Srs(ctx, full.download_affine()[rank * n_local:(rank + 1) * n_local])
+    scalars = ctx.synth(5, n_local, first_index=rank * n_local)
+    out = sharded_commit(mine, scalars, ex)
+    q.put((rank, out.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_msm_split_by_point_range_equals_single_gpu(ctx):
+    """commitment MSM sharded by point range over 2 ranks == the single-GPU commitment, limb for limb"""
+    import torch.multiprocessing as mp
+
+    import gkr_msm_b200 as g
+    from gkr_msm_b200 import hostmath as H
+    from tests.util import to_limb1
+
+    world, n_local = 2, 700
+    tau = to_limb1(0x1234567890ABCDEF)
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = 31500 + random.randrange(2000)
+    procs = [mpctx.Process(target=_msm_worker, args=(r, world, port, n_local, tau.tolist(), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1] == res[1][1]
+    srs = g.Srs.mock_setup(ctx, tau, H.g1_to_limbs(H.G1_GEN), n_local * world)
+    whole = srs.msm(ctx.synth(5, n_local * world))
+    assert whole.tolist() == res[0][1]

@@ -119,3 +119,19 @@ def test_pushforward_bucketize_matches_reference_bookkeeping():
             assert [int(v) for v in lens[y]] == [len(b) for b in buckets]
     with pytest.raises(g.GkrError):
         g.pushforward_bucketize(np.zeros((4, 4), np.uint64), 40, 8)
+
+
+def test_g1_sum_combines_partial_commitments():
+    """host combine step of the MSM split by point range: sum of G affine partial results"""
+    from gkr_msm_b200 import hostmath as H
+    from oracle.pyref import curves as CV
+
+    rng = random.Random(13)
+    pts = [CV.g1_mul(rng.randrange(1, P), CV.G1_GEN) for _ in range(5)] + [None]
+    pts.append((pts[0][0], CV.Q - pts[0][1]))  # cancels the first one
+    got = g.g1_sum(np.stack([H.g1_to_limbs(p) for p in pts]))
+    want = None
+    for p in pts:
+        want = CV.g1_add(want, p)
+    assert H.g1_from_limbs(got) == want
+    assert not g.g1_sum(np.zeros((3, 12), np.uint64)).any()

@@ -65,6 +65,7 @@ def run(args, ctx=None):
         proof_len = len(tr.proof())
     if args.profile:
         PR.PROFILE = {}
+        ctx.host_stats(True)
         tr = g.Transcript(b"fgstglsp")
         t0 = time.perf_counter()
         DPP.run_pippenger(ctx, tr, points_xy, coefs, cfg, r, key)
@@ -73,6 +74,9 @@ def run(args, ctx=None):
         for k, v in sorted(PR.PROFILE.items(), key=lambda kv: -kv[1]):
             print(f"  {v * 1e3:9.2f} ms  {k}", file=sys.stderr)
         print(f"  {tot * 1e3:9.2f} ms  total (with span syncs)", file=sys.stderr)
+        nl, nw, waits, _ = ctx.host_stats(True)
+        print(f"  round kernels: {waits} result waits, {nw / 1e6:.2f} ms spinning on results ({nw / 1e3 / max(waits, 1):.1f} us each), "
+              f"{nl / 1e6:.2f} ms inside launch calls", file=sys.stderr)
         PR.PROFILE = None
     best = min(times)
     return ({
