@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
             spec = importlib.util.spec_from_file_location("bench_pippenger", os.path.join(ROOT, "tools", "bench_pippenger.py"))
             bp = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(bp)
-            r = bp.run(argparse.Namespace(x_logsize=16, d_logsize=8, nbits=128, clm=0, reps=3, seed=7, profile=False), ctx=ctx)
+            r = bp.run(argparse.Namespace(x_logsize=16, d_logsize=8, nbits=128, clm=0, reps=3, seed=7, profile=False, python_host=False), ctx=ctx)
             pip = {"prove_ms": r["prove_ms_best"], "what": "benchutils::run_pippenger (witness + phase-1 commitments + proof), wall clock, "
                    "inputs on the host, SRS resident", "config": "x_logsize 16, d_logsize 8, nbits 128, clm 0 (BASELINE config[0]: 2^20 "
                    "point-digit incidences)", "proof_bytes": r["proof_bytes"], "gpu_launches": r["gpu_launches"],

@@ -904,3 +904,29 @@ def g1_sum(points_xy) -> np.ndarray:
     if rc:
         raise GkrError(rc, "gkr_host_g1_horner")
     return out
+
+
+def run_pippenger_native(ctx: Context, transcript: Transcript, srs: "Srs", g0_xy, knuckles: "Knuckles", points_xy, coefs_u64, d_logsize: int,
+                         x_logsize: int, num_bits: int, clm: int, r_limbs):
+    """benchutils::run_pippenger (pippenger.rs:499-559) with the host orchestration in C++ (csrc/protocol.cu).
+    Returns (dense_output (3(d+1), 2^y_logsize, 4), claim_evs (3(d+1), 4), pair (2, 12))."""
+    lib = ctx.lib
+    if not hasattr(lib.gkr_run_pippenger, "_sig"):
+        lib.gkr_run_pippenger.restype = C.c_int
+        lib.gkr_run_pippenger.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, _vp, _vp, _vp, _vp]
+        lib.gkr_run_pippenger._sig = True
+    y_size = (num_bits + d_logsize - 1) // d_logsize
+    yl = (y_size - 1).bit_length()
+    n_out = 3 * (d_logsize + 1)
+    px = np.ascontiguousarray(points_xy[0], dtype=np.uint64)
+    py = np.ascontiguousarray(points_xy[1], dtype=np.uint64)
+    co = np.ascontiguousarray(coefs_u64, dtype=np.uint64)
+    g0 = _limbs(g0_xy).reshape(12)
+    rr = _limbs(r_limbs).reshape(-1, 4)
+    assert rr.shape[0] == yl and px.shape[0] == 1 << x_logsize
+    dense = np.zeros((n_out, 1 << yl, 4), np.uint64)
+    evs = np.zeros((n_out, 4), np.uint64)
+    pair = np.zeros((2, 12), np.uint64)
+    ctx.check(lib.gkr_run_pippenger(ctx.h, transcript.h, srs.h, _ptr(g0), knuckles.h, _ptr(px), _ptr(py), _ptr(co), d_logsize, x_logsize, num_bits,
+                                    clm, _ptr(rr), _ptr(dense), _ptr(evs), _ptr(pair)))
+    return dense, evs, pair

@@ -172,5 +172,43 @@ static inline void horner_windows(const G1XH* window_sums, int c, int n_windows,
     to_affine(acc, out_xy);
 }
 
+// ark-bls12-381 0.4.0 compressed G1 (zcash / IETF format, proof_transcript.rs:52-69): 48-byte big-endian x; top bits of
+// byte 0 = (compressed, infinity, y is the lexicographically larger root).  xy: 12 u64 Montgomery limbs, all zero = infinity.
+static inline void serialize_compressed(const uint64_t xy[12], uint8_t out[48]) {
+    bool inf = true;
+    for (int i = 0; i < 12; i++) inf = inf && xy[i] == 0;
+    std::memset(out, 0, 48);
+    if (inf) {
+        out[0] = 0xC0;
+        return;
+    }
+    FqH x, y, one_raw = {{1, 0, 0, 0, 0, 0}};
+    std::memcpy(x.v, xy, 48);
+    std::memcpy(y.v, xy + 6, 48);
+    x = mul(x, one_raw);  // leave Montgomery form
+    y = mul(y, one_raw);
+    for (int i = 0; i < 6; i++)
+        for (int b = 0; b < 8; b++) out[47 - (8 * i + b)] = (uint8_t)(x.v[i] >> (8 * b));
+    out[0] |= 0x80;
+    // y > (q - 1) / 2  <=>  2y > q - 1  <=>  2y >= q + 1 (q odd)  <=>  2y > q
+    uint64_t t[7];
+    uint64_t carry = 0;
+    for (int i = 0; i < 6; i++) {
+        t[i] = (y.v[i] << 1) | carry;
+        carry = y.v[i] >> 63;
+    }
+    t[6] = carry;
+    bool greater = t[6] != 0;
+    if (!greater) {
+        for (int i = 5; i >= 0; i--) {
+            if (t[i] != MOD[i]) {
+                greater = t[i] > MOD[i];
+                break;
+            }
+        }
+    }
+    if (greater) out[0] |= 0x20;
+}
+
 }  // namespace g1h
 }  // namespace gkr

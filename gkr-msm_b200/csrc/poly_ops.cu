@@ -346,6 +346,12 @@ extern "C" int gkr_knuckles_create(gkr_ctx* ctx, uint32_t num_vars, const uint64
     *out = key;
     return GKR_OK;
 }
+extern "C" uint32_t gkr_knuckles_num_vars(const gkr_knuckles* key) { return key ? key->num_vars : 0; }
+extern "C" int gkr_knuckles_k(const gkr_knuckles* key, uint64_t out[4]) {
+    if (!key || !out) return GKR_ERR_ARG;
+    frh_to_limbs(key->k, out);
+    return GKR_OK;
+}
 extern "C" void gkr_knuckles_free(gkr_knuckles* key) {
     if (!key) return;
     if (key->inverses) cudaFreeAsync(key->inverses, key->ctx->stream);

@@ -247,6 +247,8 @@ int gkr_table_lincomb(gkr_ctx* ctx, uint32_t n_terms, gkr_table* const* src, con
 int gkr_poly_eval(gkr_ctx* ctx, const gkr_table* poly, const uint64_t x[4], uint64_t out[4]);
 int gkr_poly_div_by_linear(gkr_ctx* ctx, const gkr_table* poly, const uint64_t pt[4], gkr_table** quotient, uint64_t rem[4]);
 int gkr_knuckles_create(gkr_ctx* ctx, uint32_t num_vars, const uint64_t k[4], gkr_knuckles** out);
+uint32_t gkr_knuckles_num_vars(const gkr_knuckles* key);
+int gkr_knuckles_k(const gkr_knuckles* key, uint64_t out[4]);
 void gkr_knuckles_free(gkr_knuckles* key);
 int gkr_knuckles_compute_t(gkr_ctx* ctx, const gkr_knuckles* key, const gkr_table* poly, const uint64_t* point, uint32_t n_point,
                            gkr_table** t_out, uint64_t opening[4]);
@@ -274,6 +276,19 @@ int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out);
  * out_final_evals: n_polys elements. */
 int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_rounds, uint64_t out_claim[4],
                        uint64_t* out_point, uint64_t* out_final_evals);
+
+/* benchutils::run_pippenger   src/cleanup/protocols/pippenger.rs:499-559 -- the whole prover of `examples/pippenger`:
+ * PippengerWG::new (bucketing, images, phase-1 commitments, bintree + triangle witness), the output claims at `r`, and
+ * Pippenger::prove (ending GKR, second phase, pushforward with the logup main phase, multiopen reduction, Knuckles opening)
+ * written to `transcript`.  Host orchestration in C++ (csrc/protocol.cu), every table-sized step on the device.
+ *   srs / g0_xy / knuckles: KnucklesProvingKey (kzg.rs:17-22, knuckles.rs:42-81) with num_vars = x_logsize + clm;
+ *   points_x / points_y: 2^x_logsize affine Bandersnatch coordinates (Fr Montgomery limbs); coefs: 2^x_logsize x 4 plain
+ *   little-endian u64 (scalars of num_bits bits); r: y_logsize elements, y_size = ceil(num_bits / d_logsize);
+ *   dense_output: 3 (d_logsize + 1) tables of 2^y_logsize elements (PippengerOutput::output); claim_evs: their evaluations
+ *   at r; pair_xy: the two G1 points of the final pairing check (24 u64).  Output pointers may be NULL. */
+int gkr_run_pippenger(gkr_ctx* ctx, gkr_transcript* transcript, const gkr_srs* srs, const uint64_t* g0_xy, const gkr_knuckles* knuckles,
+                      const uint64_t* points_x, const uint64_t* points_y, const uint64_t* coefs, uint32_t d_logsize, uint32_t x_logsize,
+                      uint32_t num_bits, uint32_t clm, const uint64_t* r, uint64_t* dense_output, uint64_t* claim_evs, uint64_t* pair_xy);
 
 /* ---- multi-GPU: hypercube sharded by its top index bits, one process per GPU ----------
  * gkr_exchange: all-gather of a few field elements between the ranks of one box through POSIX shared

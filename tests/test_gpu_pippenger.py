@@ -71,6 +71,13 @@ def test_pippenger_device_vs_oracle(ctx, d, x, nbits, clm):
     # the pair returned by the prover satisfies the (mock-setup) pairing equation A == tau * B
     a, b = res_to_point(dpair[0]), res_to_point(dpair[1])
     okey.kzg.verify_pair((a, b))
+    # the C++ host orchestration (gkr_run_pippenger, csrc/protocol.cu) produces the same bytes
+    tr2 = g.Transcript(b"fgstglsp")
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr2, kzg.srs, kzg.g0, key.dev, points_xy, coefs_to_u64(coefs), d, x, nbits, clm, to_limbs(r))
+    assert tr2.proof() == oproof
+    assert [from_limbs(t) for t in ndense] == odense
+    assert from_limbs(nevs) == list(oclaims[1])
+    assert np.array_equal(npair[0], dpair[0]) and np.array_equal(npair[1], dpair[1])
 
 
 @pytest.mark.parametrize("d,x,nbits,clm", [(6, 12, 128, 0), (5, 10, 64, 2), (8, 16, 128, 0)])
@@ -97,6 +104,12 @@ def test_pippenger_full_size_properties(ctx, d, x, nbits, clm):
     tr = g.Transcript(b"fgstglsp")
     ddense, dclaims, dpair = DPP.run_pippenger(ctx, tr, points_xy, coefs_u64, cfg, r, key)
     proof = tr.proof()
+    tr2 = g.Transcript(b"fgstglsp")  # C++ host orchestration: same proof, outputs and pairing pair
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr2, key.kzg.srs, key.kzg.g0, key.dev, points_xy, coefs_u64, d, x, nbits, clm, to_limbs(r))
+    assert tr2.proof() == proof
+    assert all(np.array_equal(a, t.download()) for a, t in zip(ndense, ddense))
+    assert from_limbs(nevs) == list(dclaims[1])
+    assert np.array_equal(npair[0], dpair[0]) and np.array_equal(npair[1], dpair[1])
     okey = PP.KnucklesKey(PP.KzgKey(tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
     dense_output = [from_limbs(t.download()) for t in ddense]
     total = sum(c * (k0 + i * step) for i, c in enumerate(coefs)) % CV.TE_SUBGROUP_ORDER
