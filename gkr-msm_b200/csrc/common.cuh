@@ -76,6 +76,10 @@ struct gkr_ctx {
         event_pool.pop_back();
         return e;
     }
+    // pinned staging ring for small parameter uploads (one truly asynchronous H2D copy per object instead of a dozen
+    // pageable ones, no synchronisation until the ring wraps)
+    unsigned char* stage_host = nullptr;
+    size_t stage_size = 0, stage_pos = 0;
     int fail(int code, const std::string& msg) {
         err = msg;
         return code;
@@ -167,6 +171,20 @@ static inline gkr::FrH fr_to_host(const Fr& a) {
     for (int i = 0; i < 4; i++) r.v[i] = (uint64_t)a.l[2 * i] | ((uint64_t)a.l[2 * i + 1] << 32);
     return r;
 }
+
+// copy n bytes of host data to the device through the context's pinned staging ring (asynchronous on ctx->stream; the
+// source may be freed as soon as the call returns)
+int gkr_stage_upload(gkr_ctx* ctx, void* d_dst, const void* src, size_t n);
+
+// final_evals of a sumcheck object: element 0 of each of the n <= GKR_MAX_POLYS tables, delivered through the object's
+// result slot (one tiny kernel + a flag spin instead of n device-to-host copies and a stream synchronisation)
+struct GkrFirsts {
+    const Fr* p[GKR_MAX_POLYS];
+    int n;
+};
+int gkr_fetch_firsts(gkr_ctx* ctx, int slot, const GkrFirsts& f, gkr::FrH* out);
+// the same for any number of tables whose pointers already sit in a DEVICE array
+int gkr_fetch_firsts_dev(gkr_ctx* ctx, int slot, const Fr* const* d_ptrs, int n, gkr::FrH* out);
 
 // host side: wait for the launch `seq` on `slot` and fold its per-block partials (n_acc accumulators per block)
 int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out);

@@ -384,6 +384,7 @@ class Deg2SO : public gkr_so {
     Fr* d_pt_row = nullptr;  // device copy of the row variables (for the pad kernel)
     uint32_t m_row = 0;      // number of row variables excluding the binding one at round 0
     // data
+    unsigned char* d_params = nullptr;  // one allocation + one staged upload for every small parameter array
     Fr* slab[2] = {nullptr, nullptr};
     const Fr** d_tabs[3] = {nullptr, nullptr, nullptr};  // device pointer arrays: [0] inputs, [1]/[2] ping-pong
     std::vector<const Fr*> h_sets[3];  // host copies of the three pointer arrays
@@ -402,16 +403,10 @@ class Deg2SO : public gkr_so {
         delete dense;
         for (auto* t : dense_tables) gkr_table_free(t);
         cudaStream_t s = ctx->stream;
-        if (d_off) cudaFreeAsync(d_off, s);
-        if (d_poff) cudaFreeAsync(d_poff, s);
+        if (d_params) cudaFreeAsync(d_params, s);  // offsets, gate blocks, gammas, pads, points, pointer arrays
         if (d_eq) cudaFreeAsync(d_eq, s);
         if (d_rowcoef) cudaFreeAsync(d_rowcoef, s);
-        if (d_pt_row) cudaFreeAsync(d_pt_row, s);
         for (int i = 0; i < 2; i++) if (slab[i]) cudaFreeAsync(slab[i], s);
-        for (int i = 0; i < 3; i++) if (d_tabs[i]) cudaFreeAsync(d_tabs[i], s);
-        if (d_blocks) cudaFreeAsync(d_blocks, s);
-        if (d_gammas) cudaFreeAsync(d_gammas, s);
-        if (d_pads) cudaFreeAsync(d_pads, s);
         if (slot >= 0) gkr_result_slot_release(ctx, slot);
     }
 
@@ -545,12 +540,7 @@ class Deg2SO : public gkr_so {
         if (dense) return dense->final_evals(out);
         if (is_vecvec) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: sparse stage has no final evals (vecvec_eq.rs:390-393)");
         if (round_idx != n_sparse) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: can only be called after the last round");
-        const std::vector<const Fr*>& ptrs = h_sets[cur_set];
-        Fr* stage = ctx->slots_host[slot].part;  // pinned staging: P async copies, one synchronisation
-        for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&stage[j], ptrs[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = 0; j < P; j++) out[j] = fr_to_host(stage[j]);
-        return GKR_OK;
+        return gkr_fetch_firsts_dev(ctx, slot, d_tabs[cur_set], P, out);
     }
 
     gkr::FrH claim() const override { return dense ? dense->claim() : claim_; }
@@ -607,27 +597,16 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
             if (r < nrows) acc += lens[b][r];
         }
     }
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_off, sizeof(uint32_t) * h_off.size(), s));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_poff, sizeof(uint32_t) * h_off.size(), s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_off, h_off.data(), sizeof(uint32_t) * h_off.size(), cudaMemcpyHostToDevice, s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_poff, h_poff.data(), sizeof(uint32_t) * h_off.size(), cudaMemcpyHostToDevice, s));
-
     // gate program, gammas, pads
     std::vector<Deg2Block> blocks = expand_blocks(gs);
     n_blocks = (int)blocks.size();
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_blocks, sizeof(Deg2Block) * blocks.size(), s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_blocks, blocks.data(), sizeof(Deg2Block) * blocks.size(), cudaMemcpyHostToDevice, s));
     std::vector<Fr> g(gs.n_outs);
     for (int i = 0; i < gs.n_outs; i++) g[i] = fr_from_host(gamma_pows[i]);
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_gammas, sizeof(Fr) * g.size(), s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_gammas, g.data(), sizeof(Fr) * g.size(), cudaMemcpyHostToDevice, s));
     std::vector<Fr> pads(2 * P);
     for (int j = 0; j < P; j++) {
         pads[j] = fr_from_host(row_pads[j]);
         pads[P + j] = fr_from_host(col_pads[j]);
     }
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_pads, sizeof(Fr) * pads.size(), s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_pads, pads.data(), sizeof(Fr) * pads.size(), cudaMemcpyHostToDevice, s));
     // pad_results / col_pad_results folded with gamma (vecvec_eq.rs:309-315, 372-378)
     {
         std::vector<gkr::FrH> o(gs.n_outs);
@@ -661,20 +640,69 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
         eq_off[b] = eq_total;
         eq_total += lvl_size[b];
     }
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_eq, sizeof(Fr) * std::max<uint64_t>(eq_total, 1), s));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_pt_row, sizeof(Fr) * std::max<uint32_t>(m_row, 1), s));
-    {
-        std::vector<Fr> p(std::max<uint32_t>(m_row, 1));
-        for (uint32_t i = 0; i < m_row; i++) p[i] = fr_from_host(pt_row[i]);
-        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_pt_row, p.data(), sizeof(Fr) * p.size(), cudaMemcpyHostToDevice, s));
-        GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));  // `p`, `pads`, `g`, `blocks`, offsets are stack/heap temporaries
+    std::vector<Fr> p_row(std::max<uint32_t>(m_row, 1), fr_from_host(ZERO)), p_col(std::max<uint32_t>(col, 1), fr_from_host(ZERO));
+    for (uint32_t i = 0; i < m_row; i++) p_row[i] = fr_from_host(pt_row[i]);
+    for (uint32_t i = 0; i < col; i++) p_col[i] = fr_from_host(point[i]);
+    std::vector<Fr> singles(n_sparse + 1, fr_from_host(ZERO));  // one-entry eq levels (all remaining row variables are padding)
+    for (uint32_t b = 0; b < n_sparse; b++) {
+        uint32_t lvl = m_row >= b ? m_row - b : 0;
+        if (lvl <= npad) singles[b] = fr_from_host(prefix[lvl]);
     }
+
+    // data: ping-pong slabs sized for round 1 and round 2, pointer arrays
+    uint64_t sz1 = n_sparse >= 1 ? totals[1] : 0, sz2 = n_sparse >= 2 ? totals[2] : 0;
+    std::vector<const Fr*> p1(P), p2(P);
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[0], sizeof(Fr) * std::max<uint64_t>(sz1 * P, 1), s));
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[1], sizeof(Fr) * std::max<uint64_t>(sz2 * P, 1), s));
+    for (int j = 0; j < P; j++) {
+        p1[j] = slab[0] + (size_t)j * sz1;
+        p2[j] = slab[1] + (size_t)j * sz2;
+    }
+    h_sets[0] = inputs;
+    h_sets[1] = p1;
+    h_sets[2] = p2;
+
+    // ONE device allocation and ONE staged upload for all of the above
+    std::vector<unsigned char> arena;
+    auto put = [&](const void* src, size_t n) {
+        size_t off = (arena.size() + 31) & ~(size_t)31;
+        arena.resize(off + std::max<size_t>(n, 1));
+        if (n) std::memcpy(arena.data() + off, src, n);
+        return off;
+    };
+    const size_t o_off = put(h_off.data(), sizeof(uint32_t) * h_off.size());
+    const size_t o_poff = put(h_poff.data(), sizeof(uint32_t) * h_poff.size());
+    const size_t o_blocks = put(blocks.data(), sizeof(Deg2Block) * blocks.size());
+    const size_t o_g = put(g.data(), sizeof(Fr) * g.size());
+    const size_t o_pads = put(pads.data(), sizeof(Fr) * pads.size());
+    const size_t o_prow = put(p_row.data(), sizeof(Fr) * p_row.size());
+    const size_t o_pcol = put(p_col.data(), sizeof(Fr) * p_col.size());
+    const size_t o_single = put(singles.data(), sizeof(Fr) * singles.size());
+    const size_t o_t0 = put(inputs.data(), sizeof(Fr*) * P);
+    const size_t o_t1 = put(p1.data(), sizeof(Fr*) * P);
+    const size_t o_t2 = put(p2.data(), sizeof(Fr*) * P);
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_params, arena.size(), s));
+    {
+        int rc = gkr_stage_upload(ctx, d_params, arena.data(), arena.size());
+        if (rc) return rc;
+    }
+    d_off = (uint32_t*)(d_params + o_off);
+    d_poff = (uint32_t*)(d_params + o_poff);
+    d_blocks = (Deg2Block*)(d_params + o_blocks);
+    d_gammas = (Fr*)(d_params + o_g);
+    d_pads = (Fr*)(d_params + o_pads);
+    d_pt_row = (Fr*)(d_params + o_prow);
+    Fr* d_pt_col = (Fr*)(d_params + o_pcol);
+    const Fr* d_single = (const Fr*)(d_params + o_single);
+    d_tabs[0] = (const Fr**)(d_params + o_t0);
+    d_tabs[1] = (const Fr**)(d_params + o_t1);
+    d_tabs[2] = (const Fr**)(d_params + o_t2);
+
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_eq, sizeof(Fr) * std::max<uint64_t>(eq_total, 1), s));
     for (uint32_t b = 0; b < n_sparse; b++) {
         uint32_t lvl = m_row >= b ? m_row - b : 0;
         if (lvl <= npad) {
-            Fr v = fr_from_host(prefix[lvl]);
-            GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_eq + eq_off[b], &v, sizeof(Fr), cudaMemcpyHostToDevice, s));
-            GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
+            GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_eq + eq_off[b], d_single + b, sizeof(Fr), cudaMemcpyDeviceToDevice, s));
         } else if (b == 0) {
             int rc = gkr_eq_build_device(ctx, d_pt_row + npad, lvl - npad, fr_from_host(prefix[npad]), d_eq + eq_off[0]);
             if (rc) return rc;
@@ -688,36 +716,11 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     }
     if (is_vecvec) {
         GKR_CUDA_OK(ctx, cudaMallocAsync(&d_rowcoef, sizeof(Fr) << col, s));
-        Fr* d_pt_col = nullptr;
-        GKR_CUDA_OK(ctx, cudaMallocAsync(&d_pt_col, sizeof(Fr) * std::max<uint32_t>(col, 1), s));
-        std::vector<Fr> p(std::max<uint32_t>(col, 1));
-        for (uint32_t i = 0; i < col; i++) p[i] = fr_from_host(point[i]);
-        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_pt_col, p.data(), sizeof(Fr) * p.size(), cudaMemcpyHostToDevice, s));
-        GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
         int rc = gkr_eq_build_device(ctx, d_pt_col, col, fr_from_host(ONE), d_rowcoef);
-        cudaFreeAsync(d_pt_col, s);
         if (rc) return rc;
         has_col_tail = nrows < ((uint64_t)1 << col);
         col_tail = sub(ONE, host_eq_sum(point.data(), col, nrows));  // row_eq_coefs_tail_sums[row_count]
     }
-
-    // data: pointer arrays + ping-pong slabs sized for round 1 and round 2
-    for (int i = 0; i < 3; i++) GKR_CUDA_OK(ctx, cudaMallocAsync(&d_tabs[i], sizeof(Fr*) * P, s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[0], inputs.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
-    uint64_t sz1 = n_sparse >= 1 ? totals[1] : 0, sz2 = n_sparse >= 2 ? totals[2] : 0;
-    std::vector<const Fr*> p1(P), p2(P);
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[0], sizeof(Fr) * std::max<uint64_t>(sz1 * P, 1), s));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[1], sizeof(Fr) * std::max<uint64_t>(sz2 * P, 1), s));
-    for (int j = 0; j < P; j++) {
-        p1[j] = slab[0] + (size_t)j * sz1;
-        p2[j] = slab[1] + (size_t)j * sz2;
-    }
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[1], p1.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_tabs[2], p2.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
-    h_sets[0] = inputs;
-    h_sets[1] = p1;
-    h_sets[2] = p2;
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));
     cur_set = 0;
     multiplier = ONE;
     slot = gkr_result_slot_acquire(ctx);
@@ -738,7 +741,10 @@ int Deg2SO::bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const 
     }
     Fr** d_outs = nullptr;
     GKR_CUDA_OK(ctx, cudaMallocAsync(&d_outs, sizeof(Fr*) * P, s));
-    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_outs, outs.data(), sizeof(Fr*) * P, cudaMemcpyHostToDevice, s));
+    {
+        int rc = gkr_stage_upload(ctx, d_outs, outs.data(), sizeof(Fr*) * P);
+        if (rc) return rc;
+    }
     VvToDenseArgs a;
     a.in = d_tabs[cur_set];
     a.out = d_outs;
@@ -752,7 +758,6 @@ int Deg2SO::bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const 
     vv_to_dense_kernel<<<grid, 256, 0, s>>>(a);
     ctx->launches++;
     GKR_CUDA_OK(ctx, cudaGetLastError());
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(s));  // `outs` is a host temporary
     cudaFreeAsync(d_outs, s);
     // eq table over the vertical variables scaled by the multiplier of all bound variables (vecvec_eq.rs:176-179)
     std::vector<uint64_t> pt(4 * std::max<uint32_t>(col, 1));

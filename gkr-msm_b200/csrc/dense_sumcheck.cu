@@ -241,13 +241,13 @@ class DenseSO : public gkr_so {
 
     int final_evals(gkr::FrH* out) override {
         if (round_idx != num_vars) return ctx->fail(GKR_ERR_PROTOCOL, "final_evals: can only be called after the last round");
-        Fr* stage = ctx->slots_host[slot].part;  // pinned staging: P async copies, one synchronisation
-        for (int j = 0; j < P; j++) GKR_CUDA_OK(ctx, cudaMemcpyAsync(&stage[j], cur[j], sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-        for (int j = 0; j < P; j++) {
-            out[j] = fr_to_host(stage[j]);
-            if (fast_folds) out[j] = gkr::frh::mul(out[j], unscale_val);
-        }
+        GkrFirsts f;
+        f.n = P;
+        for (int j = 0; j < P; j++) f.p[j] = cur[j];
+        int rc = gkr_fetch_firsts(ctx, slot, f, out);
+        if (rc) return rc;
+        if (fast_folds)
+            for (int j = 0; j < P; j++) out[j] = gkr::frh::mul(out[j], unscale_val);
         return GKR_OK;
     }
 

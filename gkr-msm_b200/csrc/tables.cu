@@ -61,6 +61,39 @@ int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH
     return GKR_OK;
 }
 
+__global__ void fetch_firsts_kernel(const __grid_constant__ GkrFirsts f, RoundOut o) {
+    if (threadIdx.x < f.n) o.part[threadIdx.x] = f.p[threadIdx.x][0];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *(volatile uint32_t*)o.flag = o.seq;
+    }
+}
+int gkr_fetch_firsts(gkr_ctx* ctx, int slot, const GkrFirsts& f, gkr::FrH* out) {
+    RoundOut o = ctx->round_out(slot);
+    fetch_firsts_kernel<<<1, 32, 0, ctx->stream>>>(f, o);
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    return gkr_slot_wait(ctx, slot, 1, f.n, out);
+}
+
+__global__ void fetch_firsts_dev_kernel(const Fr* const* ptrs, int n, RoundOut o) {
+    for (int j = threadIdx.x; j < n; j += blockDim.x) o.part[j] = ptrs[j][0];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        *(volatile uint32_t*)o.flag = o.seq;
+    }
+}
+int gkr_fetch_firsts_dev(gkr_ctx* ctx, int slot, const Fr* const* d_ptrs, int n, gkr::FrH* out) {
+    if (n > GKR_MAX_BLOCKS * GKR_MAX_DEG) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many tables");
+    RoundOut o = ctx->round_out(slot);
+    fetch_firsts_dev_kernel<<<1, 64, 0, ctx->stream>>>(d_ptrs, n, o);
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    return gkr_slot_wait(ctx, slot, 1, n, out);
+}
+
 extern "C" int gkr_version(void) { return 1; }
 
 extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
@@ -114,6 +147,7 @@ extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     {
         std::lock_guard<std::mutex> lk(g_slot_mutex);
         for (size_t i = 0; i < g_pools.size(); i++)
@@ -305,6 +339,29 @@ static int eq_build(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult,
 }
 
 int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out) { return eq_build(ctx, d_point, n, mult, d_out); }
+
+int gkr_stage_upload(gkr_ctx* ctx, void* d_dst, const void* src, size_t n) {
+    if (n == 0) return GKR_OK;
+    const size_t RING = (size_t)16 << 20;
+    if (!ctx->stage_host) {
+        GKR_CUDA_OK(ctx, cudaHostAlloc(&ctx->stage_host, RING, cudaHostAllocDefault));
+        ctx->stage_size = RING;
+        ctx->stage_pos = 0;
+    }
+    if (n > ctx->stage_size / 2) {  // too large for the ring: plain copy, synchronised so that the source may be released
+        GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_dst, src, n, cudaMemcpyHostToDevice, ctx->stream));
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        return GKR_OK;
+    }
+    if (ctx->stage_pos + n > ctx->stage_size) {  // wrap: everything staged so far must have left the ring
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->stage_pos = 0;
+    }
+    std::memcpy(ctx->stage_host + ctx->stage_pos, src, n);
+    GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_dst, ctx->stage_host + ctx->stage_pos, n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stage_pos += (n + 255) & ~(size_t)255;
+    return GKR_OK;
+}
 
 extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, const uint64_t mult[4], gkr_table** out) {
     if (!ctx || !out || (!point && n) || !mult) return GKR_ERR_ARG;
