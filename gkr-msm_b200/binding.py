@@ -112,7 +112,7 @@ def load_library():
         if not os.path.exists(LIB_PATH):
             raise GkrError(GKR_ERR_CUDA, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                                          "(there is no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(os.environ.get("GKR_LIB", LIB_PATH))  # GKR_LIB: an experimental build of the same sources (tools/kernel_lab)
         _sig(_lib)
     return _lib
 

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <ctime>
+#include <memory>
 #include <string>
 #include <vector>
 #include "../../include/gkr_msm_b200.h"
@@ -32,6 +33,8 @@ struct RoundOut {  // kernel-side view of a slot
     unsigned int* ticket;
     uint32_t seq;
 };
+
+struct Deg2Layout;  // deg2.cu: row layout of the most recent ragged sumcheck bundle
 
 struct gkr_ctx {
     int device = 0;
@@ -78,6 +81,7 @@ struct gkr_ctx {
     }
     // pinned staging ring for small parameter uploads (one truly asynchronous H2D copy per object instead of a dozen
     // pageable ones, no synchronisation until the ring wraps)
+    std::shared_ptr<Deg2Layout> deg2_layout;  // reused by consecutive VecVec objects over the same rows
     unsigned char* stage_host = nullptr;
     size_t stage_size = 0, stage_pos = 0;
     int fail(int code, const std::string& msg) {

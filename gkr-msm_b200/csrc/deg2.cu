@@ -15,6 +15,7 @@
 // (1 - sum_{idx < len/2} eq_row[idx]) for the closed-form padding term; the O(1) rest (pad_results, col pad,
 // multiplier, from12) is host arithmetic exactly as in the reference.
 #include <algorithm>
+#include <memory>
 #include "common.cuh"
 #include "gates.cuh"
 #include "host_gates.hpp"
@@ -358,6 +359,80 @@ static void from12(const gkr::FrH& p1, const gkr::FrH& p2, const gkr::FrH& eq1, 
     evals[3] = mul(p3, eq3);
 }
 
+// Row layout of a ragged bundle over ALL of its sparse rounds: lens[k] = row lengths after k folds (they halve and re-pad
+// deterministically, vecvec.rs:432-437), element / pair offsets of every level on the device.  The three sumchecks of one
+// bintree layer run over the same row structure, and the rows of layer i+1 (vecvec_map_split halves every row) are the
+// level-1 rows of layer i -- so one layout, computed and uploaded once, serves every VecVec object of a proof; an object
+// whose rows equal level k of the cached layout uses it from level k on.
+struct Deg2Layout {
+    gkr_ctx* ctx = nullptr;
+    uint32_t nrows = 0;
+    bool ragged = false;
+    std::vector<std::vector<uint32_t>> lens;  // [level][row] element counts (even when ragged)
+    std::vector<uint64_t> totals;             // [level]
+    uint32_t* d_off = nullptr;                // [levels * (nrows + 1)] ELEMENT offsets
+    uint32_t* d_poff = nullptr;               // the same in PAIRS
+    ~Deg2Layout() {
+        if (d_off) cudaFreeAsync(d_off, ctx->stream);  // one allocation: d_poff follows d_off
+    }
+    size_t levels() const { return lens.size(); }
+};
+
+static int deg2_layout_get(gkr_ctx* ctx, const std::vector<uint32_t>& lens0, bool ragged, uint32_t n_levels, std::shared_ptr<Deg2Layout>* out,
+                           uint32_t* base) {
+    std::shared_ptr<Deg2Layout>& cache = ctx->deg2_layout;
+    if (cache && cache->ragged == ragged && cache->nrows == lens0.size()) {
+        for (size_t k = 0; k + n_levels <= cache->levels(); k++)
+            if (cache->lens[k] == lens0) {
+                *out = cache;
+                *base = (uint32_t)k;
+                return GKR_OK;
+            }
+    }
+    auto L = std::make_shared<Deg2Layout>();
+    L->ctx = ctx;
+    L->nrows = (uint32_t)lens0.size();
+    L->ragged = ragged;
+    const uint32_t nrows = L->nrows;
+    L->lens.resize(n_levels);
+    L->totals.assign(n_levels, 0);
+    L->lens[0] = lens0;
+    std::vector<uint32_t> h_off((size_t)2 * n_levels * (nrows + 1));
+    uint32_t* h_poff = h_off.data() + (size_t)n_levels * (nrows + 1);
+    for (uint32_t b = 0; b < n_levels; b++) {
+        if (b > 0) {
+            L->lens[b].resize(nrows);
+            const uint32_t* prev = L->lens[b - 1].data();
+            uint32_t* cur = L->lens[b].data();
+            for (uint32_t r = 0; r < nrows; r++) {
+                uint32_t h = prev[r] / 2;
+                cur[r] = ragged ? ((h + 1) & ~1u) : h;
+            }
+        }
+        const uint32_t* cur = L->lens[b].data();
+        uint32_t* o = h_off.data() + (size_t)b * (nrows + 1);
+        uint32_t* po = h_poff + (size_t)b * (nrows + 1);
+        uint64_t acc = 0;
+        for (uint32_t r = 0; r < nrows; r++) {
+            o[r] = (uint32_t)acc;
+            po[r] = (uint32_t)(acc / 2);
+            acc += cur[r];
+        }
+        if (acc >= ((uint64_t)1 << 32)) return ctx->fail(GKR_ERR_UNSUPPORTED, "more than 2^32 elements per polynomial");
+        o[nrows] = (uint32_t)acc;
+        po[nrows] = (uint32_t)(acc / 2);
+        L->totals[b] = acc;
+    }
+    GKR_CUDA_OK(ctx, cudaMallocAsync(&L->d_off, sizeof(uint32_t) * h_off.size(), ctx->stream));
+    L->d_poff = L->d_off + (size_t)n_levels * (nrows + 1);
+    int rc = gkr_stage_upload(ctx, L->d_off, h_off.data(), sizeof(uint32_t) * h_off.size());
+    if (rc) return rc;
+    if (ragged) cache = L;  // single-row dense objects are trivial: not worth evicting a ragged layout for
+    *out = L;
+    *base = 0;
+    return GKR_OK;
+}
+
 // Shared machinery of the two Deg2 objects: P ragged (or single-row dense) tables, per-round offsets and eq levels.
 class Deg2SO : public gkr_so {
    public:
@@ -372,9 +447,10 @@ class Deg2SO : public gkr_so {
     std::vector<gkr::FrH> row_pads, col_pads;
     gkr::FrH claim_, multiplier, padG, colpadG, col_tail;
     bool has_col_tail = false;
-    // per-round layout
-    std::vector<std::vector<uint32_t>> lens;  // [round][row] element counts (even)
-    std::vector<uint64_t> totals;             // [round] total elements
+    // per-round layout (shared, see Deg2Layout): round b of this object is level layout_base + b
+    std::vector<uint32_t> lens0;              // row lengths at construction
+    std::shared_ptr<Deg2Layout> layout;
+    const uint64_t* totals = nullptr;         // [round] total elements
     uint32_t* d_off = nullptr;                // [(n_sparse + 1) * (nrows + 1)] ELEMENT offsets per round
     uint32_t* d_poff = nullptr;               // same in PAIRS
     // eq levels
@@ -572,30 +648,14 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
             inv_all = mul(inv_all, sub(ONE, point[i]));
         }
     }
-    // per-round row lengths and offsets
-    lens.resize(n_sparse + 1);
-    totals.assign(n_sparse + 1, 0);
-    for (uint32_t b = 0; b <= n_sparse; b++) {
-        if (b > 0) {
-            lens[b].resize(nrows);
-            for (uint32_t r = 0; r < nrows; r++) {
-                uint32_t h = lens[b - 1][r] / 2;
-                lens[b][r] = is_vecvec ? ((h + 1) & ~1u) : h;
-            }
-        }
-        uint64_t tot = 0;
-        for (uint32_t r = 0; r < nrows; r++) tot += lens[b][r];
-        if (tot >= ((uint64_t)1 << 32)) return ctx->fail(GKR_ERR_UNSUPPORTED, "more than 2^32 elements per polynomial");
-        totals[b] = tot;
-    }
-    std::vector<uint32_t> h_off((size_t)(n_sparse + 1) * (nrows + 1)), h_poff(h_off.size());
-    for (uint32_t b = 0; b <= n_sparse; b++) {
-        uint32_t acc = 0;
-        for (uint32_t r = 0; r <= nrows; r++) {
-            h_off[(size_t)b * (nrows + 1) + r] = acc;
-            h_poff[(size_t)b * (nrows + 1) + r] = acc / 2;
-            if (r < nrows) acc += lens[b][r];
-        }
+    // per-round row lengths and offsets: shared with the other objects over the same rows
+    {
+        uint32_t base = 0;
+        int rc = deg2_layout_get(ctx, lens0, is_vecvec, n_sparse + 1, &layout, &base);
+        if (rc) return rc;
+        totals = layout->totals.data() + base;
+        d_off = layout->d_off + (size_t)base * (nrows + 1);
+        d_poff = layout->d_poff + (size_t)base * (nrows + 1);
     }
     // gate program, gammas, pads
     std::vector<Deg2Block> blocks = expand_blocks(gs);
@@ -621,7 +681,7 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     // eq levels.  Row variables: point[col .. n_vars-1); the last one (binding variable of round 0) is excluded.
     m_row = (n_vars - col) - 1;  // == row_logsize - 1
     uint64_t max_len = 0;
-    for (uint32_t r = 0; r < nrows; r++) max_len = std::max<uint64_t>(max_len, lens[0][r]);
+    for (uint32_t r = 0; r < nrows; r++) max_len = std::max<uint64_t>(max_len, lens0[r]);
     uint32_t max_seg_log = log2_ceil_lasso(max_len);
     if (!is_vecvec) max_seg_log = n_vars;  // dense tables span all variables
     // number of leading row variables over which every row is padding (EQPolyPointParts::padded_vars_range)
@@ -670,8 +730,6 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
         if (n) std::memcpy(arena.data() + off, src, n);
         return off;
     };
-    const size_t o_off = put(h_off.data(), sizeof(uint32_t) * h_off.size());
-    const size_t o_poff = put(h_poff.data(), sizeof(uint32_t) * h_poff.size());
     const size_t o_blocks = put(blocks.data(), sizeof(Deg2Block) * blocks.size());
     const size_t o_g = put(g.data(), sizeof(Fr) * g.size());
     const size_t o_pads = put(pads.data(), sizeof(Fr) * pads.size());
@@ -686,8 +744,6 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
         int rc = gkr_stage_upload(ctx, d_params, arena.data(), arena.size());
         if (rc) return rc;
     }
-    d_off = (uint32_t*)(d_params + o_off);
-    d_poff = (uint32_t*)(d_params + o_poff);
     d_blocks = (Deg2Block*)(d_params + o_blocks);
     d_gammas = (Fr*)(d_params + o_g);
     d_pads = (Fr*)(d_params + o_pads);
@@ -818,8 +874,7 @@ extern "C" int gkr_so_create_deg2_dense(gkr_ctx* ctx, const int* part_gate, cons
     so->claim_ = frh_from_limbs(claim);
     so->row_pads.assign(n_polys, gkr::frh::ZERO);
     so->col_pads.assign(n_polys, gkr::frh::ZERO);
-    so->lens.resize(1);
-    so->lens[0].assign(1, (uint32_t)((uint64_t)1 << num_vars));
+    so->lens0.assign(1, (uint32_t)((uint64_t)1 << num_vars));
     std::vector<const Fr*> in(n_polys);
     for (uint32_t j = 0; j < n_polys; j++) in[j] = tables[j]->d;
     rc = so->setup(in);
@@ -874,8 +929,7 @@ extern "C" int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* con
         so->col_pads[j] = polys[j]->col_pad;
         in[j] = polys[j]->d;
     }
-    so->lens.resize(1);
-    so->lens[0] = p0->row_len;
+    so->lens0 = p0->row_len;
     rc = so->setup(in);
     if (rc) { delete so; return rc; }
     *out = so;

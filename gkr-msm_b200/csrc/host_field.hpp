@@ -134,14 +134,30 @@ static inline void to_bytes_le(const FrH& a, uint8_t out[32]) {
     std::memcpy(out, c.v, 32);
 }
 
-// F::from_le_bytes_mod_order for inputs of at most 64 bytes (src/cleanup/proof_transcript.rs:33-41)
+// F::from_le_bytes_mod_order for inputs of at most 64 bytes (src/cleanup/proof_transcript.rs:33-41): the value is
+// lo + hi 2^256 with 256-bit halves; each half is brought below r by at most two subtractions (2^256 < 3 r) and into
+// Montgomery form by one multiplication with R^2 (two for the high half).
 static inline FrH from_le_bytes_mod_order(const uint8_t* b, size_t n) {
-    // Horner over bytes from the top: acc = acc*256 + byte.
-    FrH acc = ZERO;
-    FrH c256 = from_u64(256);
-    for (size_t i = n; i-- > 0;) {
-        acc = mul(acc, c256);
-        acc = add(acc, from_u64(b[i]));
+    uint8_t buf[64] = {0};
+    std::memcpy(buf, b, n > 64 ? 64 : n);
+    FrH lo, hi;
+    std::memcpy(lo.v, buf, 32);
+    std::memcpy(hi.v, buf + 32, 32);
+    auto reduce = [](FrH& a) {
+        while (geq_mod(a.v)) {
+            unsigned __int128 br = 0;
+            for (int i = 0; i < 4; i++) {
+                unsigned __int128 d = (unsigned __int128)a.v[i] - MOD[i] - (uint64_t)br;
+                a.v[i] = (uint64_t)d;
+                br = (d >> 64) & 1;
+            }
+        }
+    };
+    reduce(lo);
+    FrH acc = mul(lo, R2);
+    if (n > 32) {
+        reduce(hi);
+        acc = add(acc, mul(mul(hi, R2), R2));
     }
     return acc;
 }
@@ -165,41 +181,54 @@ static inline const FrH* lagrange_inv_denominators(int n) {
     return cache[n];
 }
 
-// value of the unique polynomial of degree < n through (i, evals[i]), i = 0..n-1, at x  (Lagrange)
-static inline FrH interpolate_eval(const FrH* evals, int n, const FrH& x) {
-    const FrH* inv_den = lagrange_inv_denominators(n);
-    FrH res = ZERO;
-    for (int i = 0; i < n; i++) {
-        FrH num = ONE;
-        for (int j = 0; j < n; j++) {
-            if (j == i) continue;
-            num = mul(num, sub(x, from_u64((uint64_t)j)));
+// Lagrange basis polynomials of the nodes 0..n-1 in coefficient form, computed once per n (n <= 8):
+// basis[i][k] = coefficient of X^k in prod_{j != i} (X - j) / prod_{j != i} (i - j)
+static inline const FrH (*lagrange_basis_coeffs(int n))[8] {
+    static FrH cache[9][8][8];
+    static bool ready[9] = {false, false, false, false, false, false, false, false, false};
+    if (!ready[n]) {
+        const FrH* inv_den = lagrange_inv_denominators(n);
+        for (int i = 0; i < n; i++) {
+            std::vector<FrH> num(1, ONE);
+            for (int j = 0; j < n; j++) {
+                if (j == i) continue;
+                std::vector<FrH> nw(num.size() + 1, ZERO);
+                FrH fj = from_u64((uint64_t)j);
+                for (size_t k = 0; k < num.size(); k++) {
+                    nw[k] = sub(nw[k], mul(fj, num[k]));
+                    nw[k + 1] = add(nw[k + 1], num[k]);
+                }
+                num.swap(nw);
+            }
+            for (int k = 0; k < n; k++) cache[n][i][k] = mul(num[k], inv_den[i]);
         }
-        res = add(res, mul(evals[i], mul(num, inv_den[i])));
+        ready[n] = true;
     }
-    return res;
+    return cache[n];
 }
 
-// coefficients (low -> high) of that polynomial: UniPoly::from_evals(..).as_vec()
-static inline std::vector<FrH> interpolate_coeffs(const FrH* evals, int n) {
-    const FrH* inv_den = lagrange_inv_denominators(n);
-    std::vector<FrH> coeffs(n, ZERO);
-    for (int i = 0; i < n; i++) {
-        std::vector<FrH> num(1, ONE);
-        for (int j = 0; j < n; j++) {
-            if (j == i) continue;
-            std::vector<FrH> nw(num.size() + 1, ZERO);
-            FrH fj = from_u64((uint64_t)j);
-            for (size_t k = 0; k < num.size(); k++) {
-                nw[k] = sub(nw[k], mul(fj, num[k]));
-                nw[k + 1] = add(nw[k + 1], num[k]);
-            }
-            num.swap(nw);
-        }
-        FrH s = mul(evals[i], inv_den[i]);
-        for (size_t k = 0; k < num.size(); k++) coeffs[k] = add(coeffs[k], mul(num[k], s));
+// coefficients (low -> high) of the unique polynomial of degree < n through (i, evals[i]): UniPoly::from_evals(..).as_vec()
+static inline void interpolate_coeffs_into(const FrH* evals, int n, FrH* coeffs) {
+    const FrH(*basis)[8] = lagrange_basis_coeffs(n);
+    for (int k = 0; k < n; k++) {
+        FrH c = ZERO;
+        for (int i = 0; i < n; i++) c = add(c, mul(evals[i], basis[i][k]));
+        coeffs[k] = c;
     }
+}
+static inline std::vector<FrH> interpolate_coeffs(const FrH* evals, int n) {
+    std::vector<FrH> coeffs(n, ZERO);
+    interpolate_coeffs_into(evals, n, coeffs.data());
     return coeffs;
+}
+
+// value of that polynomial at x
+static inline FrH interpolate_eval(const FrH* evals, int n, const FrH& x) {
+    FrH c[8];
+    interpolate_coeffs_into(evals, n, c);
+    FrH ret = ZERO;
+    for (int i = n; i-- > 0;) ret = add(mul(ret, x), c[i]);
+    return ret;
 }
 
 static inline FrH evaluate_univar(const std::vector<FrH>& coeffs, const FrH& x) {  // sumcheck.rs:33-44

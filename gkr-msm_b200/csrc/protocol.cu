@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdlib>
+#include <map>
 #include <memory>
 #include "common.cuh"
 #include "host_g1.hpp"
@@ -65,6 +66,40 @@ struct Span {
             if (sync) cudaStreamSynchronize(ctx->stream);
             fprintf(stderr, "  [gkr_run_pippenger] %9.2f ms  %s\n", (gkr_now_ns() - t0) / 1e6, name);
         }
+    }
+};
+
+// flat accumulators next to the span tree: host time per sumcheck kind, split into object construction and rounds
+struct TraceAcc {
+    struct Row {
+        uint64_t ns = 0, calls = 0, rounds = 0;
+    };
+    static std::map<std::string, Row>& rows() {
+        static std::map<std::string, Row> r;
+        return r;
+    }
+    static bool on() {
+        static const bool v = getenv("GKR_TRACE") != nullptr;
+        return v;
+    }
+    const char* name;
+    uint64_t t0 = 0, rounds;
+    TraceAcc(const char* n, uint64_t nr = 0) : name(n), rounds(nr) {
+        if (on()) t0 = gkr_now_ns();
+    }
+    ~TraceAcc() {
+        if (!on()) return;
+        Row& r = rows()[name];
+        r.ns += gkr_now_ns() - t0;
+        r.calls++;
+        r.rounds += rounds;
+    }
+    static void dump() {
+        if (!on()) return;
+        for (auto& kv : rows())
+            fprintf(stderr, "  [gkr_run_pippenger acc] %9.2f ms  %6llu calls %6llu rounds  %s\n", kv.second.ns / 1e6, (unsigned long long)kv.second.calls,
+                    (unsigned long long)kv.second.rounds, kv.first.c_str());
+        rows().clear();
     }
 };
 
@@ -345,11 +380,17 @@ struct DenseDeg2Sumcheck : Layer {  // dense_eq.rs:192-221
         uint64_t cl[4];
         frh_to_limbs(claim, cl);
         gkr_so* so = nullptr;
-        ck(gkr_so_create_deg2_dense(d.ctx, pg.data(), pr.data(), (uint32_t)pg.size(), in.data(), (uint32_t)in.size(), limbs_of(gp).data(), cl,
-                                    limbs_of(claims.point).data(), (uint32_t)claims.point.size(), &so));
+        {
+            TraceAcc ta("deg2 dense: create");
+            ck(gkr_so_create_deg2_dense(d.ctx, pg.data(), pr.data(), (uint32_t)pg.size(), in.data(), (uint32_t)in.size(), limbs_of(gp).data(), cl,
+                                        limbs_of(claims.point).data(), (uint32_t)claims.point.size(), &so));
+        }
         SoH guard(so);
         Claims out;
-        d.sumcheck_prove(so, num_vars, &out.point, &out.evs);
+        {
+            TraceAcc ta("deg2 dense: rounds", num_vars);
+            d.sumcheck_prove(so, num_vars, &out.point, &out.evs);
+        }
         d.tr->write_scalars(out.evs.data(), out.evs.size());
         return out;
     }
@@ -370,11 +411,17 @@ struct VecVecDeg2Sumcheck : Layer {  // vecvec_eq.rs:418-450
         uint64_t cl[4];
         frh_to_limbs(claim, cl);
         gkr_so* so = nullptr;
-        ck(gkr_so_create_deg2_vecvec(d.ctx, gate.gid, in.data(), (uint32_t)in.size(), limbs_of(gp).data(), cl, limbs_of(claims.point).data(),
-                                     (uint32_t)claims.point.size(), nvv, &so));
+        {
+            TraceAcc ta("deg2 vecvec: create");
+            ck(gkr_so_create_deg2_vecvec(d.ctx, gate.gid, in.data(), (uint32_t)in.size(), limbs_of(gp).data(), cl, limbs_of(claims.point).data(),
+                                         (uint32_t)claims.point.size(), nvv, &so));
+        }
         SoH guard(so);
         Claims out;
-        d.sumcheck_prove(so, num_vars, &out.point, &out.evs);
+        {
+            TraceAcc ta("deg2 vecvec: rounds (sparse + dense tail)", num_vars);
+            d.sumcheck_prove(so, num_vars, &out.point, &out.evs);
+        }
         out.evs.pop_back();  // poly_evs.pop(): the eq evaluation is not sent (vecvec_eq.rs:445)
         d.tr->write_scalars(out.evs.data(), out.evs.size());
         return out;
@@ -693,8 +740,16 @@ Claims dense_eq_prove(Dev& d, const Gate& gate, uint32_t num_vars, const Claims&
         return out;
     }
     std::vector<Tab> keep;
-    SoH so(dense_eq_so(d, gate, advice, claims.point, claims.evs, gamma, &keep));
-    d.sumcheck_prove(so.h, num_vars, &out.point, &out.evs);
+    gkr_so* raw = nullptr;
+    {
+        TraceAcc ta("dense eq: create");
+        raw = dense_eq_so(d, gate, advice, claims.point, claims.evs, gamma, &keep);
+    }
+    SoH so(raw);
+    {
+        TraceAcc ta("dense eq: rounds", num_vars);
+        d.sumcheck_prove(so.h, num_vars, &out.point, &out.evs);
+    }
     out.evs.pop_back();
     d.tr->write_scalars(out.evs.data(), out.evs.size());
     return out;
@@ -1104,6 +1159,7 @@ extern "C" int gkr_run_pippenger(gkr_ctx* ctx, gkr_transcript* transcript, const
             std::memcpy(pair_xy, pair.first.data(), 96);
             std::memcpy(pair_xy + 12, pair.second.data(), 96);
         }
+        TraceAcc::dump();
         return GKR_OK;
     } catch (const Fail& f) {
         return f.code;

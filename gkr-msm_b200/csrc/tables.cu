@@ -146,6 +146,7 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
 extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    ctx->deg2_layout.reset();  // frees its device arrays on the stream
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     {

@@ -22,16 +22,52 @@ static inline void keccak_f1600(uint64_t st[25]) {
         0x0000000080008009ULL, 0x000000008000000aULL, 0x000000008000808bULL, 0x800000000000008bULL, 0x8000000000008089ULL,
         0x8000000000008003ULL, 0x8000000000008002ULL, 0x8000000000000080ULL, 0x000000000000800aULL, 0x800000008000000aULL,
         0x8000000080008081ULL, 0x8000000000008080ULL, 0x0000000080000001ULL, 0x8000000080008008ULL};
-    static const int ROT[5][5] = {{0, 36, 3, 41, 18}, {1, 44, 10, 45, 2}, {62, 6, 43, 15, 61}, {28, 55, 25, 21, 56}, {27, 20, 39, 8, 14}};
+    // fully unrolled by hand (nvcc's front end drops GCC unroll pragmas): theta, rho+pi along the 24-cycle of pi, chi, iota
     for (int rnd = 0; rnd < 24; rnd++) {
-        uint64_t c[5], d[5], b[25];
-        for (int x = 0; x < 5; x++) c[x] = st[x] ^ st[x + 5] ^ st[x + 10] ^ st[x + 15] ^ st[x + 20];
-        for (int x = 0; x < 5; x++) d[x] = c[(x + 4) % 5] ^ rotl64(c[(x + 1) % 5], 1);
-        for (int i = 0; i < 25; i++) st[i] ^= d[i % 5];
-        for (int x = 0; x < 5; x++)
-            for (int y = 0; y < 5; y++) b[y + 5 * ((2 * x + 3 * y) % 5)] = rotl64(st[x + 5 * y], ROT[x][y]);
-        for (int x = 0; x < 5; x++)
-            for (int y = 0; y < 5; y++) st[x + 5 * y] = b[x + 5 * y] ^ ((~b[(x + 1) % 5 + 5 * y]) & b[(x + 2) % 5 + 5 * y]);
+        uint64_t c0 = st[0] ^ st[5] ^ st[10] ^ st[15] ^ st[20], c1 = st[1] ^ st[6] ^ st[11] ^ st[16] ^ st[21];
+        uint64_t c2 = st[2] ^ st[7] ^ st[12] ^ st[17] ^ st[22], c3 = st[3] ^ st[8] ^ st[13] ^ st[18] ^ st[23];
+        uint64_t c4 = st[4] ^ st[9] ^ st[14] ^ st[19] ^ st[24];
+        const uint64_t d0 = c4 ^ rotl64(c1, 1), d1 = c0 ^ rotl64(c2, 1), d2 = c1 ^ rotl64(c3, 1), d3 = c2 ^ rotl64(c4, 1), d4 = c3 ^ rotl64(c0, 1);
+        st[0] ^= d0; st[1] ^= d1; st[2] ^= d2; st[3] ^= d3; st[4] ^= d4;
+        st[5] ^= d0; st[6] ^= d1; st[7] ^= d2; st[8] ^= d3; st[9] ^= d4;
+        st[10] ^= d0; st[11] ^= d1; st[12] ^= d2; st[13] ^= d3; st[14] ^= d4;
+        st[15] ^= d0; st[16] ^= d1; st[17] ^= d2; st[18] ^= d3; st[19] ^= d4;
+        st[20] ^= d0; st[21] ^= d1; st[22] ^= d2; st[23] ^= d3; st[24] ^= d4;
+        uint64_t t = st[1], b0;
+        b0 = st[10]; st[10] = rotl64(t, 1); t = b0;
+        b0 = st[7]; st[7] = rotl64(t, 3); t = b0;
+        b0 = st[11]; st[11] = rotl64(t, 6); t = b0;
+        b0 = st[17]; st[17] = rotl64(t, 10); t = b0;
+        b0 = st[18]; st[18] = rotl64(t, 15); t = b0;
+        b0 = st[3]; st[3] = rotl64(t, 21); t = b0;
+        b0 = st[5]; st[5] = rotl64(t, 28); t = b0;
+        b0 = st[16]; st[16] = rotl64(t, 36); t = b0;
+        b0 = st[8]; st[8] = rotl64(t, 45); t = b0;
+        b0 = st[21]; st[21] = rotl64(t, 55); t = b0;
+        b0 = st[24]; st[24] = rotl64(t, 2); t = b0;
+        b0 = st[4]; st[4] = rotl64(t, 14); t = b0;
+        b0 = st[15]; st[15] = rotl64(t, 27); t = b0;
+        b0 = st[23]; st[23] = rotl64(t, 41); t = b0;
+        b0 = st[19]; st[19] = rotl64(t, 56); t = b0;
+        b0 = st[13]; st[13] = rotl64(t, 8); t = b0;
+        b0 = st[12]; st[12] = rotl64(t, 25); t = b0;
+        b0 = st[2]; st[2] = rotl64(t, 43); t = b0;
+        b0 = st[20]; st[20] = rotl64(t, 62); t = b0;
+        b0 = st[14]; st[14] = rotl64(t, 18); t = b0;
+        b0 = st[22]; st[22] = rotl64(t, 39); t = b0;
+        b0 = st[9]; st[9] = rotl64(t, 61); t = b0;
+        b0 = st[6]; st[6] = rotl64(t, 20); t = b0;
+        b0 = st[1]; st[1] = rotl64(t, 44); t = b0;
+        c0 = st[0]; c1 = st[1]; c2 = st[2]; c3 = st[3]; c4 = st[4];
+        st[0] = c0 ^ (~c1 & c2); st[1] = c1 ^ (~c2 & c3); st[2] = c2 ^ (~c3 & c4); st[3] = c3 ^ (~c4 & c0); st[4] = c4 ^ (~c0 & c1);
+        c0 = st[5]; c1 = st[6]; c2 = st[7]; c3 = st[8]; c4 = st[9];
+        st[5] = c0 ^ (~c1 & c2); st[6] = c1 ^ (~c2 & c3); st[7] = c2 ^ (~c3 & c4); st[8] = c3 ^ (~c4 & c0); st[9] = c4 ^ (~c0 & c1);
+        c0 = st[10]; c1 = st[11]; c2 = st[12]; c3 = st[13]; c4 = st[14];
+        st[10] = c0 ^ (~c1 & c2); st[11] = c1 ^ (~c2 & c3); st[12] = c2 ^ (~c3 & c4); st[13] = c3 ^ (~c4 & c0); st[14] = c4 ^ (~c0 & c1);
+        c0 = st[15]; c1 = st[16]; c2 = st[17]; c3 = st[18]; c4 = st[19];
+        st[15] = c0 ^ (~c1 & c2); st[16] = c1 ^ (~c2 & c3); st[17] = c2 ^ (~c3 & c4); st[18] = c3 ^ (~c4 & c0); st[19] = c4 ^ (~c0 & c1);
+        c0 = st[20]; c1 = st[21]; c2 = st[22]; c3 = st[23]; c4 = st[24];
+        st[20] = c0 ^ (~c1 & c2); st[21] = c1 ^ (~c2 & c3); st[22] = c2 ^ (~c3 & c4); st[23] = c3 ^ (~c4 & c0); st[24] = c4 ^ (~c0 & c1);
         st[0] ^= RC[rnd];
     }
 }
@@ -132,9 +168,15 @@ class ProofTranscript2 {
     }
     void raw_challenge(uint8_t* out, size_t n) { merlin.challenge_bytes(nullptr, 0, out, n); }
     void write_scalars(const FrH* v, size_t n) {  // ark-serialize compressed Fr: 32 B LE canonical value
-        std::vector<uint8_t> buf(32 * n);
-        for (size_t i = 0; i < n; i++) frh::to_bytes_le(v[i], buf.data() + 32 * i);
-        write_raw_msg(buf.data(), buf.size());
+        uint8_t small[32 * 8];
+        std::vector<uint8_t> big;
+        uint8_t* buf = small;
+        if (n > 8) {
+            big.resize(32 * n);
+            buf = big.data();
+        }
+        for (size_t i = 0; i < n; i++) frh::to_bytes_le(v[i], buf + 32 * i);
+        write_raw_msg(buf, 32 * n);
     }
     FrH challenge(uint32_t bitsize) {  // F::from_le_bytes_mod_order(raw_challenge((bits+7)/8))
         uint8_t buf[64];

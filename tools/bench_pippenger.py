@@ -57,6 +57,7 @@ def run(args, ctx=None):
         tr = g.Transcript(b"fgstglsp")
         l0 = ctx.launches
         ctx.sync()
+        ctx.host_stats(True)
         t0 = time.perf_counter()
         if args.python_host:
             dense_output, claims, pair = DPP.run_pippenger(ctx, tr, points_xy, coefs, cfg, r, key)
@@ -66,6 +67,7 @@ def run(args, ctx=None):
         times.append(time.perf_counter() - t0)
         launches = ctx.launches - l0
         proof_len = len(tr.proof())
+        hs = ctx.host_stats(True)
     if args.profile:
         PR.PROFILE = {}
         ctx.host_stats(True)
@@ -86,7 +88,8 @@ def run(args, ctx=None):
         "bench": "run_pippenger (witness + commit + prove)", "host": "python" if args.python_host else "c++ (gkr_run_pippenger)", "x_logsize": xl, "d_logsize": dl, "nbits": nbits, "clm": clm,
         "y_size": cfg["y_size"], "incidences": cfg["y_size"] << xl, "prove_ms_best": best * 1e3, "prove_ms_all": [t * 1e3 for t in times],
         "proof_bytes": proof_len, "gpu_launches": launches, "input_generation_s": t_inputs, "srs_setup_s": t_setup,
-        "srs_points": 2 * (1 << nv) - 1})
+        "srs_points": 2 * (1 << nv) - 1,
+        "round_waits": hs[2], "round_wait_ms": hs[1] / 1e6, "round_launch_call_ms": hs[0] / 1e6})
 
 
 def main():
