@@ -43,6 +43,9 @@ struct gkr_ctx {
     std::string err;
     uint64_t launches = 0;
     uint64_t ns_launch = 0, ns_wait = 0, n_waits = 0;  // host-side latency accounting (gkr_ctx_host_stats)
+    // GKR_TRACE: waits by object kind (0 dense, 1 Deg2 dense, 2 Deg2 ragged) and log2 of the pairs of the round
+    int wait_kind = 0, wait_log = 0;
+    uint64_t wait_hist_ns[3][40] = {{0}}, wait_hist_n[3][40] = {{0}};
     bool no_fast_fold = false;      // test hook (GKR_NO_FAST_FOLD=1): always fold with the full Montgomery product
     Fr* partials = nullptr;         // [GKR_MAX_BLOCKS * GKR_MAX_DEG] device scratch (device-side two-stage reductions)
     unsigned int* ticket = nullptr; // device counter for the last-block pattern

@@ -19,173 +19,17 @@
 #include "common.cuh"
 #include "gates.cuh"
 #include "host_gates.hpp"
+#include "deg2_kernel.cuh"
 #include "so.hpp"
+
+#define GKR_DEG2_COMPACT_MAX_PAIRS 32768  // pairs x gate blocks up to which a round runs the compact kernel
 
 int gkr_result_slot_acquire(gkr_ctx* ctx);
 void gkr_result_slot_release(gkr_ctx* ctx, int slot);
 int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out);
 
-struct Deg2Block {
-    int gate;
-    int in_idx[6];
-    int out_off;
-    int own_mask;  // bit k: this block writes the folded table in_idx[k] (each table has exactly one owner)
-};
-
-// One round of a Deg2 object: FOLD the previous round's tables with the challenge (unless this is round 0), write the
-// new tables, evaluate the gate stack at 1 and "2" on the fresh pairs, weight by eq, and add the closed-form padding sum.
-struct Deg2RoundArgs {
-    const Fr* const* in;       // [P] round b-1 tables when fold != 0, else the current tables
-    Fr* const* out;            // [P] round b tables (written when fold != 0)
-    const Deg2Block* blocks;   // [gridDim.y]
-    const Fr* gammas;          // [n_outs], gammas[0] == 1
-    const uint32_t* off_old;   // element offsets of round b-1 [nrows + 1] (fold only)
-    const uint32_t* pair_off;  // PAIR offsets of round b [nrows + 1]; nullptr: one dense row
-    uint32_t nrows;
-    const Fr* eq;              // eq table of round b (row-local part)
-    const Fr* rowcoef;         // [nrows] or nullptr
-    uint64_t n_pairs;          // pairs of round b
-    int fold;
-    Fr t;
-    const Fr* row_pads;        // [P]
-    const Fr* pt;              // row variables of this round's eq table, for the padding term
-    uint32_t n_pt;
-    int do_pad;                // ragged objects only
-    RoundOut o;                // 3 accumulators: S1, S2, T
-};
-
-template <int G>
-__device__ __forceinline__ void deg2_block_round(const Deg2RoundArgs& A, const Deg2Block& blk, uint64_t q, uint32_t row, uint64_t idx,
-                                                 const Fr& w, Fr* acc) {
-    constexpr int NI = MoGate<G>::N_INS, NO = MoGate<G>::N_OUTS;
-    Fr a1[NI], a2[NI];
-    uint64_t old_base = 0, half_old = 0;
-    if (A.fold) {
-        if (A.pair_off) {
-            old_base = A.off_old[row];
-            half_old = (A.off_old[row + 1] - old_base) >> 1;
-        } else {
-            half_old = 2 * A.n_pairs;  // dense: the old table has 4 * n_pairs entries
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < NI; j++) {
-        const int tj = blk.in_idx[j];
-        Fr p0, p1;
-        if (A.fold) {
-            const Fr* src = A.in[tj] + old_base;
-            const uint64_t i0 = 2 * idx, i1 = 2 * idx + 1;  // positions of the two new elements inside the row
-            if (i0 < half_old) {
-                Fr e0 = src[2 * i0], e1 = src[2 * i0 + 1];
-                p0 = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
-            } else {
-                p0 = A.row_pads[tj];
-            }
-            if (i1 < half_old) {
-                Fr e0 = src[2 * i1], e1 = src[2 * i1 + 1];
-                p1 = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
-            } else {
-                p1 = A.row_pads[tj];  // odd half re-padded with row_pad (vecvec.rs:432-436)
-            }
-            if ((blk.own_mask >> j) & 1) {
-                Fr* dst = A.out[tj] + 2 * q;
-                dst[0] = p0;
-                dst[1] = p1;
-            }
-        } else {
-            const Fr* src = A.in[tj] + 2 * q;
-            p0 = src[0];
-            p1 = src[1];
-        }
-        a1[j] = p1;
-        a2[j] = fr_sub(fr_dbl(p1), p0);  // the "2-1" value 2 p(1) - p(0) of make_21, never stored
-    }
-    Fr o1[NO], o2[NO];
-    MoGate<G>::eval(a1, o1);
-    MoGate<G>::eval(a2, o2);
-    Fr g1, g2;
-    if (blk.out_off == 0) {
-        g1 = o1[0];
-        g2 = o2[0];
-    } else {
-        Fr gm = A.gammas[blk.out_off];
-        g1 = fr_mul(o1[0], gm);
-        g2 = fr_mul(o2[0], gm);
-    }
-#pragma unroll
-    for (int o = 1; o < NO; o++) {
-        Fr gm = A.gammas[blk.out_off + o];
-        g1 = fr_add(g1, fr_mul(o1[o], gm));
-        g2 = fr_add(g2, fr_mul(o2[o], gm));
-    }
-    acc[0] = fr_add(acc[0], fr_mul(g1, w));
-    acc[1] = fr_add(acc[1], fr_mul(g2, w));
-}
-
-// grid = (x: pairs, y: gate blocks).  All blocks reduce into the same three sums.
-__global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __grid_constant__ Deg2RoundArgs A) {
-    __shared__ Fr smem[3 * (GKR_REDUCE_THREADS / 32)];
-    Fr acc[3] = {fr_zero(), fr_zero(), fr_zero()};
-    const Deg2Block blk = A.blocks[blockIdx.y];
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; q < A.n_pairs; q += stride) {
-        Fr w;
-        uint32_t row = 0;
-        uint64_t idx = q;
-        if (A.pair_off) {
-            uint32_t lo = 0, hi = A.nrows;  // largest r with pair_off[r] <= q (empty rows repeat an offset)
-            while (hi - lo > 1) {
-                uint32_t mid = (lo + hi) >> 1;
-                if ((uint64_t)A.pair_off[mid] <= q) lo = mid; else hi = mid;
-            }
-            row = lo;
-            idx = q - A.pair_off[lo];
-            w = fr_mul(A.eq[idx], A.rowcoef[lo]);
-        } else {
-            w = A.eq[q];
-        }
-        switch (blk.gate) {
-            case GATE_AFF_L1: deg2_block_round<GATE_AFF_L1>(A, blk, q, row, idx, w, acc); break;
-            case GATE_AFF_L2: deg2_block_round<GATE_AFF_L2>(A, blk, q, row, idx, w, acc); break;
-            case GATE_AFF_L3: deg2_block_round<GATE_AFF_L3>(A, blk, q, row, idx, w, acc); break;
-            case GATE_PRJ_L1: deg2_block_round<GATE_PRJ_L1>(A, blk, q, row, idx, w, acc); break;
-            case GATE_PRJ_L2: deg2_block_round<GATE_PRJ_L2>(A, blk, q, row, idx, w, acc); break;
-            case GATE_PRJ_L3: deg2_block_round<GATE_PRJ_L3>(A, blk, q, row, idx, w, acc); break;
-            case GATE_BITCHECK: deg2_block_round<GATE_BITCHECK>(A, blk, q, row, idx, w, acc); break;
-            case GATE_LOGUP_LAYER: deg2_block_round<GATE_LOGUP_LAYER>(A, blk, q, row, idx, w, acc); break;
-            case GATE_ADD_INVERSES: deg2_block_round<GATE_ADD_INVERSES>(A, blk, q, row, idx, w, acc); break;
-            default: break;
-        }
-    }
-    // T = sum_rows rowcoef[row] * (1 - eq_sum(pt, len_row / 2)): closed form of src/utils.rs:265-291 per row
-    // (vecvec_eq.rs:344-369), computed once by the y == 0 slice of the grid
-    if (A.do_pad && blockIdx.y == 0) {
-        const Fr one = fr_one();
-        for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.nrows; r += stride) {
-            uint64_t k = A.pair_off[r + 1] - A.pair_off[r];
-            Fr s;
-            if (k >= ((uint64_t)1 << A.n_pt)) {
-                s = one;
-            } else {
-                Fr mult = one;
-                s = fr_zero();
-                for (uint32_t i = 0; i < A.n_pt; i++) {
-                    uint32_t bit = (uint32_t)(k >> (A.n_pt - i - 1)) & 1u;
-                    Fr p = A.pt[i];
-                    if (bit) {
-                        Fr nm = fr_mul(mult, p);
-                        s = fr_add(s, fr_sub(mult, nm));
-                        mult = nm;
-                    } else {
-                        mult = fr_mul(mult, fr_sub(one, p));
-                    }
-                }
-            }
-            acc[2] = fr_add(acc[2], fr_mul(A.rowcoef[r], fr_sub(one, s)));
-        }
-    }
-    grid_reduce_to_host<3>(acc, smem, A.o);
-}
+// defined in deg2_compact.cu: the same kernel built with the out-of-line multiplier
+int gkr_launch_deg2_round_compact(const Deg2RoundArgs& a, dim3 grid, unsigned threads, cudaStream_t stream);
 
 // ragged fold (VecVecPolynomial::bind_21): grid.y = table
 struct VvFoldArgs {
@@ -520,14 +364,19 @@ class Deg2SO : public gkr_so {
         a.n_pt = m_row >= b ? m_row - b : 0;
         a.do_pad = is_vecvec ? 1 : 0;
         a.o = ctx->round_out(slot);
-        uint64_t work = std::max<uint64_t>(n_pairs, is_vecvec ? nrows : 1);
+        uint64_t work = std::max<uint64_t>(2 * n_pairs, is_vecvec ? nrows : 1);  // two lanes per pair
         uint64_t want = (work + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
         uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->num_sms * 3, GKR_MAX_BLOCKS) / n_blocks);
         dim3 grid((unsigned)std::max<uint64_t>(1, std::min(want, cap)), (unsigned)n_blocks);
         unsigned threads = GKR_REDUCE_THREADS;
         if (grid.x == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (work + 31) / 32 * 32));
         pending_blocks = grid.x * grid.y;
-        deg2_round_kernel<<<grid, threads, 0, ctx->stream>>>(a);
+        // latency flavour for rounds that fit in about one wave of blocks, throughput flavour above
+        if (n_pairs * (uint64_t)n_blocks <= GKR_DEG2_COMPACT_MAX_PAIRS) {
+            gkr_launch_deg2_round_compact(a, grid, threads, ctx->stream);
+        } else {
+            deg2_inline::deg2_round_kernel<<<grid, threads, 0, ctx->stream>>>(a);
+        }
         ctx->launches++;
         GKR_CUDA_OK(ctx, cudaGetLastError());
         cur_set = dst_set;
@@ -544,6 +393,9 @@ class Deg2SO : public gkr_so {
             if (rc) return rc;
         }
         gkr::FrH r[3];
+        ctx->wait_kind = is_vecvec ? 2 : 1;
+        ctx->wait_log = 0;
+        while (((uint64_t)2 << ctx->wait_log) <= totals[round_idx]) ctx->wait_log++;
         int rcw = gkr_slot_wait(ctx, slot, pending_blocks, 3, r);
         if (rcw) return rcw;
         sums_pending = false;

@@ -136,3 +136,63 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS, MINB) dense_round_kernel(c
     grid_reduce_to_host<NACC>(acc, smem, A.o);
 }
 
+
+// ---- small rounds ----------------------------------------------------------------------------------------------------
+// ~90 % of the rounds of a proof run on tables of at most a few thousand entries, where one launch of the kernel above is
+// bounded by the chain of 2P folds + DEG gate evaluations every thread walks alone (and by streaming that much straight-line
+// code through a cold instruction cache).  This kernel spreads one item over the block instead:
+//   phase A: one thread per (item, table, half): fold (or load) ONE element, store it, park it in shared memory;
+//   phase B: one thread per (item, evaluation node): one gate evaluation from the parked values (warp w = node w + 1).
+// Same arithmetic, same results; the dependent chain per thread drops from 2P folds + DEG gates to ~ceil(2P/4) folds + 1 gate.
+#define GKR_DENSE_SMALL_QB 32        // items per block iteration
+#define GKR_DENSE_SMALL_MAX 4096     // items up to which launch_dense_round picks this kernel
+
+template <class SO, int MODE, bool FAST>
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_small_kernel(const __grid_constant__ DenseRoundArgs A) {
+    constexpr int P = SO::P, DEG = SO::DEG, QB = GKR_DENSE_SMALL_QB;
+    static_assert(DEG * QB <= GKR_REDUCE_THREADS, "one warp per evaluation node");
+    __shared__ Fr smem[DEG * (GKR_REDUCE_THREADS / 32)];
+    __shared__ Fr sv[2 * P][QB];  // [2 * table + half][item]
+    Fr mine = fr_zero();
+    const uint32_t node = threadIdx.x >> 5, quad = threadIdx.x & 31;
+    for (uint64_t base = (uint64_t)blockIdx.x * QB; base < A.n_items; base += (uint64_t)gridDim.x * QB) {
+        for (uint32_t task = threadIdx.x; task < 2 * P * QB; task += GKR_REDUCE_THREADS) {
+            const uint32_t k = task / QB, j = k >> 1, half = k & 1;
+            const uint64_t i = base + (task % QB);
+            if (i < A.n_items) {
+                Fr v;
+                if (MODE == 1) {
+                    const Fr* src = A.in[j] + 4 * i + 2 * half;
+                    const Fr e0 = src[0], e1 = src[1];
+                    if (FAST) v = fr_fold128(e0, fr_sub(e1, e0), A.t128);
+                    else v = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+                    A.out[j][2 * i + half] = v;
+                } else {
+                    v = A.in[j][2 * i + half];
+                }
+                sv[k][task % QB] = v;
+            }
+        }
+        __syncthreads();
+        if (node < DEG && base + quad < A.n_items) {
+            Fr a[P];
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                const Fr lo = sv[2 * j][quad], hi = sv[2 * j + 1][quad];
+                const Fr d = fr_sub(hi, lo);
+                Fr x = hi;  // node 0 evaluates at 1 (args = p[2i+1]), node s at 1 + s (args += difs), sumcheck.rs:295-313
+                if (node >= 1) x = fr_add(x, d);
+                if (node >= 2) x = fr_add(x, d);
+                a[j] = x;
+            }
+            mine = fr_add(mine, SO::evalx(a, A.consts));
+        }
+        __syncthreads();
+    }
+    Fr acc[DEG];
+#pragma unroll
+    for (int s = 0; s < DEG; s++)
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[s].l[k] = (node == (uint32_t)s) ? mine.l[k] : 0u;
+    grid_reduce_to_host<DEG>(acc, smem, A.o);
+}

@@ -67,6 +67,19 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
         GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_kernel<SO, MODE, FAST>, GKR_REDUCE_THREADS, 0));
         blocks_per_sm = std::max(b, 1);
     }
+    if constexpr (MODE != 2) {
+        if (args.n_items <= GKR_DENSE_SMALL_MAX) {  // small round: the block-cooperative kernel
+            unsigned grid = (unsigned)std::max<uint64_t>(1, (args.n_items + GKR_DENSE_SMALL_QB - 1) / GKR_DENSE_SMALL_QB);
+            *n_blocks_out = grid;
+            {
+                GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : GKR_K_DENSE_FOLD_EVAL, args.n_items);
+                dense_small_kernel<SO, MODE, FAST><<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(args);
+            }
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+            return GKR_OK;
+        }
+    }
     uint64_t want = (args.n_items + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
     uint64_t cap = std::min<uint64_t>((uint64_t)ctx->num_sms * blocks_per_sm, GKR_MAX_BLOCKS);
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
@@ -171,6 +184,8 @@ class DenseSO : public gkr_so {
                 });
                 if (rc) return rc;
             }
+            ctx->wait_kind = 0;
+            ctx->wait_log = (int)(num_vars - round_idx - 1);
             int rcw = gkr_slot_wait(ctx, slot, pending_blocks, DEG, evals + 1);
             if (rcw) return rcw;
             if (fast_folds)

@@ -210,6 +210,8 @@ struct SoProd3 {
     __host__ __device__ static constexpr int gamma_shift(int) { return 0; }
     __device__ __forceinline__ static Fr eval(const Fr* a, const GateConsts&) { return fr_mul(fr_mul(a[0], a[1]), a[2]); }
     __device__ __forceinline__ static void mac(FrWide& w, const Fr* a, const GateConsts&) { frw_mac(w, fr_mul(a[0], a[1]), a[2]); }
+    // evalx(): the value mac() accumulates, reduced (same gate constants as mac: the small-round kernel, dense_kernel.cuh)
+    __device__ __forceinline__ static Fr evalx(const Fr* a, const GateConsts& c) { return eval(a, c); }
 };
 
 template <int NARGS>
@@ -227,6 +229,7 @@ struct SoFoldedProd {
 #pragma unroll
         for (int i = 1; i < NARGS; i++) frw_mac(w, fr_mul(a[i], c.g[i]), a[i + NARGS]);
     }
+    __device__ __forceinline__ static Fr evalx(const Fr* a, const GateConsts& c) { return eval(a, c); }
 };
 
 // EqWrapper(GammaWrapper(G, gamma)): last input is the eq table
@@ -244,5 +247,9 @@ struct SoEqGamma {
             frw_mac(w, gamma_eval_scaled<G>(a, c), a[MoGate<G>::N_INS]);
         else
             frw_mac(w, gamma_eval<G>(a, c), a[MoGate<G>::N_INS]);
+    }
+    __device__ __forceinline__ static Fr evalx(const Fr* a, const GateConsts& c) {
+        if (MoGate<G>::HOMOG) return fr_mul(gamma_eval_scaled<G>(a, c), a[MoGate<G>::N_INS]);
+        return fr_mul(gamma_eval<G>(a, c), a[MoGate<G>::N_INS]);
     }
 };

@@ -94,8 +94,17 @@ struct TraceAcc {
         r.calls++;
         r.rounds += rounds;
     }
-    static void dump() {
+    static void dump(gkr_ctx* ctx) {
         if (!on()) return;
+        static const char* kinds[3] = {"dense", "deg2 dense", "deg2 ragged"};
+        for (int k = 0; k < 3; k++)
+            for (int l = 0; l < 40; l++)
+                if (ctx->wait_hist_n[k][l]) {
+                    fprintf(stderr, "  [gkr_run_pippenger wait] %-12s 2^%-2d pairs: %5llu waits %9.2f ms  (%7.1f us each)\n", kinds[k], l,
+                            (unsigned long long)ctx->wait_hist_n[k][l], ctx->wait_hist_ns[k][l] / 1e6,
+                            ctx->wait_hist_ns[k][l] / 1e3 / ctx->wait_hist_n[k][l]);
+                    ctx->wait_hist_n[k][l] = ctx->wait_hist_ns[k][l] = 0;
+                }
         for (auto& kv : rows())
             fprintf(stderr, "  [gkr_run_pippenger acc] %9.2f ms  %6llu calls %6llu rounds  %s\n", kv.second.ns / 1e6, (unsigned long long)kv.second.calls,
                     (unsigned long long)kv.second.rounds, kv.first.c_str());
@@ -1159,7 +1168,7 @@ extern "C" int gkr_run_pippenger(gkr_ctx* ctx, gkr_transcript* transcript, const
             std::memcpy(pair_xy, pair.first.data(), 96);
             std::memcpy(pair_xy + 12, pair.second.data(), 96);
         }
-        TraceAcc::dump();
+        TraceAcc::dump(ctx);
         return GKR_OK;
     } catch (const Fail& f) {
         return f.code;

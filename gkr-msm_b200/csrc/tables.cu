@@ -51,8 +51,11 @@ int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH
         }
     }
     __atomic_thread_fence(__ATOMIC_ACQUIRE);
-    ctx->ns_wait += gkr_now_ns() - t0;
+    const uint64_t dt = gkr_now_ns() - t0;
+    ctx->ns_wait += dt;
     ctx->n_waits++;
+    ctx->wait_hist_ns[ctx->wait_kind % 3][ctx->wait_log % 40] += dt;
+    ctx->wait_hist_n[ctx->wait_kind % 3][ctx->wait_log % 40]++;
     for (int a = 0; a < n_acc; a++) {
         gkr::FrH acc = gkr::frh::ZERO;
         for (uint32_t b = 0; b < n_blocks; b++) acc = gkr::frh::add(acc, fr_to_host(s->part[(size_t)b * n_acc + a]));

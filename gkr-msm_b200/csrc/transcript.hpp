@@ -168,7 +168,7 @@ class ProofTranscript2 {
     }
     void raw_challenge(uint8_t* out, size_t n) { merlin.challenge_bytes(nullptr, 0, out, n); }
     void write_scalars(const FrH* v, size_t n) {  // ark-serialize compressed Fr: 32 B LE canonical value
-        uint8_t small[32 * 8];
+        uint8_t small[32 * 8] = {0};
         std::vector<uint8_t> big;
         uint8_t* buf = small;
         if (n > 8) {
