@@ -882,6 +882,31 @@ def pushforward_bucketize(coefs_u64, y_size: int, d_logsize: int):
     return digits, counter, order, lens
 
 
+def pushforward_bucketize_dev(ctx: "Context", coefs_u64, y_size: int, d_logsize: int):
+    """The same bookkeeping by a stable counting sort on the device (csrc/bucketize.cu).  Returns host copies of
+    (digits[y][n], counter[y][n], padded_order (bucket contents, even-padded with 0xffffffff), lens[y][2^d])."""
+    lib = ctx.lib
+    lib.gkr_pushforward_bucketize_dev.restype = C.c_int
+    lib.gkr_pushforward_bucketize_dev.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _vp]
+    lib.gkr_u32_download.restype = C.c_int
+    lib.gkr_u32_download.argtypes = [_vp, _vp, _vp]
+    lib.gkr_u32_len.restype = C.c_uint64
+    lib.gkr_u32_len.argtypes = [_vp]
+    _poly_sigs(lib)
+    co = np.ascontiguousarray(coefs_u64, dtype=np.uint64).reshape(-1, 4)
+    n = co.shape[0]
+    lens = np.empty((y_size, 1 << d_logsize), np.uint32)
+    hd, hc, ho = _vp(), _vp(), _vp()
+    ctx.check(lib.gkr_pushforward_bucketize_dev(ctx.h, _ptr(co), n, y_size, d_logsize, C.byref(hd), C.byref(hc), C.byref(ho), _ptr(lens)))
+    outs = []
+    for h in (hd, hc, ho):
+        a = np.empty(int(lib.gkr_u32_len(h)), np.uint32)
+        ctx.check(lib.gkr_u32_download(ctx.h, h, _ptr(a)))
+        lib.gkr_u32_free(h)
+        outs.append(a)
+    return outs[0].reshape(y_size, n), outs[1].reshape(y_size, n), outs[2], lens
+
+
 FQ_MONT_ONE = np.array([0x760900000002FFFD, 0xEBF4000BC40C0002, 0x5F48985753C758BA, 0x77CE585370525745, 0x5C071A97A256EC6D,
                         0x15F65EC3FA80E493], dtype=np.uint64)
 

@@ -179,6 +179,20 @@ static inline gkr::FrH fr_to_host(const Fr& a) {
     return r;
 }
 
+// Device memory: the stream-ordered pool (cudaMallocAsync) for everything small, and a per-stream cache of LARGE blocks
+// (>= GKR_BIG_BLOCK) in front of it.  A proof at x = 20 allocates and frees hundreds of 0.1 - 1.5 GB tables and slabs; handing
+// those back to the pool lets it fragment, and the driver then re-maps physical memory to satisfy the next large request --
+// sporadic stalls of hundreds of ms.  Sizes repeat exactly from sumcheck to sumcheck and from proof to proof, so freed large
+// blocks are kept and handed out again (best fit, at most 2x the request); reuse is ordered by the single context stream.
+#define GKR_BIG_BLOCK ((size_t)4 << 20)
+cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s);
+cudaError_t gkr_free_async(void* p, cudaStream_t s);
+void gkr_big_cache_release(cudaStream_t s);  // return every cached block of this stream to the pool
+template <class T>
+static inline cudaError_t gkr_malloc_async(T** p, size_t n, cudaStream_t s) {
+    return gkr_malloc_async_impl((void**)p, n, s);
+}
+
 // copy n bytes of host data to the device through the context's pinned staging ring (asynchronous on ctx->stream; the
 // source may be freed as soon as the call returns)
 int gkr_stage_upload(gkr_ctx* ctx, void* d_dst, const void* src, size_t n);

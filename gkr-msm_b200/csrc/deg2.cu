@@ -217,7 +217,7 @@ struct Deg2Layout {
     uint32_t* d_off = nullptr;                // [levels * (nrows + 1)] ELEMENT offsets
     uint32_t* d_poff = nullptr;               // the same in PAIRS
     ~Deg2Layout() {
-        if (d_off) cudaFreeAsync(d_off, ctx->stream);  // one allocation: d_poff follows d_off
+        if (d_off) gkr_free_async(d_off, ctx->stream);  // one allocation: d_poff follows d_off
     }
     size_t levels() const { return lens.size(); }
 };
@@ -267,7 +267,7 @@ static int deg2_layout_get(gkr_ctx* ctx, const std::vector<uint32_t>& lens0, boo
         po[nrows] = (uint32_t)(acc / 2);
         L->totals[b] = acc;
     }
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&L->d_off, sizeof(uint32_t) * h_off.size(), ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&L->d_off, sizeof(uint32_t) * h_off.size(), ctx->stream));
     L->d_poff = L->d_off + (size_t)n_levels * (nrows + 1);
     int rc = gkr_stage_upload(ctx, L->d_off, h_off.data(), sizeof(uint32_t) * h_off.size());
     if (rc) return rc;
@@ -323,10 +323,10 @@ class Deg2SO : public gkr_so {
         delete dense;
         for (auto* t : dense_tables) gkr_table_free(t);
         cudaStream_t s = ctx->stream;
-        if (d_params) cudaFreeAsync(d_params, s);  // offsets, gate blocks, gammas, pads, points, pointer arrays
-        if (d_eq) cudaFreeAsync(d_eq, s);
-        if (d_rowcoef) cudaFreeAsync(d_rowcoef, s);
-        for (int i = 0; i < 2; i++) if (slab[i]) cudaFreeAsync(slab[i], s);
+        if (d_params) gkr_free_async(d_params, s);  // offsets, gate blocks, gammas, pads, points, pointer arrays
+        if (d_eq) gkr_free_async(d_eq, s);
+        if (d_rowcoef) gkr_free_async(d_rowcoef, s);
+        for (int i = 0; i < 2; i++) if (slab[i]) gkr_free_async(slab[i], s);
         if (slot >= 0) gkr_result_slot_release(ctx, slot);
     }
 
@@ -564,8 +564,8 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     // data: ping-pong slabs sized for round 1 and round 2, pointer arrays
     uint64_t sz1 = n_sparse >= 1 ? totals[1] : 0, sz2 = n_sparse >= 2 ? totals[2] : 0;
     std::vector<const Fr*> p1(P), p2(P);
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[0], sizeof(Fr) * std::max<uint64_t>(sz1 * P, 1), s));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&slab[1], sizeof(Fr) * std::max<uint64_t>(sz2 * P, 1), s));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&slab[0], sizeof(Fr) * std::max<uint64_t>(sz1 * P, 1), s));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&slab[1], sizeof(Fr) * std::max<uint64_t>(sz2 * P, 1), s));
     for (int j = 0; j < P; j++) {
         p1[j] = slab[0] + (size_t)j * sz1;
         p2[j] = slab[1] + (size_t)j * sz2;
@@ -591,7 +591,7 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     const size_t o_t0 = put(inputs.data(), sizeof(Fr*) * P);
     const size_t o_t1 = put(p1.data(), sizeof(Fr*) * P);
     const size_t o_t2 = put(p2.data(), sizeof(Fr*) * P);
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_params, arena.size(), s));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_params, arena.size(), s));
     {
         int rc = gkr_stage_upload(ctx, d_params, arena.data(), arena.size());
         if (rc) return rc;
@@ -606,7 +606,7 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     d_tabs[1] = (const Fr**)(d_params + o_t1);
     d_tabs[2] = (const Fr**)(d_params + o_t2);
 
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_eq, sizeof(Fr) * std::max<uint64_t>(eq_total, 1), s));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_eq, sizeof(Fr) * std::max<uint64_t>(eq_total, 1), s));
     for (uint32_t b = 0; b < n_sparse; b++) {
         uint32_t lvl = m_row >= b ? m_row - b : 0;
         if (lvl <= npad) {
@@ -623,7 +623,7 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
         }
     }
     if (is_vecvec) {
-        GKR_CUDA_OK(ctx, cudaMallocAsync(&d_rowcoef, sizeof(Fr) << col, s));
+        GKR_CUDA_OK(ctx, gkr_malloc_async(&d_rowcoef, sizeof(Fr) << col, s));
         int rc = gkr_eq_build_device(ctx, d_pt_col, col, fr_from_host(ONE), d_rowcoef);
         if (rc) return rc;
         has_col_tail = nrows < ((uint64_t)1 << col);
@@ -648,7 +648,7 @@ int Deg2SO::bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const 
         outs[j] = dense_tables[j]->d;
     }
     Fr** d_outs = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_outs, sizeof(Fr*) * P, s));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_outs, sizeof(Fr*) * P, s));
     {
         int rc = gkr_stage_upload(ctx, d_outs, outs.data(), sizeof(Fr*) * P);
         if (rc) return rc;
@@ -666,7 +666,7 @@ int Deg2SO::bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const 
     vv_to_dense_kernel<<<grid, 256, 0, s>>>(a);
     ctx->launches++;
     GKR_CUDA_OK(ctx, cudaGetLastError());
-    cudaFreeAsync(d_outs, s);
+    gkr_free_async(d_outs, s);
     // eq table over the vertical variables scaled by the multiplier of all bound variables (vecvec_eq.rs:176-179)
     std::vector<uint64_t> pt(4 * std::max<uint32_t>(col, 1));
     for (uint32_t i = 0; i < col; i++) frh_to_limbs(point[i], pt.data() + 4 * i);
@@ -819,7 +819,7 @@ extern "C" int gkr_vecvec_upload(gkr_ctx* ctx, const uint64_t* flat, const uint3
         so += row_len[r];
         dof += v->row_len[r];
     }
-    cudaError_t e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), ctx->stream);
+    cudaError_t e = gkr_malloc_async(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), ctx->stream);
     if (e == cudaSuccess && total) e = cudaMemcpyAsync(v->d, padded.data(), sizeof(Fr) * total, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { delete v; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
@@ -841,6 +841,48 @@ __global__ void vecvec_gather_kernel(Fr* out, const Fr* src, uint64_t src_n, con
         out[i] = v;
     }
 }
+// shared tail of the two gather entries: `d_idx` is the PADDED gather index on the device (0xffffffff = row_pad entry)
+static int vecvec_gather_impl(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const uint32_t* d_idx, uint64_t total,
+                              const std::vector<uint32_t>& even, const uint64_t* row_pads, const uint64_t* col_pads, uint32_t row_logsize,
+                              uint32_t col_logsize, gkr_vecvec** outs) {
+    cudaStream_t st = ctx->stream;
+    int* d_bad = nullptr;
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_bad, sizeof(int), st));
+    cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+    for (uint32_t k = 0; k < n_src; k++) outs[k] = nullptr;
+    for (uint32_t k = 0; k < n_src && e == cudaSuccess; k++) {
+        gkr_vecvec* v = new gkr_vecvec();
+        outs[k] = v;
+        v->ctx = ctx;
+        v->row_pad = frh_from_limbs(row_pads + 4 * k);
+        v->col_pad = frh_from_limbs(col_pads + 4 * k);
+        v->row_logsize = row_logsize;
+        v->col_logsize = col_logsize;
+        v->row_len = even;
+        v->total = total;
+        e = gkr_malloc_async(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), st);
+        if (e == cudaSuccess && total) {
+            unsigned g = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 8);
+            vecvec_gather_kernel<<<g, 256, 0, st>>>(v->d, srcs[k] ? srcs[k]->d : nullptr, srcs[k] ? srcs[k]->n : 0, d_idx, total,
+                                                    fr_from_host(v->row_pad), d_bad);
+            ctx->launches++;
+            e = cudaGetLastError();
+        }
+    }
+    int bad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    gkr_free_async(d_bad, st);
+    if (e != cudaSuccess || bad) {
+        for (uint32_t k = 0; k < n_src; k++) {
+            gkr_vecvec_free(outs[k]);
+            outs[k] = nullptr;
+        }
+        return e != cudaSuccess ? ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)) : ctx->fail(GKR_ERR_ARG, "gather index out of range");
+    }
+    return GKR_OK;
+}
+
 extern "C" int gkr_vecvec_gather_multi(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const uint32_t* idx, const uint32_t* row_len,
                                        uint32_t n_rows, const uint64_t* row_pads, const uint64_t* col_pads, uint32_t row_logsize,
                                        uint32_t col_logsize, gkr_vecvec** outs) {
@@ -866,42 +908,31 @@ extern "C" int gkr_vecvec_gather_multi(gkr_ctx* ctx, const gkr_table* const* src
     }
     cudaStream_t st = ctx->stream;
     uint32_t* d_idx = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_idx, sizeof(uint32_t) * (std::max<uint64_t>(total, 1) + 1), st));
-    int* d_bad = (int*)(d_idx + std::max<uint64_t>(total, 1));
-    cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
-    if (e == cudaSuccess && total) e = cudaMemcpyAsync(d_idx, pidx.data(), sizeof(uint32_t) * total, cudaMemcpyHostToDevice, st);
-    for (uint32_t k = 0; k < n_src; k++) outs[k] = nullptr;
-    for (uint32_t k = 0; k < n_src && e == cudaSuccess; k++) {
-        gkr_vecvec* v = new gkr_vecvec();
-        outs[k] = v;
-        v->ctx = ctx;
-        v->row_pad = frh_from_limbs(row_pads + 4 * k);
-        v->col_pad = frh_from_limbs(col_pads + 4 * k);
-        v->row_logsize = row_logsize;
-        v->col_logsize = col_logsize;
-        v->row_len = even;
-        v->total = total;
-        e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(total, 1), st);
-        if (e == cudaSuccess && total) {
-            unsigned g = (unsigned)std::min<uint64_t>((total + 255) / 256, (uint64_t)ctx->num_sms * 8);
-            vecvec_gather_kernel<<<g, 256, 0, st>>>(v->d, srcs[k] ? srcs[k]->d : nullptr, srcs[k] ? srcs[k]->n : 0, d_idx, total,
-                                                    fr_from_host(v->row_pad), d_bad);
-            ctx->launches++;
-            e = cudaGetLastError();
-        }
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_idx, sizeof(uint32_t) * std::max<uint64_t>(total, 1), st));
+    if (total) GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_idx, pidx.data(), sizeof(uint32_t) * total, cudaMemcpyHostToDevice, st));
+    int rc = vecvec_gather_impl(ctx, srcs, n_src, d_idx, total, even, row_pads, col_pads, row_logsize, col_logsize, outs);  // synchronises
+    gkr_free_async(d_idx, st);
+    return rc;
+}
+
+// the same with the padded gather index already on the device (gkr_pushforward_bucketize_dev): `row_len` are the UNPADDED
+// row lengths, the index holds every row padded to even length
+extern "C" int gkr_vecvec_gather_multi_dev(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const gkr_u32buf* padded_idx,
+                                           const uint32_t* row_len, uint32_t n_rows, const uint64_t* row_pads, const uint64_t* col_pads,
+                                           uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** outs) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!outs || !srcs || n_src == 0 || !row_pads || !col_pads || !padded_idx || (n_rows && !row_len)) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (col_logsize >= 32 || row_logsize >= 32 || n_rows > ((uint64_t)1 << col_logsize)) return ctx->fail(GKR_ERR_ARG, "too many rows for col_logsize");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    std::vector<uint32_t> even(n_rows);
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < n_rows; r++) {
+        if (row_len[r] > ((uint64_t)1 << row_logsize)) return ctx->fail(GKR_ERR_ARG, "row longer than 1 << row_logsize");
+        even[r] = (row_len[r] + 1) & ~1u;
+        total += even[r];
     }
-    int bad = 0;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFreeAsync(d_idx, st);
-    if (e != cudaSuccess || bad) {
-        for (uint32_t k = 0; k < n_src; k++) {
-            gkr_vecvec_free(outs[k]);
-            outs[k] = nullptr;
-        }
-        return e != cudaSuccess ? ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)) : ctx->fail(GKR_ERR_ARG, "gather index out of range");
-    }
-    return GKR_OK;
+    if (total != padded_idx->n) return ctx->fail(GKR_ERR_ARG, "padded index length != sum of the even-padded row lengths");
+    return vecvec_gather_impl(ctx, srcs, n_src, padded_idx->d, total, even, row_pads, col_pads, row_logsize, col_logsize, outs);
 }
 extern "C" int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, const uint32_t* row_len, uint32_t n_rows,
                                  const uint64_t row_pad[4], const uint64_t col_pad[4], uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** out) {
@@ -926,6 +957,6 @@ extern "C" int gkr_vecvec_download(gkr_ctx* ctx, const gkr_vecvec* v, uint64_t* 
 
 extern "C" void gkr_vecvec_free(gkr_vecvec* v) {
     if (!v) return;
-    if (v->d) cudaFreeAsync(v->d, v->ctx->stream);
+    if (v->d) gkr_free_async(v->d, v->ctx->stream);
     delete v;
 }

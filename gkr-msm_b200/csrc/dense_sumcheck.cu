@@ -150,7 +150,7 @@ class DenseSO : public gkr_so {
     int slot = -1;
 
     ~DenseSO() override {
-        if (slab) cudaFreeAsync(slab, ctx->stream);
+        if (slab) gkr_free_async(slab, ctx->stream);
         if (slot >= 0) gkr_result_slot_release(ctx, slot);
     }
 
@@ -207,7 +207,7 @@ class DenseSO : public gkr_so {
         const uint64_t new_len = cur_len >> 1;
         if (!slab) {
             uint64_t per = new_len + (new_len >> 1);
-            GKR_CUDA_OK(ctx, cudaMallocAsync(&slab, sizeof(Fr) * per * P, ctx->stream));
+            GKR_CUDA_OK(ctx, gkr_malloc_async(&slab, sizeof(Fr) * per * P, ctx->stream));
             for (int j = 0; j < P; j++) {
                 buf[0][j] = slab + (size_t)j * per;
                 buf[1][j] = slab + (size_t)j * per + new_len;

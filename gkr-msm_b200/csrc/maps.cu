@@ -213,17 +213,17 @@ struct DevArrays {  // small device-side argument arrays of one map launch
     uint32_t* offs = nullptr;
     ~DevArrays() {
         cudaStream_t s = ctx->stream;
-        if (in) cudaFreeAsync(in, s);
-        if (out) cudaFreeAsync(out, s);
-        if (blocks) cudaFreeAsync(blocks, s);
-        if (pads) cudaFreeAsync(pads, s);
-        if (offs) cudaFreeAsync(offs, s);
+        if (in) gkr_free_async(in, s);
+        if (out) gkr_free_async(out, s);
+        if (blocks) gkr_free_async(blocks, s);
+        if (pads) gkr_free_async(pads, s);
+        if (offs) gkr_free_async(offs, s);
     }
 };
 
 template <class T>
 int to_device(gkr_ctx* ctx, const std::vector<T>& h, T** d) {
-    GKR_CUDA_OK(ctx, cudaMallocAsync(d, sizeof(T) * std::max<size_t>(h.size(), 1), ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(d, sizeof(T) * std::max<size_t>(h.size(), 1), ctx->stream));
     if (!h.empty()) GKR_CUDA_OK(ctx, cudaMemcpyAsync(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
     return GKR_OK;
 }
@@ -369,7 +369,7 @@ extern "C" int gkr_map_vecvec(gkr_ctx* ctx, const int* part_gate, const uint32_t
             v->col_pad = cp_tab[t];
             v->row_logsize = mode == 0 ? p0->row_logsize : p0->row_logsize - 1;
             v->col_logsize = p0->col_logsize;
-            cudaError_t e = cudaMallocAsync(&v->d, sizeof(Fr) * std::max<uint64_t>(v->total, 1), ctx->stream);
+            cudaError_t e = gkr_malloc_async(&v->d, sizeof(Fr) * std::max<uint64_t>(v->total, 1), ctx->stream);
             if (e != cudaSuccess) { delete v; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
             out[t] = v;
             outs[t] = v->d;

@@ -420,7 +420,7 @@ extern "C" int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, 
     s->n = n;
     s->kind = projective ? 1 : 0;
     size_t bytes = (size_t)n * s->stride();
-    cudaError_t e = cudaMallocAsync(&s->d, std::max<size_t>(bytes, 16), ctx->stream);
+    cudaError_t e = gkr_malloc_async(&s->d, std::max<size_t>(bytes, 16), ctx->stream);
     if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(s->d, points, bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -435,7 +435,7 @@ extern "C" uint64_t gkr_srs_len(const gkr_srs* s) { return s ? s->n : 0; }
 
 extern "C" void gkr_srs_free(gkr_srs* s) {
     if (!s) return;
-    if (s->d) cudaFreeAsync(s->d, s->ctx->stream);
+    if (s->d) gkr_free_async(s->d, s->ctx->stream);
     delete s;
 }
 
@@ -508,7 +508,7 @@ static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, 
     const uint32_t segs = 1u << (c - seg_log);
     const uint64_t n_threads = (uint64_t)W * segs;
     G1X* seg_out = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&seg_out, sizeof(G1X) * (n_threads + W), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * (n_threads + W), st));
     G1X* wsums = seg_out + n_threads;
     msm_segment_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out);
     msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs, wsums);
@@ -517,7 +517,7 @@ static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, 
     h.resize(W);
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(h.data(), wsums, sizeof(G1X) * W, cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(seg_out, st);
+    gkr_free_async(seg_out, st);
     return GKR_OK;
 }
 
@@ -556,13 +556,13 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     const size_t nbk = (size_t)W << c;
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *work = nullptr;
     G1X* buckets = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&digits, sizeof(uint32_t) * W * n, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * W * n, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&digits, sizeof(uint32_t) * W * n, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&sorted, sizeof(uint32_t) * W * n, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS), st));
     offsets = counts + nbk;
     cursor = counts + 2 * nbk;
     work = counts + 3 * nbk;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&buckets, sizeof(G1X) * nbk * n_problems, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&buckets, sizeof(G1X) * nbk * n_problems, st));
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
     msm_digits_kernel<<<g1, 256, 0, st>>>(scalars->d, (uint32_t)n, c, W, digits, counts);
@@ -574,10 +574,10 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, (uint64_t)W * n, work, buckets, n_problems,
                             (uint32_t)problem_stride);
     if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, c, (uint32_t)W * n_problems, h);
-    cudaFreeAsync(digits, st);
-    cudaFreeAsync(sorted, st);
-    cudaFreeAsync(counts, st);
-    cudaFreeAsync(buckets, st);
+    gkr_free_async(digits, st);
+    gkr_free_async(sorted, st);
+    gkr_free_async(counts, st);
+    gkr_free_async(buckets, st);
     if (rc == GKR_OK) msm_host_tail(h, c, W, n_problems, out_xy);
     return rc;
 }
@@ -637,11 +637,11 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
     res->ctx = ctx;
     res->n = n_buckets;
     res->kind = 2;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&res->d, sizeof(G1X) * nbk, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_p, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_b, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS + 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&res->d, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_p, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_b, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&sorted, sizeof(uint32_t) * std::max<uint64_t>(n, 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS + 1), st));
     uint32_t* offsets = counts + nbk;
     uint32_t* cursor = counts + 2 * nbk;
     d_bad = (int*)(counts + 3 * nbk);
@@ -663,10 +663,10 @@ extern "C" int gkr_g1_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32
     int bad = 0;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));  // host index arrays may be released by the caller now
-    cudaFreeAsync(d_p, st);
-    cudaFreeAsync(d_b, st);
-    cudaFreeAsync(sorted, st);
-    cudaFreeAsync(counts, st);
+    gkr_free_async(d_p, st);
+    gkr_free_async(d_b, st);
+    gkr_free_async(sorted, st);
+    gkr_free_async(counts, st);
     if (bad) {
         gkr_srs_free(res);
         return ctx->fail(GKR_ERR_ARG, "bucket index out of range");
@@ -720,9 +720,9 @@ extern "C" int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const g
     res->ctx = ctx;
     res->n = n_buckets;
     res->kind = 2;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&res->d, sizeof(G1X) * nbk, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&sorted, sizeof(uint32_t) * n, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS + 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&res->d, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&sorted, sizeof(uint32_t) * n, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS + 1), st));
     uint32_t* offsets = counts + nbk;
     uint32_t* cursor = counts + 2 * nbk;
     int* d_bad = (int*)(counts + 3 * nbk);
@@ -740,8 +740,8 @@ extern "C" int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const g
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
     }
-    cudaFreeAsync(sorted, st);
-    cudaFreeAsync(counts, st);
+    gkr_free_async(sorted, st);
+    gkr_free_async(counts, st);
     if (rc == GKR_OK && bad) rc = ctx->fail(GKR_ERR_ARG, "bucket index out of range");
     if (rc) {
         gkr_srs_free(res);
@@ -799,13 +799,13 @@ extern "C" int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t
     }
     if (pts->kind != 2) return ctx->fail(GKR_ERR_UNSUPPORTED, "download of Jacobian bases is not needed by the path");
     G1Aff* tmp = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&tmp, sizeof(G1Aff) * std::max<uint64_t>(pts->n, 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&tmp, sizeof(G1Aff) * std::max<uint64_t>(pts->n, 1), st));
     unsigned g = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((pts->n + 63) / 64, (uint64_t)ctx->num_sms * 8));
     g1_to_affine_kernel<<<g, 64, 0, st>>>((const G1X*)pts->d, pts->n, tmp);
     ctx->launches++;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(out_xy, tmp, sizeof(G1Aff) * pts->n, cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(tmp, st);
+    gkr_free_async(tmp, st);
     return GKR_OK;
 }
 
@@ -861,9 +861,9 @@ extern "C" int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uin
     s->kind = 0;
     G1X* Tx = nullptr;
     G1Aff* Ta = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&s->d, std::max<size_t>(sizeof(G1Aff) * n, 16), st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&Tx, sizeof(G1X) * 255, st));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&Ta, sizeof(G1Aff) * 255, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&s->d, std::max<size_t>(sizeof(G1Aff) * n, 16), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&Tx, sizeof(G1X) * 255, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&Ta, sizeof(G1Aff) * 255, st));
     G1Aff g0;
     std::memcpy(&g0, g0_xy, sizeof(G1Aff));
     srs_doublings_kernel<<<1, 32, 0, st>>>(g0, Tx);
@@ -875,8 +875,8 @@ extern "C" int gkr_srs_mock_setup(gkr_ctx* ctx, const uint64_t tau[4], const uin
     ctx->launches += 3;
     GKR_CUDA_OK(ctx, cudaGetLastError());
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(Tx, st);
-    cudaFreeAsync(Ta, st);
+    gkr_free_async(Tx, st);
+    gkr_free_async(Ta, st);
     *out = s;
     return GKR_OK;
 }

@@ -55,7 +55,7 @@ extern "C" int gkr_u32_upload(gkr_ctx* ctx, const uint32_t* vals, uint64_t n, gk
     gkr_u32buf* b = new gkr_u32buf();
     b->ctx = ctx;
     b->n = n;
-    cudaError_t e = cudaMallocAsync(&b->d, sizeof(uint32_t) * std::max<uint64_t>(n, 1), ctx->stream);
+    cudaError_t e = gkr_malloc_async(&b->d, sizeof(uint32_t) * std::max<uint64_t>(n, 1), ctx->stream);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(b->d, vals, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { delete b; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
@@ -64,7 +64,7 @@ extern "C" int gkr_u32_upload(gkr_ctx* ctx, const uint32_t* vals, uint64_t n, gk
 }
 extern "C" void gkr_u32_free(gkr_u32buf* b) {
     if (!b) return;
-    if (b->d) cudaFreeAsync(b->d, b->ctx->stream);
+    if (b->d) gkr_free_async(b->d, b->ctx->stream);
     delete b;
 }
 
@@ -103,7 +103,7 @@ extern "C" int gkr_table_gather(gkr_ctx* ctx, const gkr_table* src, const gkr_u3
     int rc = gkr_table_alloc(ctx, idx->n, out);
     if (rc) return rc;
     int* d_bad = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_bad, sizeof(int), ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_bad, sizeof(int), ctx->stream));
     GKR_CUDA_OK(ctx, cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
     if (idx->n) {
         unsigned g = (unsigned)std::min<uint64_t>((idx->n + 255) / 256, (uint64_t)ctx->num_sms * 8);
@@ -113,7 +113,7 @@ extern "C" int gkr_table_gather(gkr_ctx* ctx, const gkr_table* src, const gkr_u3
     int bad = 0;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_bad, ctx->stream);
+    gkr_free_async(d_bad, ctx->stream);
     if (bad) {
         gkr_table_free(*out);
         *out = nullptr;
@@ -167,7 +167,7 @@ extern "C" int gkr_table_lincomb(gkr_ctx* ctx, uint32_t n_terms, gkr_table* cons
     int rc = gkr_table_alloc(ctx, out_len, out);
     if (rc) return rc;
     LinTerm* d_terms = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_terms, sizeof(LinTerm) * std::max<uint32_t>(n_terms, 1), ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_terms, sizeof(LinTerm) * std::max<uint32_t>(n_terms, 1), ctx->stream));
     if (n_terms) GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_terms, terms.data(), sizeof(LinTerm) * n_terms, cudaMemcpyHostToDevice, ctx->stream));
     if (out_len) {
         unsigned g = (unsigned)std::min<uint64_t>((out_len + 255) / 256, (uint64_t)ctx->num_sms * 8);
@@ -176,7 +176,7 @@ extern "C" int gkr_table_lincomb(gkr_ctx* ctx, uint32_t n_terms, gkr_table* cons
         GKR_CUDA_OK(ctx, cudaGetLastError());
     }
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    cudaFreeAsync(d_terms, ctx->stream);
+    gkr_free_async(d_terms, ctx->stream);
     return GKR_OK;
 }
 
@@ -248,7 +248,7 @@ extern "C" int gkr_poly_eval(gkr_ctx* ctx, const gkr_table* poly, const uint64_t
     cudaStream_t st = ctx->stream;
     uint64_t chunk = pick_chunk(poly->n), n_chunks = (poly->n + chunk - 1) / chunk;
     Fr* buf = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&buf, sizeof(Fr) * (2 * n_chunks + 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&buf, sizeof(Fr) * (2 * n_chunks + 1), st));
     Fr xx = fr_from_host(frh_from_limbs(x));
     horner_chunks_kernel<<<(unsigned)((n_chunks + 63) / 64), 64, 0, st>>>(poly->d, poly->n, chunk, xx, buf, n_chunks);
     horner_scan_kernel<<<1, 512, 0, st>>>(buf, n_chunks, chunk, xx, buf + n_chunks, buf + 2 * n_chunks);
@@ -257,7 +257,7 @@ extern "C" int gkr_poly_eval(gkr_ctx* ctx, const gkr_table* poly, const uint64_t
     Fr r;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(&r, buf + 2 * n_chunks, sizeof(Fr), cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(buf, st);
+    gkr_free_async(buf, st);
     frh_to_limbs(fr_to_host(r), out);
     return GKR_OK;
 }
@@ -272,7 +272,7 @@ extern "C" int gkr_poly_div_by_linear(gkr_ctx* ctx, const gkr_table* poly, const
     if (rc) return rc;
     uint64_t chunk = pick_chunk(poly->n), n_chunks = (poly->n + chunk - 1) / chunk;
     Fr* buf = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&buf, sizeof(Fr) * (2 * n_chunks + 1), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&buf, sizeof(Fr) * (2 * n_chunks + 1), st));
     Fr xx = fr_from_host(frh_from_limbs(pt));
     horner_chunks_kernel<<<(unsigned)((n_chunks + 63) / 64), 64, 0, st>>>(poly->d, poly->n, chunk, xx, buf, n_chunks);
     horner_scan_kernel<<<1, 512, 0, st>>>(buf, n_chunks, chunk, xx, buf + n_chunks, buf + 2 * n_chunks);
@@ -282,7 +282,7 @@ extern "C" int gkr_poly_div_by_linear(gkr_ctx* ctx, const gkr_table* poly, const
     Fr r;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(&r, buf + 2 * n_chunks, sizeof(Fr), cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(buf, st);
+    gkr_free_async(buf, st);
     if (rem) frh_to_limbs(fr_to_host(r), rem);
     return GKR_OK;
 }
@@ -335,7 +335,7 @@ extern "C" int gkr_knuckles_create(gkr_ctx* ctx, uint32_t num_vars, const uint64
     key->num_vars = num_vars;
     key->k = frh_from_limbs(k);
     const uint64_t n = (uint64_t)1 << num_vars, len = 2 * n - 1;
-    cudaError_t e = cudaMallocAsync(&key->inverses, sizeof(Fr) * len, ctx->stream);
+    cudaError_t e = gkr_malloc_async(&key->inverses, sizeof(Fr) * len, ctx->stream);
     if (e != cudaSuccess) { delete key; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
     unsigned g = (unsigned)std::min<uint64_t>((len + 127) / 128, (uint64_t)ctx->num_sms * 8);
     knuckles_kpows_kernel<<<g, 128, 0, ctx->stream>>>(key->inverses, len, n, fr_from_host(key->k));
@@ -354,7 +354,7 @@ extern "C" int gkr_knuckles_k(const gkr_knuckles* key, uint64_t out[4]) {
 }
 extern "C" void gkr_knuckles_free(gkr_knuckles* key) {
     if (!key) return;
-    if (key->inverses) cudaFreeAsync(key->inverses, key->ctx->stream);
+    if (key->inverses) gkr_free_async(key->inverses, key->ctx->stream);
     delete key;
 }
 
@@ -410,7 +410,7 @@ extern "C" int gkr_knuckles_compute_t(gkr_ctx* ctx, const gkr_knuckles* key, con
         std::swap(a, b);
     }
     Fr* d_open = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_open, sizeof(Fr), st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_open, sizeof(Fr), st));
     unsigned g = (unsigned)std::min<uint64_t>((len + 255) / 256, (uint64_t)ctx->num_sms * 8);
     compute_t_finish_kernel<<<g, 256, 0, st>>>(a->d, key->inverses, len, n, d_open);
     ctx->launches++;
@@ -418,7 +418,7 @@ extern "C" int gkr_knuckles_compute_t(gkr_ctx* ctx, const gkr_knuckles* key, con
     Fr o;
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(&o, d_open, sizeof(Fr), cudaMemcpyDeviceToHost, st));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(st));
-    cudaFreeAsync(d_open, st);
+    gkr_free_async(d_open, st);
     gkr_table_free(b);
     if (opening) frh_to_limbs(fr_to_host(o), opening);
     *t_out = a;

@@ -628,42 +628,62 @@ struct PushForwardState {
         x_size = (uint64_t)1 << x_logsize;
         const uint32_t nb = 1u << d_logsize;
         const uint64_t m = (uint64_t)y_size * x_size;
-        // index matrices: uninitialised storage, first touched (page-faulted) by the bucketize threads themselves
-        std::unique_ptr<uint32_t[]> digits_(new uint32_t[m]), counter_(new uint32_t[m]), order_(new uint32_t[m]);
-        uint32_t *digits = digits_.get(), *counter = counter_.get(), *order = order_.get();
         std::vector<uint32_t> lens((size_t)y_size * nb);
-        {
-            Span s1(ctx, "  state: bucketize (host)");
-            ck(gkr_pushforward_bucketize(coefs, x_size, y_size, d_logsize, digits, counter, order, lens.data()));
-        }
-        std::unique_ptr<Span> s2(new Span(ctx, "  state: images + tables"));
-        p_0 = dv.upload(px, x_size);
-        p_1 = dv.upload(py, x_size);
         uint64_t zero[4] = {0, 0, 0, 0}, one[4];
         frh_to_limbs(F::ONE, one);
-        {  // bucket images of (x, y, 1): row (y, digit) holds the coordinates of the bucket's points in input order
-            const gkr_table* srcs[3] = {p_0->h, p_1->h, nullptr};
-            uint64_t pads[12];
-            std::memcpy(pads, zero, 32);
-            std::memcpy(pads + 4, one, 32);
-            std::memcpy(pads + 8, zero, 32);
-            gkr_vecvec* outs[3] = {nullptr, nullptr, nullptr};
-            ck(gkr_vecvec_gather_multi(ctx, srcs, 3, order, lens.data(), (uint32_t)lens.size(), pads, pads, x_logsize, y_logsize + d_logsize, outs));
-            for (int k = 0; k < 3; k++) image.push_back(std::make_shared<VvH>(outs[k]));
-        }
+        uint64_t pads[12];
+        std::memcpy(pads, zero, 32);
+        std::memcpy(pads + 4, one, 32);
+        std::memcpy(pads + 8, zero, 32);
         auto u32p = [&](const uint32_t* v, uint64_t n) {
             gkr_u32buf* b = nullptr;
             ck(gkr_u32_upload(ctx, v, n, &b));
             return std::make_shared<U32H>(b);
         };
         auto u32 = [&](const std::vector<uint32_t>& v) { return u32p(v.data(), v.size()); };
+        std::unique_ptr<Span> s2;
+        if (d_logsize <= 13) {
+            // digits, in-bucket ranks and bucket contents by a stable counting sort on the device: only the scalars are uploaded
+            U32 order;
+            {
+                Span s1(ctx, "  state: bucketize (device)");
+                gkr_u32buf *dg = nullptr, *ct = nullptr, *po = nullptr;
+                ck(gkr_pushforward_bucketize_dev(ctx, coefs, x_size, y_size, d_logsize, &dg, &ct, &po, lens.data()));
+                d_idx = std::make_shared<U32H>(dg);
+                c_idx = std::make_shared<U32H>(ct);
+                order = std::make_shared<U32H>(po);
+            }
+            s2.reset(new Span(ctx, "  state: images + tables"));
+            p_0 = dv.upload(px, x_size);
+            p_1 = dv.upload(py, x_size);
+            const gkr_table* srcs[3] = {p_0->h, p_1->h, nullptr};
+            gkr_vecvec* outs[3] = {nullptr, nullptr, nullptr};
+            ck(gkr_vecvec_gather_multi_dev(ctx, srcs, 3, order->h, lens.data(), (uint32_t)lens.size(), pads, pads, x_logsize, y_logsize + d_logsize, outs));
+            for (int k = 0; k < 3; k++) image.push_back(std::make_shared<VvH>(outs[k]));
+        } else {
+            // index matrices: uninitialised storage, first touched (page-faulted) by the bucketize threads themselves
+            std::unique_ptr<uint32_t[]> digits_(new uint32_t[m]), counter_(new uint32_t[m]), order_(new uint32_t[m]);
+            uint32_t *digits = digits_.get(), *counter = counter_.get(), *order = order_.get();
+            {
+                Span s1(ctx, "  state: bucketize (host)");
+                ck(gkr_pushforward_bucketize(coefs, x_size, y_size, d_logsize, digits, counter, order, lens.data()));
+            }
+            s2.reset(new Span(ctx, "  state: images + tables"));
+            p_0 = dv.upload(px, x_size);
+            p_1 = dv.upload(py, x_size);
+            // bucket images of (x, y, 1): row (y, digit) holds the coordinates of the bucket's points in input order
+            const gkr_table* srcs[3] = {p_0->h, p_1->h, nullptr};
+            gkr_vecvec* outs[3] = {nullptr, nullptr, nullptr};
+            ck(gkr_vecvec_gather_multi(ctx, srcs, 3, order, lens.data(), (uint32_t)lens.size(), pads, pads, x_logsize, y_logsize + d_logsize, outs));
+            for (int k = 0; k < 3; k++) image.push_back(std::make_shared<VvH>(outs[k]));
+            d_idx = u32p(digits, m);
+            c_idx = u32p(counter, m);
+        }
         auto to_field = [&](const U32& b, int negate) {
             gkr_table* t = nullptr;
             ck(gkr_table_from_u32(ctx, b->h, negate, &t));
             return std::make_shared<TabH>(t);
         };
-        d_idx = u32p(digits, m);
-        c_idx = u32p(counter, m);
         d = to_field(d_idx, 0);
         c = to_field(c_idx, 0);
         // access counts from the bucket sizes: ac_d[v] = #incidences with digit v; ac_c[v] = #buckets longer than v

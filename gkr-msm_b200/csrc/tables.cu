@@ -35,6 +35,65 @@ void gkr_result_slot_release(gkr_ctx* ctx, int slot) {
 
 // Spin on the slot's flag (written by the last block into mapped host memory) and fold the per-block partials.
 // Every ~64k spins the stream is queried so that a faulted or vanished kernel turns into an error, never a hang.
+// ---- large-block cache in front of the stream-ordered pool (see common.cuh) ---------------------------------------------
+#include <map>
+#include <unordered_map>
+namespace {
+struct BigCache {
+    std::multimap<size_t, void*> free_blocks;
+    std::unordered_map<void*, size_t> live;  // large blocks handed out
+};
+std::mutex g_big_mutex;
+std::map<cudaStream_t, BigCache> g_big;
+}  // namespace
+
+cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
+    if (n < GKR_BIG_BLOCK) return cudaMallocAsync(p, n, s);
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    BigCache& c = g_big[s];
+    auto it = c.free_blocks.lower_bound(n);
+    if (it != c.free_blocks.end() && it->first <= 2 * n) {
+        *p = it->second;
+        c.live[*p] = it->first;
+        c.free_blocks.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMallocAsync(p, n, s);
+    if (e != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
+        for (auto& kv : c.free_blocks) cudaFreeAsync(kv.second, s);
+        c.free_blocks.clear();
+        (void)cudaGetLastError();
+        e = cudaMallocAsync(p, n, s);
+    }
+    if (e == cudaSuccess) c.live[*p] = n;
+    return e;
+}
+
+cudaError_t gkr_free_async(void* p, cudaStream_t s) {
+    if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_big_mutex);
+        auto ci = g_big.find(s);
+        if (ci != g_big.end()) {
+            auto it = ci->second.live.find(p);
+            if (it != ci->second.live.end()) {
+                ci->second.free_blocks.emplace(it->second, p);
+                ci->second.live.erase(it);
+                return cudaSuccess;
+            }
+        }
+    }
+    return cudaFreeAsync(p, s);
+}
+
+void gkr_big_cache_release(cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    auto ci = g_big.find(s);
+    if (ci == g_big.end()) return;
+    for (auto& kv : ci->second.free_blocks) cudaFreeAsync(kv.second, s);
+    g_big.erase(ci);
+}
+
 int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out) {
     GkrSlot* s = &ctx->slots_host[slot];
     const uint32_t seq = ctx->slot_seq[slot];
@@ -150,6 +209,7 @@ extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     ctx->deg2_layout.reset();  // frees its device arrays on the stream
+    if (ctx->stream) gkr_big_cache_release(ctx->stream);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stage_host) cudaFreeHost(ctx->stage_host);
     {
@@ -187,10 +247,10 @@ extern "C" int gkr_table_alloc(gkr_ctx* ctx, uint64_t n, gkr_table** out) {
     gkr_table* t = new gkr_table();
     t->ctx = ctx;
     t->n = n;
-    cudaError_t e = cudaMallocAsync(&t->d, sizeof(Fr) * std::max<uint64_t>(n, 1), ctx->stream);
+    cudaError_t e = gkr_malloc_async(&t->d, sizeof(Fr) * std::max<uint64_t>(n, 1), ctx->stream);
     if (e != cudaSuccess) {
         delete t;
-        return ctx->fail(GKR_ERR_CUDA, std::string("cudaMallocAsync(table): ") + cudaGetErrorString(e));
+        return ctx->fail(GKR_ERR_CUDA, std::string("gkr_malloc_async(table): ") + cudaGetErrorString(e));
     }
     *out = t;
     return GKR_OK;
@@ -216,7 +276,7 @@ extern "C" void* gkr_table_device_ptr(gkr_table* t) { return t ? (void*)t->d : n
 
 extern "C" void gkr_table_free(gkr_table* t) {
     if (!t) return;
-    if (t->owned && t->d) cudaFreeAsync(t->d, t->ctx->stream);  // stream-ordered: queued kernels finish first
+    if (t->owned && t->d) gkr_free_async(t->d, t->ctx->stream);  // stream-ordered: queued kernels finish first
     delete t;
 }
 
@@ -325,8 +385,8 @@ static int eq_build(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult,
     }
     uint32_t h = n / 2, k = n - h;
     Fr *hi = nullptr, *lo = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&hi, sizeof(Fr) << h, ctx->stream));
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&lo, sizeof(Fr) << k, ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&hi, sizeof(Fr) << h, ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&lo, sizeof(Fr) << k, ctx->stream));
     int rc = eq_build(ctx, d_point, h, mult, hi);
     if (rc == GKR_OK) rc = eq_build(ctx, d_point + h, k, fr_from_host(gkr::frh::ONE), lo);
     if (rc == GKR_OK) {
@@ -337,8 +397,8 @@ static int eq_build(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult,
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
     }
-    cudaFreeAsync(hi, ctx->stream);
-    cudaFreeAsync(lo, ctx->stream);
+    gkr_free_async(hi, ctx->stream);
+    gkr_free_async(lo, ctx->stream);
     return rc;
 }
 
@@ -377,10 +437,10 @@ extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, con
     int rc = gkr_table_alloc(ctx, (uint64_t)1 << n, out);
     if (rc) return rc;
     Fr* d_point = nullptr;
-    GKR_CUDA_OK(ctx, cudaMallocAsync(&d_point, sizeof(Fr) * std::max<uint32_t>(n, 1), ctx->stream));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_point, sizeof(Fr) * std::max<uint32_t>(n, 1), ctx->stream));
     if (n) GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_point, point, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
     rc = eq_build(ctx, d_point, n, fr_from_host(m), (*out)->d);
-    cudaFreeAsync(d_point, ctx->stream);
+    gkr_free_async(d_point, ctx->stream);
     if (rc) {
         gkr_table_free(*out);
         *out = nullptr;

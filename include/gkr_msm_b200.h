@@ -151,6 +151,10 @@ int gkr_vecvec_gather(gkr_ctx* ctx, const gkr_table* src, const uint32_t* idx, c
 int gkr_vecvec_gather_multi(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const uint32_t* idx, const uint32_t* row_len,
                             uint32_t n_rows, const uint64_t* row_pads, const uint64_t* col_pads, uint32_t row_logsize,
                             uint32_t col_logsize, gkr_vecvec** outs);
+/* The same with the padded gather index resident on the device (output of gkr_pushforward_bucketize_dev). */
+int gkr_vecvec_gather_multi_dev(gkr_ctx* ctx, const gkr_table* const* srcs, uint32_t n_src, const gkr_u32buf* padded_idx,
+                                const uint32_t* row_len, uint32_t n_rows, const uint64_t* row_pads, const uint64_t* col_pads,
+                                uint32_t row_logsize, uint32_t col_logsize, gkr_vecvec** outs);
 uint32_t gkr_vecvec_num_rows(const gkr_vecvec* v);
 uint64_t gkr_vecvec_total_len(const gkr_vecvec* v); /* elements after even-padding */
 int gkr_vecvec_download(gkr_ctx* ctx, const gkr_vecvec* v, uint64_t* flat_out, uint32_t* row_len_out, uint64_t row_pad[4],
@@ -239,6 +243,8 @@ int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_windows, uint64
  * gkr_knuckles_*: KnucklesProvingKey::new inverses and compute_t (knuckles.rs:65-81, 111-154). */
 typedef struct gkr_knuckles gkr_knuckles;
 int gkr_u32_upload(gkr_ctx* ctx, const uint32_t* vals, uint64_t n, gkr_u32buf** out);
+int gkr_u32_download(gkr_ctx* ctx, const gkr_u32buf* b, uint32_t* out);
+uint64_t gkr_u32_len(const gkr_u32buf* b);
 void gkr_u32_free(gkr_u32buf* b);
 int gkr_table_from_u32(gkr_ctx* ctx, const gkr_u32buf* v, int negate, gkr_table** out);
 int gkr_table_gather(gkr_ctx* ctx, const gkr_table* src, const gkr_u32buf* idx, gkr_table** out);
@@ -258,6 +264,12 @@ int gkr_knuckles_compute_t(gkr_ctx* ctx, const gkr_knuckles* key, const gkr_tabl
  * little-endian u64 (the integer value of the Bandersnatch scalar, not Montgomery form). */
 int gkr_pushforward_bucketize(const uint64_t* coefs, uint64_t n, uint32_t y_size, uint32_t d_logsize, uint32_t* digits,
                               uint32_t* counter, uint32_t* order, uint32_t* lens);
+/* The same bookkeeping on the device (csrc/bucketize.cu: a stable counting sort per digit row): only the scalars cross PCIe.
+ * digits / counter: [y_size][n] device arrays; padded_order: the bucket contents back to back with every bucket padded to
+ * even length by 0xffffffff (the gather index gkr_vecvec_gather_multi_dev takes); lens: HOST output [y_size][2^d].
+ * Supports 1 <= d_logsize <= 13 (GKR_ERR_UNSUPPORTED above: use the host version). */
+int gkr_pushforward_bucketize_dev(gkr_ctx* ctx, const uint64_t* coefs, uint64_t n, uint32_t y_size, uint32_t d_logsize, gkr_u32buf** digits,
+                                  gkr_u32buf** counter, gkr_u32buf** padded_order, uint32_t* lens);
 
 /* ---- host-side protocol mirror (stand-in for the Rust host while no Rust toolchain exists) --------
  * ProofTranscript2  src/cleanup/proof_transcript.rs:76-147 (merlin 3.0 STROBE-128, label b"" per message) */

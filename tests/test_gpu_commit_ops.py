@@ -148,3 +148,29 @@ def test_bucket_sums_rows_matches_host_index_route(ctx, clm):
         assert comms[k] == CV.g1_msm([bases[x + x_size * (y % cm)] for y in ys for x in range(x_size)], [int(digits[y][x]) for y in ys for x in range(x_size)])
     with pytest.raises(g.GkrError):  # a digit that does not fit group_log bits
         srs.bucket_sums_rows(g.U32Buf(ctx, digits.reshape(-1)), xl, clm, 1)
+
+
+@pytest.mark.parametrize("n,y_size,d", [(1, 1, 1), (37, 5, 3), (2048, 3, 8), (2049, 16, 8), (5000, 13, 10), (70001, 4, 13), (4097, 32, 8)])
+def test_bucketize_device_equals_host(ctx, n, y_size, d):
+    """gkr_pushforward_bucketize_dev (stable counting sort on the device) == the host bookkeeping (pushforward.rs:351-396):
+    digits, in-bucket ranks in input order, bucket sizes, and the even-padded bucket contents."""
+    rng = np.random.default_rng(n * 31 + d)
+    co = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    if n > 100:
+        co[: n // 3] = co[0]  # heavy buckets: many equal scalars in a row
+        co[n // 2] = 0
+    hd, hc, ho, hl = g.pushforward_bucketize(co, y_size, d)
+    dd, dc, dpo, dl = g.pushforward_bucketize_dev(ctx, co, y_size, d)
+    assert np.array_equal(dl, hl) and np.array_equal(dd, hd) and np.array_equal(dc, hc)
+    # host padded order: every bucket's x list, padded to even length with 0xffffffff
+    exp = []
+    for y in range(y_size):
+        off = 0
+        for b in range(1 << d):
+            ln = int(hl[y, b])
+            exp.append(ho[y, off:off + ln])
+            if ln & 1:
+                exp.append(np.array([0xFFFFFFFF], np.uint32))
+            off += ln
+    exp = np.concatenate(exp) if exp else np.zeros(0, np.uint32)
+    assert np.array_equal(dpo, exp)
