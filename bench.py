@@ -275,21 +275,30 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"oracle C port (OpenMP), full Prod3 sumcheck over 2^{args.ref_log_n} x 3 tables, median of {reps} runs ({sec:.3f} s each)"}
 
-    # ---- secondary: the whole `examples/pippenger` prover on BASELINE config[0] (x=16, d=8, 128 bit, clm 0) ------------
-    pip = None
+    # ---- secondary: the whole `examples/pippenger` prover: BASELINE config[0] (x=16, d=8, 128 bit, clm 0) and the 2^20-point
+    # shape of config[2] (x=20, d=10, 128 bit) on this one GPU -- "GKR-MSM prove ms @2^20 pts/128-bit" of BASELINE.json's metric
+    pip, pip20 = None, None
     if world == 1 and not args.no_pippenger:
         try:
             import importlib.util
             spec = importlib.util.spec_from_file_location("bench_pippenger", os.path.join(ROOT, "tools", "bench_pippenger.py"))
             bp = importlib.util.module_from_spec(spec)
             spec.loader.exec_module(bp)
-            r = bp.run(argparse.Namespace(x_logsize=16, d_logsize=8, nbits=128, clm=0, reps=3, seed=7, profile=False, python_host=False), ctx=ctx)
-            pip = {"prove_ms": r["prove_ms_best"], "what": "benchutils::run_pippenger (witness + phase-1 commitments + proof), wall clock, "
-                   "inputs on the host, SRS resident", "config": "x_logsize 16, d_logsize 8, nbits 128, clm 0 (BASELINE config[0]: 2^20 "
-                   "point-digit incidences)", "proof_bytes": r["proof_bytes"], "gpu_launches": r["gpu_launches"],
-                   "prove_ms_all": r["prove_ms_all"]}
+
+            def prove(x, d, reps):
+                r = bp.run(argparse.Namespace(x_logsize=x, d_logsize=d, nbits=128, clm=0, reps=reps, seed=7, profile=False, python_host=False), ctx=ctx)
+                return {"prove_ms": r["prove_ms_best"], "prove_ms_median": statistics.median(r["prove_ms_all"][1:]),
+                        "what": "benchutils::run_pippenger (witness + phase-1 commitments + proof), wall clock, inputs on the host, SRS resident",
+                        "config": f"x_logsize {x}, d_logsize {d}, nbits 128, clm 0 ({r['incidences']} point-digit incidences)",
+                        "proof_bytes": r["proof_bytes"], "gpu_launches": r["gpu_launches"], "prove_ms_all": r["prove_ms_all"],
+                        "round_waits": r["round_waits"], "round_wait_ms": r["round_wait_ms"]}
+
+            pip = prove(16, 8, 4)
+            if not args.no_pippenger_2e20:
+                pip20 = prove(20, 10, 4)
         except Exception as e:  # pragma: no cover
-            pip = {"error": repr(e)}
+            pip = pip or {"error": repr(e)}
+            pip20 = pip20 or {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -301,7 +310,7 @@ def run_ours(args, rank, world, local_rank):
                    "parallelism": f"hypercube sharded by top index bits over {world} GPU(s)",
                    "l2": "inputs (1.5 GiB per GPU) larger than the 126 MB L2", "transcript": "merlin on host, one challenge per round"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "pippenger_prove": pip,
+        "pippenger_prove": pip, "pippenger_prove_2e20": pip20,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -319,6 +328,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pippenger", action="store_true")
+    ap.add_argument("--no-pippenger-2e20", action="store_true", help="skip the x=20 whole-prover leg (about 15 s of input generation)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -214,6 +214,7 @@ struct Deg2Layout {
     bool ragged = false;
     std::vector<std::vector<uint32_t>> lens;  // [level][row] element counts (even when ragged)
     std::vector<uint64_t> totals;             // [level]
+    std::vector<char> one_pair;               // [level] every row holds exactly one pair
     uint32_t* d_off = nullptr;                // [levels * (nrows + 1)] ELEMENT offsets
     uint32_t* d_poff = nullptr;               // the same in PAIRS
     ~Deg2Layout() {
@@ -240,6 +241,7 @@ static int deg2_layout_get(gkr_ctx* ctx, const std::vector<uint32_t>& lens0, boo
     const uint32_t nrows = L->nrows;
     L->lens.resize(n_levels);
     L->totals.assign(n_levels, 0);
+    L->one_pair.assign(n_levels, 0);
     L->lens[0] = lens0;
     std::vector<uint32_t> h_off((size_t)2 * n_levels * (nrows + 1));
     uint32_t* h_poff = h_off.data() + (size_t)n_levels * (nrows + 1);
@@ -257,11 +259,14 @@ static int deg2_layout_get(gkr_ctx* ctx, const std::vector<uint32_t>& lens0, boo
         uint32_t* o = h_off.data() + (size_t)b * (nrows + 1);
         uint32_t* po = h_poff + (size_t)b * (nrows + 1);
         uint64_t acc = 0;
+        bool all_two = true;
         for (uint32_t r = 0; r < nrows; r++) {
             o[r] = (uint32_t)acc;
             po[r] = (uint32_t)(acc / 2);
             acc += cur[r];
+            all_two &= cur[r] == 2;
         }
+        L->one_pair[b] = all_two ? 1 : 0;
         if (acc >= ((uint64_t)1 << 32)) return ctx->fail(GKR_ERR_UNSUPPORTED, "more than 2^32 elements per polynomial");
         o[nrows] = (uint32_t)acc;
         po[nrows] = (uint32_t)(acc / 2);
@@ -295,6 +300,7 @@ class Deg2SO : public gkr_so {
     std::vector<uint32_t> lens0;              // row lengths at construction
     std::shared_ptr<Deg2Layout> layout;
     const uint64_t* totals = nullptr;         // [round] total elements
+    const char* one_pair = nullptr;           // [round] every row holds exactly one pair
     uint32_t* d_off = nullptr;                // [(n_sparse + 1) * (nrows + 1)] ELEMENT offsets per round
     uint32_t* d_poff = nullptr;               // same in PAIRS
     // eq levels
@@ -363,16 +369,23 @@ class Deg2SO : public gkr_so {
         a.pt = d_pt_row;
         a.n_pt = m_row >= b ? m_row - b : 0;
         a.do_pad = is_vecvec ? 1 : 0;
+        a.one_pair_rows = (is_vecvec && one_pair[b]) ? 1 : 0;
         a.o = ctx->round_out(slot);
-        uint64_t work = std::max<uint64_t>(2 * n_pairs, is_vecvec ? nrows : 1);  // two lanes per pair
-        uint64_t want = (work + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS;
-        uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->num_sms * 3, GKR_MAX_BLOCKS) / n_blocks);
-        dim3 grid((unsigned)std::max<uint64_t>(1, std::min(want, cap)), (unsigned)n_blocks);
-        unsigned threads = GKR_REDUCE_THREADS;
-        if (grid.x == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (work + 31) / 32 * 32));
-        pending_blocks = grid.x * grid.y;
+        const uint64_t want = std::max<uint64_t>(1, (2 * n_pairs + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS);  // two lanes per pair
         // latency flavour for rounds that fit in about one wave of blocks, throughput flavour above
-        if (n_pairs * (uint64_t)n_blocks <= GKR_DEG2_COMPACT_MAX_PAIRS) {
+        const bool compact = n_pairs * (uint64_t)n_blocks <= GKR_DEG2_COMPACT_MAX_PAIRS;
+        // compact + ragged: extra blocks at the tail of every slice for the padding term, one row per thread (only the y == 0
+        // ones work), so that T overlaps the gate evaluations instead of following them
+        const uint64_t pad_blocks = (is_vecvec && compact) ? std::min<uint64_t>(128, (nrows + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS) : 0;
+        const uint64_t cap = std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)ctx->num_sms * 3, GKR_MAX_BLOCKS - 3 * 128) / n_blocks);
+        uint64_t work_blocks = std::min(want, cap);
+        if (is_vecvec && !compact) work_blocks = std::max<uint64_t>(work_blocks, std::min<uint64_t>(cap, (nrows + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS));
+        a.work_blocks_x = (uint32_t)work_blocks;
+        dim3 grid((unsigned)(work_blocks + pad_blocks), (unsigned)n_blocks);
+        unsigned threads = GKR_REDUCE_THREADS;
+        if (grid.x == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (2 * n_pairs + 31) / 32 * 32));
+        pending_blocks = grid.x * grid.y;
+        if (compact) {
             gkr_launch_deg2_round_compact(a, grid, threads, ctx->stream);
         } else {
             deg2_inline::deg2_round_kernel<<<grid, threads, 0, ctx->stream>>>(a);
@@ -506,6 +519,7 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
         int rc = deg2_layout_get(ctx, lens0, is_vecvec, n_sparse + 1, &layout, &base);
         if (rc) return rc;
         totals = layout->totals.data() + base;
+        one_pair = layout->one_pair.data() + base;
         d_off = layout->d_off + (size_t)base * (nrows + 1);
         d_poff = layout->d_poff + (size_t)base * (nrows + 1);
     }

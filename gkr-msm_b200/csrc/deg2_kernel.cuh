@@ -37,7 +37,10 @@ struct Deg2RoundArgs {
     const Fr* row_pads;        // [P]
     const Fr* pt;              // row variables of this round's eq table, for the padding term
     uint32_t n_pt;
-    int do_pad;                // ragged objects only
+    int do_pad;                // ragged objects only: compute the padding term T (compact flavour: by the blocks with
+                               // blockIdx.x >= work_blocks_x of the y == 0 slice; inline flavour: epilogue of the y == 0 blocks)
+    uint32_t work_blocks_x;    // blocks per gate slice that evaluate pairs
+    int one_pair_rows;         // every row of this round holds exactly one pair: row == pair index, no search
     RoundOut o;                // 3 accumulators: S1, S2, T
 };
 
@@ -104,7 +107,14 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
     __shared__ Fr smem[3 * (GKR_REDUCE_THREADS / 32)];
     Fr mine = fr_zero();
     const Deg2Block blk = A.blocks[blockIdx.y];
+#ifdef GKR_COMPACT_FIELD
+    // latency flavour: the tail of the grid (blockIdx.x >= work_blocks_x) only computes T, overlapping the gate evaluations
+    const bool pad_slice = blockIdx.x >= A.work_blocks_x;
+    const uint64_t stride = (uint64_t)A.work_blocks_x * blockDim.x, n_lanes = pad_slice ? 0 : 2 * A.n_pairs;
+#else
+    // throughput flavour: T is a negligible epilogue of the y == 0 blocks (launched with work_blocks_x == gridDim.x)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x, n_lanes = 2 * A.n_pairs;
+#endif
     const uint32_t lane = threadIdx.x & 31, role = lane & 1;
     for (uint64_t wb = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); wb < n_lanes; wb += stride) {
         const uint64_t t = wb + lane, q = t >> 1;
@@ -113,6 +123,13 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
         uint32_t row = 0;
         uint64_t idx = q;
         if (active) {
+#ifdef GKR_COMPACT_FIELD
+            if (A.pair_off && A.one_pair_rows) {
+                row = (uint32_t)q;
+                idx = 0;
+                w = fr_mul(A.eq[0], A.rowcoef[row]);
+            } else
+#endif
             if (A.pair_off) {
                 uint32_t lo = 0, hi = A.nrows;  // largest r with pair_off[r] <= q (empty rows repeat an offset)
                 while (hi - lo > 1) {
@@ -149,10 +166,17 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
         acc[2].l[k] = 0u;
     }
     // T = sum_rows rowcoef[row] * (1 - eq_sum(pt, len_row / 2)): closed form of src/utils.rs:265-291 per row
-    // (vecvec_eq.rs:344-369), computed once by the y == 0 slice of the grid
+    // (vecvec_eq.rs:344-369), computed by its own slice of the grid so that it overlaps the gate evaluations
+#ifdef GKR_COMPACT_FIELD
+    if (pad_slice && A.do_pad && blockIdx.y == 0) {
+        const Fr one = fr_one();
+        const uint64_t pstride = (uint64_t)(gridDim.x - A.work_blocks_x) * blockDim.x;
+        for (uint64_t r = (uint64_t)(blockIdx.x - A.work_blocks_x) * blockDim.x + threadIdx.x; r < A.nrows; r += pstride) {
+#else
     if (A.do_pad && blockIdx.y == 0) {
         const Fr one = fr_one();
         for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < A.nrows; r += stride) {
+#endif
             uint64_t k = A.pair_off[r + 1] - A.pair_off[r];
             Fr s;
             if (k >= ((uint64_t)1 << A.n_pt)) {

@@ -51,7 +51,7 @@ def test_bucket_sums_running_sum_and_msm_nonaff(ctx):
         srs.bucket_sums([0, 1], [0, 99], 8)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 64, 1000, 5000])
+@pytest.mark.parametrize("n", [1, 2, 5, 64, 511, 512, 513, 1000, 5000, 32768, 32769, 40001])  # 1, 2 and 3 chunk levels
 def test_poly_eval_and_div_by_linear(ctx, n):
     rng = random.Random(n)
     poly = [rng.randrange(P) for _ in range(n)]
