@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(256) msm_accumulate_huge_kernel(const __grid_c
 
 // per window: sum_d d * B_d.  A thread owns the segment [lo, lo + L) of one window; descending running sums give
 // tot = sum (d - lo + 1) B_d and run = sum B_d, so the segment contributes tot + (lo - 1) * run.
-__global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, int c, int seg_log, uint64_t n_threads, G1X* seg_out) {
+__global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, int c, int seg_log, uint64_t n_threads, G1X* seg_out,
+                                                          uint32_t out_stride /* entries per window in seg_out */) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     const uint32_t segs = 1u << (c - seg_log);
@@ -380,8 +381,73 @@ __global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, in
         neg.Y = fq_sub(fq_zero(), neg.Y);
         g1x_add(tot, neg);
     }
-    seg_out[t] = tot;
+    seg_out[(size_t)w * out_stride + sgm] = tot;
 }
+// Two-level variant for large bucket arrays (the scalar multiplication by lo - 1 above is 3/5 of a thread's work at c = 16):
+// level 0 leaves tot_s = sum_{d in segment} (d - lo) B_d and hands run8_s = 2^seg_log * run_s to level 1, because
+//   sum_d d B_d = sum_s tot_s + sum_s s * (2^seg_log run_s),
+// the second sum being the same weighted sum over an array 2^seg_log times shorter (msm_segment_kernel on it).
+// Per bucket: (2 L + seg_log) / L additions here + 5 / L above, instead of 5.
+__global__ void __launch_bounds__(128) msm_segment_level0_kernel(const G1X* buckets, int c, int seg_log, uint64_t n_threads, G1X* tot_out,
+                                                                 uint32_t tot_stride, G1X* run_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_threads) return;
+    const uint32_t segs = 1u << (c - seg_log);
+    const uint32_t w = (uint32_t)(t / segs), sgm = (uint32_t)(t % segs);
+    const G1X* B = buckets + ((size_t)w << c);
+    const uint32_t lo = sgm << seg_log, hi = lo + (1u << seg_log);
+    G1X run = g1x_inf(), tot = g1x_inf();
+    for (uint32_t d = hi; d-- > lo + 1;) {
+        g1x_add(run, B[d]);
+        g1x_add(tot, run);
+    }
+    g1x_add(run, B[lo]);  // weight zero inside the segment
+    for (int k = 0; k < seg_log; k++) run = g1x_dbl(run);
+    tot_out[(size_t)w * tot_stride + sgm] = tot;
+    run_out[t] = run;
+}
+
+// Tiny windows (c == 4: the commitments-times-coefficients combinations of a proof, a handful of points): one WARP per
+// window instead of a 40-addition chain in one thread.  sum_d d B_d = sum_j 2^j (sum of the 8 buckets with bit j set):
+// lane (j, p) fetches the p-th such bucket, three shuffle levels give the four bit sums, lane 0 combines them with
+// three doublings -- a dependent chain of 9 group operations.
+__global__ void __launch_bounds__(128) msm_window_bits_kernel(const G1X* buckets, uint32_t n_windows, G1X* window_sums) {
+    const uint32_t lane = threadIdx.x & 31, w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= n_windows) return;
+    const uint32_t j = lane >> 3, p = lane & 7;
+    // p-th 4-bit value with bit j set: insert a one at position j into the 3-bit number p
+    const uint32_t low = p & ((1u << j) - 1u), d = ((p >> j) << (j + 1)) | (1u << j) | low;
+    G1X v = buckets[((size_t)w << 4) + d];
+    for (int off = 4; off > 0; off >>= 1) {
+        G1X o;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            o.X.l[k] = __shfl_down_sync(0xffffffffu, v.X.l[k], off);
+            o.Y.l[k] = __shfl_down_sync(0xffffffffu, v.Y.l[k], off);
+            o.ZZ.l[k] = __shfl_down_sync(0xffffffffu, v.ZZ.l[k], off);
+            o.ZZZ.l[k] = __shfl_down_sync(0xffffffffu, v.ZZZ.l[k], off);
+        }
+        if (p < (uint32_t)off) g1x_add(v, o);
+    }
+    // lanes 0, 8, 16, 24 hold the bit sums b0..b3
+    G1X acc = g1x_inf();
+    for (int bit = 3; bit >= 0; bit--) {
+        G1X b;
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            b.X.l[k] = __shfl_sync(0xffffffffu, v.X.l[k], bit * 8);
+            b.Y.l[k] = __shfl_sync(0xffffffffu, v.Y.l[k], bit * 8);
+            b.ZZ.l[k] = __shfl_sync(0xffffffffu, v.ZZ.l[k], bit * 8);
+            b.ZZZ.l[k] = __shfl_sync(0xffffffffu, v.ZZZ.l[k], bit * 8);
+        }
+        if (lane == 0) {
+            if (bit != 3) acc = g1x_dbl(acc);
+            g1x_add(acc, b);
+        }
+    }
+    if (lane == 0) window_sums[w] = acc;
+}
+
 // window_sums[w] = sum of the window's segment contributions (strided partial sums + shared-memory tree)
 __global__ void __launch_bounds__(256) msm_window_tree_kernel(const G1X* seg_out, uint32_t segs, G1X* window_sums) {
     extern __shared__ unsigned char smem_raw[];
@@ -504,15 +570,37 @@ static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint3
 // per-group tree on the device, result (extended Jacobian) copied to the host.
 static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, std::vector<gkr::G1XH>& h) {
     cudaStream_t st = ctx->stream;
-    const int seg_log = c < 3 ? c : 3;
-    const uint32_t segs = 1u << (c - seg_log);
-    const uint64_t n_threads = (uint64_t)W * segs;
     G1X* seg_out = nullptr;
-    GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * (n_threads + W), st));
-    G1X* wsums = seg_out + n_threads;
-    msm_segment_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out);
-    msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs, wsums);
-    ctx->launches += 2;
+    G1X* wsums = nullptr;
+    if (c == 4) {  // tiny windows: one warp per window
+        GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * W, st));
+        wsums = seg_out;
+        msm_window_bits_kernel<<<(W + 3) / 4, 128, 0, st>>>(buckets, W, wsums);
+        ctx->launches++;
+    } else {
+        const int seg_log = c < 3 ? c : 3;
+        const uint32_t segs = 1u << (c - seg_log);
+        const uint64_t n_threads = (uint64_t)W * segs;
+        if (((uint64_t)W << c) >= ((uint64_t)1 << 20) && c >= 9) {  // measured: faster from 2^20 buckets up (MSMs of >= 2^20 points), slower below
+            // two levels: running sums per segment, then the weighted sum of the (pre-scaled) segment totals
+            const int c1 = c - seg_log, seg_log1 = 3;
+            const uint32_t segs1 = 1u << (c1 - seg_log1), stride = segs + segs1;
+            const uint64_t n_threads1 = (uint64_t)W * segs1;
+            GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * ((uint64_t)W * stride + n_threads + W), st));
+            G1X* runs = seg_out + (uint64_t)W * stride;
+            wsums = runs + n_threads;
+            msm_segment_level0_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, stride, runs);
+            msm_segment_kernel<<<(unsigned)((n_threads1 + 127) / 128), 128, 0, st>>>(runs, c1, seg_log1, n_threads1, seg_out + segs, stride);
+            msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, stride, wsums);
+            ctx->launches += 3;
+        } else {
+            GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * (n_threads + W), st));
+            wsums = seg_out + n_threads;
+            msm_segment_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, segs);
+            msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs, wsums);
+            ctx->launches += 2;
+        }
+    }
     GKR_CUDA_OK(ctx, cudaGetLastError());
     h.resize(W);
     GKR_CUDA_OK(ctx, cudaMemcpyAsync(h.data(), wsums, sizeof(G1X) * W, cudaMemcpyDeviceToHost, st));
