@@ -116,27 +116,53 @@ extern "C" int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out) {
 }
 
 // GenericSumcheckProtocol::prove  (src/cleanup/protocols/sumcheck.rs:101-123)
+// GKR_TRACE: where the host time of the round loop goes (printed by gkr_sumcheck_prove_stats_dump)
+static uint64_t g_sc_ns[4] = {0, 0, 0, 0};  // unipoly (launch-to-result wait included), interpolation + transcript, bind, final_evals
+static uint64_t g_sc_rounds = 0;
+extern "C" void gkr_sumcheck_prove_stats_dump(void) {
+    if (!g_sc_rounds) return;
+    fprintf(stderr, "  [gkr_sumcheck_prove] %llu rounds: unipoly %.2f ms, interpolate+transcript %.2f ms, bind %.2f ms, final_evals %.2f ms\n",
+            (unsigned long long)g_sc_rounds, g_sc_ns[0] / 1e6, g_sc_ns[1] / 1e6, g_sc_ns[2] / 1e6, g_sc_ns[3] / 1e6);
+    g_sc_rounds = 0;
+    for (int i = 0; i < 4; i++) g_sc_ns[i] = 0;
+}
+
 extern "C" int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_rounds, uint64_t out_claim[4],
                                   uint64_t* out_point, uint64_t* out_final_evals) {
     if (!t || !so) return GKR_ERR_ARG;
+    static const bool trace = getenv("GKR_TRACE") != nullptr;
     gkr::FrH claim = so->claim();
     std::vector<gkr::FrH> r;
     r.reserve(num_rounds);
+    uint64_t t0 = trace ? gkr_now_ns() : 0;
     for (uint32_t k = 0; k < num_rounds; k++) {
         gkr::FrH ev[GKR_MAX_DEG + 1];
         uint32_t n = 0;
         int rc = so->unipoly(ev, &n);
         if (rc) return rc;
-        std::vector<gkr::FrH> poly = gkr::frh::interpolate_coeffs(ev, (int)n);  // unipoly().as_vec()
-        std::vector<gkr::FrH> msg;                                               // compress_coefficients: drop the linear term
-        msg.push_back(poly[0]);
-        for (size_t i = 2; i < poly.size(); i++) msg.push_back(poly[i]);
-        t->t.write_scalars(msg.data(), msg.size());
+        uint64_t t1 = trace ? gkr_now_ns() : 0;
+        gkr::FrH poly[GKR_MAX_DEG + 1], msg[GKR_MAX_DEG + 1];
+        gkr::frh::interpolate_coeffs_into(ev, (int)n, poly);  // unipoly().as_vec()
+        uint32_t nm = 0;                                       // compress_coefficients: drop the linear term
+        msg[nm++] = poly[0];
+        for (uint32_t i = 2; i < n; i++) msg[nm++] = poly[i];
+        t->t.write_scalars(msg, nm);
         gkr::FrH x = t->t.challenge(128);
         r.push_back(x);
+        uint64_t t2 = trace ? gkr_now_ns() : 0;
         rc = so->bind(x);
         if (rc) return rc;
-        claim = gkr::frh::evaluate_univar(poly, x);
+        gkr::FrH c = gkr::frh::ZERO;  // evaluate_univar(poly, x)
+        for (uint32_t i = n; i-- > 0;) c = gkr::frh::add(gkr::frh::mul(c, x), poly[i]);
+        claim = c;
+        if (trace) {
+            uint64_t t3 = gkr_now_ns();
+            g_sc_ns[0] += t1 - t0;
+            g_sc_ns[1] += t2 - t1;
+            g_sc_ns[2] += t3 - t2;
+            g_sc_rounds++;
+            t0 = t3;
+        }
     }
     if (out_claim) frh_to_limbs(claim, out_claim);
     if (out_point)
@@ -146,6 +172,7 @@ extern "C" int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_ro
         int rc = so->final_evals(fe.data());
         if (rc) return rc;
         for (size_t i = 0; i < fe.size(); i++) frh_to_limbs(fe[i], out_final_evals + 4 * i);
+        if (trace) g_sc_ns[3] += gkr_now_ns() - t0;
     }
     return GKR_OK;
 }

@@ -69,6 +69,7 @@ struct Span {
     }
 };
 
+extern "C" void gkr_sumcheck_prove_stats_dump(void);
 // flat accumulators next to the span tree: host time per sumcheck kind, split into object construction and rounds
 struct TraceAcc {
     struct Row {
@@ -96,6 +97,7 @@ struct TraceAcc {
     }
     static void dump(gkr_ctx* ctx) {
         if (!on()) return;
+        gkr_sumcheck_prove_stats_dump();
         static const char* kinds[3] = {"dense", "deg2 dense", "deg2 ragged"};
         for (int k = 0; k < 3; k++)
             for (int l = 0; l < 40; l++)
