@@ -931,6 +931,54 @@ def g1_sum(points_xy) -> np.ndarray:
     return out
 
 
+class MsmTeam:
+    """Commitment MSMs split by point range over the GPUs of one box (csrc/msm_team.cu).  rank 0 = leader (creates the
+    shared segment and attaches the team to its context), ranks > 0 call serve(srs) and answer until the leader quits."""
+
+    def __init__(self, ctx: Context, name: str, rank: int, world: int, max_n: int, open_timeout_s: float = 60.0):
+        lib = ctx.lib
+        lib.gkr_msm_team_open.restype = C.c_int
+        lib.gkr_msm_team_open.argtypes = [_vp, C.c_char_p, C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(_vp)]
+        lib.gkr_msm_team_serve.restype = C.c_int
+        lib.gkr_msm_team_serve.argtypes = [_vp, _vp, _vp, C.c_double]
+        lib.gkr_msm_team_wait_ready.restype = C.c_int
+        lib.gkr_msm_team_wait_ready.argtypes = [_vp, _vp, C.c_double]
+        lib.gkr_msm_team_quit.restype = None
+        lib.gkr_msm_team_quit.argtypes = [_vp]
+        lib.gkr_msm_team_close.restype = None
+        lib.gkr_msm_team_close.argtypes = [_vp, _vp]
+        self.ctx, self.rank, self.world, self.h = ctx, rank, world, _vp()
+        import time as _time
+        t0 = _time.time()
+        while True:  # workers retry until the leader has created the segment
+            rc = lib.gkr_msm_team_open(ctx.h, name.encode(), rank, world, max_n, 1 if rank == 0 else 0, C.byref(self.h))
+            if rc == 0:
+                break
+            if rank == 0 or _time.time() - t0 > open_timeout_s:
+                ctx.check(rc)
+            _time.sleep(0.05)
+
+    def set_min_n(self, n: int):
+        self.ctx.lib.gkr_msm_team_set_min_n.restype = None
+        self.ctx.lib.gkr_msm_team_set_min_n.argtypes = [_vp, C.c_uint64]
+        self.ctx.lib.gkr_msm_team_set_min_n(self.ctx.h, int(n))
+
+    def serve(self, srs: "Srs", idle_timeout_s: float = 120.0):
+        self.ctx.check(self.ctx.lib.gkr_msm_team_serve(self.ctx.h, self.h, srs.h, float(idle_timeout_s)))
+
+    def wait_ready(self, timeout_s: float = 120.0):
+        self.ctx.check(self.ctx.lib.gkr_msm_team_wait_ready(self.ctx.h, self.h, float(timeout_s)))
+
+    def quit(self):
+        if self.h:
+            self.ctx.lib.gkr_msm_team_quit(self.h)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.gkr_msm_team_close(self.ctx.h, self.h)
+            self.h = None
+
+
 def run_pippenger_native(ctx: Context, transcript: Transcript, srs: "Srs", g0_xy, knuckles: "Knuckles", points_xy, coefs_u64, d_logsize: int,
                          x_logsize: int, num_bits: int, clm: int, r_limbs):
     """benchutils::run_pippenger (pippenger.rs:499-559) with the host orchestration in C++ (csrc/protocol.cu).

@@ -35,6 +35,7 @@ struct RoundOut {  // kernel-side view of a slot
 };
 
 struct Deg2Layout;  // deg2.cu: row layout of the most recent ragged sumcheck bundle
+struct gkr_msm_team;  // msm_team.cu: commitment MSMs split by point range over the GPUs of one box
 
 struct gkr_ctx {
     int device = 0;
@@ -84,6 +85,8 @@ struct gkr_ctx {
     }
     // pinned staging ring for small parameter uploads (one truly asynchronous H2D copy per object instead of a dozen
     // pageable ones, no synchronisation until the ring wraps)
+    gkr_msm_team* team = nullptr;        // leader only: large gkr_msm_g1 calls are shared with the worker ranks
+    uint64_t team_min_n = (uint64_t)1 << 18;
     std::shared_ptr<Deg2Layout> deg2_layout;  // reused by consecutive VecVec objects over the same rows
     unsigned char* stage_host = nullptr;
     size_t stage_size = 0, stage_pos = 0;

@@ -626,12 +626,15 @@ static void msm_host_tail(const std::vector<gkr::G1XH>& h, int c, int W, uint32_
     for (auto& t : th) t.join();
 }
 
-static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems, const gkr_table* scalars,
-                       uint64_t n, uint64_t* out_xy) {
+int gkr_msm_team_run(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr* d_scalars, uint64_t n, uint64_t* out_xy);  // msm_team.cu
+
+static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems, const Fr* d_scalars,
+                       uint64_t n, uint64_t* out_xy, bool allow_team = true) {
     if (!ctx) return GKR_ERR_ARG;
-    if (!srs || !scalars || !out_xy || n_problems == 0) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (!srs || !d_scalars || !out_xy || n_problems == 0) return ctx->fail(GKR_ERR_ARG, "null argument");
     if (first + (uint64_t)(n_problems - 1) * problem_stride + n > srs->n) return ctx->fail(GKR_ERR_ARG, "Vector is too large.");  // kzg.rs:124
-    if (scalars->n < n) return ctx->fail(GKR_ERR_ARG, "fewer scalars than requested");
+    // MSM split by point range over the GPUs of the box (msm_team.cu): affine SRS bases, one problem, large enough to pay
+    if (allow_team && ctx->team && n_problems == 1 && srs->kind == 0 && n >= ctx->team_min_n) return gkr_msm_team_run(ctx, srs, first, d_scalars, n, out_xy);
     if (srs->n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "MSM larger than 2^31 points");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
@@ -653,7 +656,7 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     GKR_CUDA_OK(ctx, gkr_malloc_async(&buckets, sizeof(G1X) * nbk * n_problems, st));
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
-    msm_digits_kernel<<<g1, 256, 0, st>>>(scalars->d, (uint32_t)n, c, W, digits, counts);
+    msm_digits_kernel<<<g1, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, counts);
     msm_scan_kernel<<<W, 1024, 0, st>>>(counts, offsets, c);
     msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, c, W, offsets, cursor, sorted);
     ctx->launches += 3;
@@ -673,14 +676,24 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
 // <bases[first .. first+n), scalars>   scalars: device table of n Fr (Montgomery).  out_xy: affine result, 12 u64
 // (x then y, Montgomery form; all zero for the point at infinity).
 extern "C" int gkr_msm_g1(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
-    return msm_g1_impl(ctx, srs, first, 0, 1, scalars, n, out_xy);
+    if (!ctx) return GKR_ERR_ARG;
+    if (!scalars) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (scalars->n < n) return ctx->fail(GKR_ERR_ARG, "fewer scalars than requested");
+    return msm_g1_impl(ctx, srs, first, 0, 1, scalars->d, n, out_xy);
+}
+// the local bucket MSM on this GPU over raw device scalars, never delegated to a team (used by both sides of msm_team.cu)
+int gkr_msm_g1_local(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr* d_scalars, uint64_t n, uint64_t* out_xy) {
+    return msm_g1_impl(ctx, srs, first, 0, 1, d_scalars, n, out_xy, false);
 }
 // `n_problems` MSMs with the SAME scalars over the base ranges [first + p * problem_stride, + n): the c_pull / d_pull
 // commitments of PushForwardState::second_phase (one msm_nonaff per commitment chunk over that chunk's bucket sums with
 // eq_c / eq_d as scalars, pushforward.rs:598-604).  The digit sort is shared; out_xy: n_problems x 12 u64.
 extern "C" int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
                                 const gkr_table* scalars, uint64_t n, uint64_t* out_xy) {
-    return msm_g1_impl(ctx, srs, first, problem_stride, n_problems, scalars, n, out_xy);
+    if (!ctx) return GKR_ERR_ARG;
+    if (!scalars) return ctx->fail(GKR_ERR_ARG, "null argument");
+    if (scalars->n < n) return ctx->fail(GKR_ERR_ARG, "fewer scalars than requested");
+    return msm_g1_impl(ctx, srs, first, problem_stride, n_problems, scalars->d, n, out_xy);
 }
 
 

@@ -228,6 +228,19 @@ int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t f
 int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
                      const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
 int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
+/* Commitment MSM split by point range over the GPUs of one box (csrc/msm_team.cu).  One process per GPU, every
+ * rank holds the same SRS.  The leader (rank 0, `create` = 1, opened first) attaches the team to its context: from then on
+ * every gkr_msm_g1 of at least 2^18 points over affine bases is cut into `world` slices; the workers answer from
+ * gkr_msm_team_serve (returns GKR_OK after gkr_msm_team_quit, an error after `idle_timeout_s` without a command).  The result
+ * is the same point and the same limbs as the single-GPU call. */
+typedef struct gkr_msm_team gkr_msm_team;
+int gkr_msm_team_open(gkr_ctx* ctx, const char* name, int rank, int world, uint64_t max_n, int create, gkr_msm_team** out);
+int gkr_msm_team_serve(gkr_ctx* ctx, gkr_msm_team* team, const gkr_srs* srs, double idle_timeout_s);
+int gkr_msm_team_wait_ready(gkr_ctx* ctx, gkr_msm_team* team, double timeout_s);
+void gkr_msm_team_quit(gkr_msm_team* team);
+int gkr_msm_team_world(const gkr_msm_team* team);
+void gkr_msm_team_set_min_n(gkr_ctx* ctx, uint64_t n); /* smallest MSM shared with the team (default 2^18 points) */
+void gkr_msm_team_close(gkr_ctx* ctx, gkr_msm_team* team);
 /* test hook, host only: the O(windows) tail of every MSM (Horner over the extended-Jacobian window sums X, Y, ZZ, ZZZ --
  * 24 u64 each -- with c doublings per window, then one inversion to affine) runs on the CPU; see csrc/host_g1.hpp. */
 int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_windows, uint64_t* out_xy);

@@ -20,6 +20,21 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
+def team_worker(args):
+    """rank > 0 of `--gpus N`: same SRS on cuda:rank, then serve slices of the leader's commitment MSMs (csrc/msm_team.cu)"""
+    import gkr_msm_b200 as g
+    from gkr_msm_b200 import hostmath as H
+    from gkr_msm_b200 import pippenger as DPP
+
+    ctx = g.Context(args.team_worker)
+    nv = args.x_logsize + args.clm
+    kzg = DPP.KzgKey.mock_setup(ctx, int(args.team_tau, 16), H.G1_GEN, 2 * (1 << nv) - 1)
+    team = g.MsmTeam(ctx, args.team_name, args.team_worker, args.gpus, 2 * (1 << nv))
+    team.serve(kzg.srs, idle_timeout_s=300.0)
+    team.close()
+    ctx.close()
+
+
 def run(args, ctx=None):
     import gkr_msm_b200 as g
     from gkr_msm_b200 import hostmath as H
@@ -51,6 +66,15 @@ def run(args, ctx=None):
     key = DPP.KnucklesKey(ctx, kzg, nv, 2)
     ctx.sync()
     t_setup = time.perf_counter() - t0
+    team, workers = None, []
+    if getattr(args, "gpus", 1) > 1:  # commitment MSMs split by point range over N GPUs: this process leads, N - 1 workers serve
+        import subprocess
+        name = f"/gkr_msm_team_{os.getpid()}"
+        team = g.MsmTeam(ctx, name, 0, args.gpus, 2 * (1 << nv))
+        for rk in range(1, args.gpus):
+            workers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--x-logsize", str(xl), "--clm", str(clm), "--gpus", str(args.gpus),
+                                             "--team-worker", str(rk), "--team-name", name, "--team-tau", "%x" % tau]))
+        team.wait_ready(timeout_s=300.0)
 
     times, proof_len, launches = [], 0, 0
     for rep in range(args.reps):
@@ -83,12 +107,18 @@ def run(args, ctx=None):
         print(f"  round kernels: {waits} result waits, {nw / 1e6:.2f} ms spinning on results ({nw / 1e3 / max(waits, 1):.1f} us each), "
               f"{nl / 1e6:.2f} ms inside launch calls", file=sys.stderr)
         PR.PROFILE = None
+    if team is not None:
+        team.quit()
+        for w in workers:
+            w.wait(timeout=120)
+        team.close()
     best = min(times)
     return ({
         "bench": "run_pippenger (witness + commit + prove)", "host": "python" if args.python_host else "c++ (gkr_run_pippenger)", "x_logsize": xl, "d_logsize": dl, "nbits": nbits, "clm": clm,
         "y_size": cfg["y_size"], "incidences": cfg["y_size"] << xl, "prove_ms_best": best * 1e3, "prove_ms_all": [t * 1e3 for t in times],
         "proof_bytes": proof_len, "gpu_launches": launches, "input_generation_s": t_inputs, "srs_setup_s": t_setup,
-        "srs_points": 2 * (1 << nv) - 1,
+        "srs_points": 2 * (1 << nv) - 1, "n_gpus": getattr(args, "gpus", 1),
+        "multi_gpu": "commitment MSMs of >= 2^18 points split by point range over the GPUs (csrc/msm_team.cu); everything else on GPU 0" if getattr(args, "gpus", 1) > 1 else None,
         "round_waits": hs[2], "round_wait_ms": hs[1] / 1e6, "round_launch_call_ms": hs[0] / 1e6})
 
 
@@ -102,7 +132,15 @@ def main():
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--profile", action="store_true", help="print a per-phase breakdown of the last repetition (python host)")
     ap.add_argument("--python-host", action="store_true", help="time the python orchestration instead of gkr_run_pippenger (C++)")
-    print(json.dumps(run(ap.parse_args())), flush=True)
+    ap.add_argument("--gpus", type=int, default=1, help="N > 1: spawn N - 1 worker processes (cuda:1..N-1) that share the large commitment MSMs")
+    ap.add_argument("--team-worker", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--team-name", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--team-tau", default="", help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.team_worker > 0:
+        team_worker(args)
+        return
+    print(json.dumps(run(args)), flush=True)
 
 
 if __name__ == "__main__":
