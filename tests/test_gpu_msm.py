@@ -121,3 +121,38 @@ def test_msm_skewed_buckets(ctx, kind):
     for p, s in zip(pts, sc):
         tot[p] = (tot.get(p, 0) + s) % P
     assert got == CV.g1_msm(list(tot.keys()), list(tot.values()))
+
+
+@pytest.mark.parametrize("log_n", [18, 20])
+def test_msm_large_closed_form(ctx, log_n):
+    """Sizes the textbook oracle cannot reach (2^20 points: window reduction in two levels, >= 2^20 buckets): over the mock
+    SRS tau^i * g0 (kzg.rs:84-97) the commitment is (sum_i s_i tau^i) * g0 -- the shortcut the reference's own mock setup
+    makes possible -- so the device result is checked against one host scalar multiplication."""
+    from gkr_msm_b200 import hostmath as H
+
+    n = 1 << log_n
+    tau = 0x5DEECE66D1234567890ABCDEF0123456789ABCDEF0FEDCBA9876543210F00D
+    srs = g.Srs.mock_setup(ctx, to_limbs([tau])[0], H.g1_to_limbs(CV.G1_GEN), n)
+    sc = ctx.synth(1234 + log_n, n)
+    got = res_to_point(srs.msm(sc))
+    vals = from_limbs_fast(sc.download())
+    acc, pw = 0, 1
+    for v in vals:
+        acc = (acc + v * pw) % P
+        pw = pw * tau % P
+    assert got == CV.g1_mul(acc, CV.G1_GEN)
+    # a sub-range with an offset into the SRS: sum_{i < m} s_i tau^(first + i)
+    first, m = 12345, n - 20000
+    got2 = res_to_point(srs.msm(sc, n=m, first=first))
+    acc2, pw = 0, pow(tau, first, P)
+    for v in vals[:m]:
+        acc2 = (acc2 + v * pw) % P
+        pw = pw * tau % P
+    assert got2 == CV.g1_mul(acc2, CV.G1_GEN)
+
+
+def from_limbs_fast(arr):
+    """Montgomery u64 limbs -> ints (vectorised split, python big-int reduction)"""
+    a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
+    rinv = pow(1 << 256, -1, P)
+    return [((int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192)) * rinv) % P for r in a]
