@@ -605,6 +605,12 @@ class Srs:
         self.ctx.check(self.ctx.lib.gkr_msm_g1(self.ctx.h, self.h, first, scalars.h, n, _ptr(out)))
         return out
 
+    def precompute(self, c: int = 20):
+        """fixed-base window table T[k][i] = 2^(c k) P_i (proving-key preprocessing, see include/gkr_msm_b200.h)"""
+        self.ctx.lib.gkr_srs_precompute.restype = C.c_int
+        self.ctx.lib.gkr_srs_precompute.argtypes = [_vp, _vp, C.c_int]
+        self.ctx.check(self.ctx.lib.gkr_srs_precompute(self.ctx.h, self.h, int(c)))
+
     def msm_batch(self, scalars: "Table", n: int, first: int, stride: int, count: int) -> np.ndarray:
         """`count` MSMs with the same scalars over the base ranges [first + p * stride, + n): (count, 12) affine results."""
         out = np.zeros((count, 12), np.uint64)

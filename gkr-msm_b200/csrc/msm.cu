@@ -185,6 +185,27 @@ __global__ void msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, int c
     }
 }
 
+// exclusive scan of ONE long histogram (the 2^c buckets of the fixed-base path) in 1024-entry tiles:
+// tile-local scan + tile totals, msm_scan_kernel over the totals, then the tile bases are added
+__global__ void msm_scan_tiles_kernel(const uint32_t* counts, uint32_t* offsets, uint32_t* tile_sums) {
+    __shared__ uint32_t tmp[1024];
+    const size_t i = (size_t)blockIdx.x * 1024 + threadIdx.x;
+    const uint32_t v = counts[i];
+    tmp[threadIdx.x] = v;
+    __syncthreads();
+    for (uint32_t s = 1; s < 1024; s <<= 1) {
+        uint32_t t = threadIdx.x >= s ? tmp[threadIdx.x - s] : 0;
+        __syncthreads();
+        tmp[threadIdx.x] += t;
+        __syncthreads();
+    }
+    offsets[i] = tmp[threadIdx.x] - v;
+    if (threadIdx.x == 1023) tile_sums[blockIdx.x] = tmp[1023];
+}
+__global__ void msm_scan_add_kernel(uint32_t* offsets, const uint32_t* tile_offs) {
+    offsets[(size_t)blockIdx.x * 1024 + threadIdx.x] += tile_offs[blockIdx.x];
+}
+
 __global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, int n_windows, const uint32_t* offsets, uint32_t* cursor,
                                    uint32_t* sorted /* [W][n] */) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -448,6 +469,68 @@ __global__ void __launch_bounds__(128) msm_window_bits_kernel(const G1X* buckets
     if (lane == 0) window_sums[w] = acc;
 }
 
+// ---- fixed-base windows (gkr_srs_precompute) ----------------------------------------------------------------------------
+// The SRS of a proving key is fixed, so the window shifts can be paid once: with T[k][i] = 2^(c k) P_i resident, digit k of
+// scalar i selects T[k][i] and ALL windows fall into ONE set of 2^c buckets,
+//     sum_i s_i P_i = sum_d d * (sum of the T[k][i] with digit_k(s_i) == d).
+// That removes the per-window bucket sets (c can grow to 20: 13 instead of 16 additions per 255-bit scalar), the per-window
+// running-sum reductions and the Horner tail over the windows.
+__global__ void __launch_bounds__(128) srs_precompute_kernel(const G1Aff* P, uint64_t n, int c, int n_windows, G1Aff* T) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const G1Aff p = P[i];
+        T[i] = p;
+        if (g1a_is_inf(p)) {
+            for (int k = 1; k < n_windows; k++) T[(size_t)k * n + i] = p;
+            continue;
+        }
+        G1X cur;
+        cur.X = p.x; cur.Y = p.y; cur.ZZ = fq_one(); cur.ZZZ = fq_one();
+        for (int k = 1; k < n_windows; k++) {
+            for (int j = 0; j < c; j++) cur = g1x_dbl(cur);
+            G1Aff r;
+            if (g1x_is_inf(cur)) {
+                r.x = fq_zero(); r.y = fq_zero();
+            } else {
+                // one inversion: 1/ZZZ, then 1/ZZ = ZZZ^-1 * ZZZ / ZZ ... use 1/ZZ = (ZZ * ZZZ^-1)^2 (ZZ^3 == ZZZ^2)
+                const Fq izzz = fq_inv(cur.ZZZ);
+                const Fq t = fq_mul(cur.ZZ, izzz);  // = 1 / sqrt(ZZ) up to the curve relation: (ZZ / ZZZ)^2 = 1 / ZZ
+                r.x = fq_mul(cur.X, fq_sqr(t));
+                r.y = fq_mul(cur.Y, izzz);
+            }
+            T[(size_t)k * n + i] = r;
+        }
+    }
+}
+
+// digits of all windows into one histogram; entry e = k * n + i
+__global__ void msm_digits_pre_kernel(const Fr* scalars, uint32_t n, int c, int n_windows, uint32_t* digits /* [W][n] */, uint32_t* counts /* [2^c] */) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Fr one_raw = fr_zero();
+        one_raw.l[0] = 1;
+        Fr s = fr_mul(scalars[i], one_raw);  // the canonical integer
+        for (int w = 0; w < n_windows; w++) {
+            const int bit = w * c, limb = bit >> 5, sh = bit & 31;
+            uint64_t v = s.l[limb];
+            if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
+            const uint32_t d = (uint32_t)(v >> sh) & ((1u << c) - 1);
+            digits[(size_t)w * n + i] = d;
+            if (d) atomicAdd(&counts[d], 1u);
+        }
+    }
+}
+// sorted[offsets[d] + pos] = index of T[k][first + i] in the table of `srs_n` points per window
+__global__ void msm_scatter_pre_kernel(const uint32_t* digits, uint32_t n, int n_windows, uint32_t first, uint32_t srs_n, const uint32_t* offsets,
+                                       uint32_t* cursor, uint32_t* sorted) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        for (int w = 0; w < n_windows; w++) {
+            const uint32_t d = digits[(size_t)w * n + i];
+            if (!d) continue;
+            const uint32_t pos = atomicAdd(&cursor[d], 1u);
+            sorted[offsets[d] + pos] = (uint32_t)w * srs_n + first + i;
+        }
+    }
+}
+
 // window_sums[w] = sum of the window's segment contributions (strided partial sums + shared-memory tree)
 __global__ void __launch_bounds__(256) msm_window_tree_kernel(const G1X* seg_out, uint32_t segs, G1X* window_sums) {
     extern __shared__ unsigned char smem_raw[];
@@ -474,6 +557,9 @@ struct gkr_srs {
     void* d = nullptr;
     uint64_t n = 0;
     int kind = 0;  // 0: affine (x, y) 2x6 u64; 1: Jacobian (X, Y, Z) 3x6 u64; 2: XYZZ 4x6 u64 (device-produced bucket sums)
+    // gkr_srs_precompute: pre[k * n + i] = 2^(pre_c * k) * P_i for k = 0 .. pre_w - 1 (affine; k = 0 is a copy of d)
+    G1Aff* pre = nullptr;
+    int pre_c = 0, pre_w = 0;
     size_t stride() const { return kind == 0 ? sizeof(G1Aff) : (kind == 1 ? 3 * sizeof(Fq) : sizeof(G1X)); }
 };
 
@@ -501,6 +587,7 @@ extern "C" uint64_t gkr_srs_len(const gkr_srs* s) { return s ? s->n : 0; }
 
 extern "C" void gkr_srs_free(gkr_srs* s) {
     if (!s) return;
+    if (s->pre) gkr_free_async(s->pre, s->ctx->stream);
     if (s->d) gkr_free_async(s->d, s->ctx->stream);
     delete s;
 }
@@ -628,6 +715,96 @@ static void msm_host_tail(const std::vector<gkr::G1XH>& h, int c, int W, uint32_
 
 int gkr_msm_team_run(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr* d_scalars, uint64_t n, uint64_t* out_xy);  // msm_team.cu
 
+// Fixed-base window table of an affine SRS (proving-key preprocessing, not part of a proof): (n_windows - 1) * n more points.
+extern "C" int gkr_srs_precompute(gkr_ctx* ctx, gkr_srs* srs, int c) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!srs || srs->kind != 0 || c < 12 || c > 22 || srs->n == 0) return ctx->fail(GKR_ERR_ARG, "gkr_srs_precompute: affine SRS and 12 <= c <= 22");
+    const int W = (255 + c - 1) / c;
+    if ((uint64_t)W * srs->n >= ((uint64_t)1 << 32)) return ctx->fail(GKR_ERR_UNSUPPORTED, "gkr_srs_precompute: table index does not fit 32 bits");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (srs->pre) gkr_free_async(srs->pre, ctx->stream);
+    srs->pre = nullptr;
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&srs->pre, sizeof(G1Aff) * (size_t)W * srs->n, ctx->stream));
+    unsigned g = (unsigned)std::min<uint64_t>((srs->n + 127) / 128, (uint64_t)ctx->num_sms * 16);
+    srs_precompute_kernel<<<g, 128, 0, ctx->stream>>>((const G1Aff*)srs->d, srs->n, c, W, srs->pre);
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    srs->pre_c = c;
+    srs->pre_w = W;
+    return GKR_OK;
+}
+
+// One bucket set for all windows over the fixed-base table.  The 2^c buckets are reduced as V = 2^(c - 14) chunks of 2^14:
+// chunk j contributes S_j = sum_{d in chunk} (d - j 2^14) B_d (the device window sums with c' = 14) plus j 2^14 R_j with
+// R_j = sum_{d in chunk} B_d; the V pairs go to the host, which finishes with a running sum over the R_j.
+static int msm_g1_pre(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr* d_scalars, uint64_t n, uint64_t* out_xy) {
+    cudaStream_t st = ctx->stream;
+    const int c = srs->pre_c, W = srs->pre_w, cc = c < 14 ? c : 14;
+    const size_t nbk = (size_t)1 << c;
+    const uint32_t V = 1u << (c - cc);
+    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr;
+    G1X* buckets = nullptr;
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&digits, sizeof(uint32_t) * W * n, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&sorted, sizeof(uint32_t) * W * n, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS), st));
+    uint32_t *offsets = counts + nbk, *cursor = counts + 2 * nbk, *work = counts + 3 * nbk;
+    const uint32_t parts = (uint32_t)(nbk >> 10) ? (uint32_t)(nbk >> 10) : 1;  // partial sums of 1024 buckets each
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&buckets, sizeof(G1X) * (nbk + V + parts), st));
+    G1X* chunk_sums = buckets + nbk;
+    G1X* part_sums = chunk_sums + V;
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
+    unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    msm_digits_pre_kernel<<<g1, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, counts);
+    if (c >= 12) {  // tiled scan: `cursor` (still zero) doubles as scratch for the tile totals / bases and is cleared again
+        const uint32_t tiles = 1u << (c - 10);
+        uint32_t *tile_sums = cursor, *tile_offs = cursor + tiles;
+        msm_scan_tiles_kernel<<<tiles, 1024, 0, st>>>(counts, offsets, tile_sums);
+        msm_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tile_offs, c - 10);
+        msm_scan_add_kernel<<<tiles, 1024, 0, st>>>(offsets, tile_offs);
+        GKR_CUDA_OK(ctx, cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * 2 * tiles, st));
+        ctx->launches += 2;
+    } else {
+        msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, c);
+    }
+    msm_scatter_pre_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, W, (uint32_t)first, (uint32_t)srs->n, offsets, cursor, sorted);
+    ctx->launches += 3;
+    std::vector<gkr::G1XH> hs, hr(V);
+    int rc = msm_accumulate(ctx, srs->pre, 0, sorted, counts, offsets, (uint32_t)((uint64_t)W * n), c, nbk, (uint64_t)W * n, work, buckets);
+    if (rc == GKR_OK) {
+        if (nbk >= 1024 && parts >= V) {  // plain chunk sums R_j in two stages, so that the first one fills the machine
+            msm_window_tree_kernel<<<parts, 256, sizeof(G1X) * 256, st>>>(buckets, 1024, part_sums);
+            msm_window_tree_kernel<<<V, 256, sizeof(G1X) * 256, st>>>(part_sums, parts / V, chunk_sums);
+            ctx->launches += 2;
+        } else {
+            msm_window_tree_kernel<<<V, 256, sizeof(G1X) * 256, st>>>(buckets, 1u << cc, chunk_sums);
+            ctx->launches++;
+        }
+        rc = msm_window_sums(ctx, buckets, cc, V, hs);  // synchronises
+    }
+    if (rc == GKR_OK) {
+        cudaError_t e = cudaMemcpyAsync(hr.data(), chunk_sums, sizeof(G1X) * V, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    gkr_free_async(digits, st);
+    gkr_free_async(sorted, st);
+    gkr_free_async(counts, st);
+    gkr_free_async(buckets, st);
+    if (rc) return rc;
+    using namespace gkr::g1h;
+    gkr::G1XH total = inf(), run = inf(), wsum = inf();
+    for (uint32_t j = V; j-- > 1;) {  // wsum = sum_j j R_j by descending running sums
+        run = add(run, hr[j]);
+        wsum = add(wsum, run);
+    }
+    for (int k = 0; k < cc; k++) wsum = dbl(wsum);
+    for (uint32_t j = 0; j < V; j++) total = add(total, hs[j]);
+    total = add(total, wsum);
+    to_affine(total, out_xy);
+    return GKR_OK;
+}
+
 static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems, const Fr* d_scalars,
                        uint64_t n, uint64_t* out_xy, bool allow_team = true) {
     if (!ctx) return GKR_ERR_ARG;
@@ -635,6 +812,11 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     if (first + (uint64_t)(n_problems - 1) * problem_stride + n > srs->n) return ctx->fail(GKR_ERR_ARG, "Vector is too large.");  // kzg.rs:124
     // MSM split by point range over the GPUs of the box (msm_team.cu): affine SRS bases, one problem, large enough to pay
     if (allow_team && ctx->team && n_problems == 1 && srs->kind == 0 && n >= ctx->team_min_n) return gkr_msm_team_run(ctx, srs, first, d_scalars, n, out_xy);
+    // fixed-base window table present and enough entries per bucket to pay for reducing 2^c buckets
+    if (srs->pre && n_problems == 1 && n > 0 && (uint64_t)srs->pre_w * n >= ((uint64_t)4 << srs->pre_c)) {
+        GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        return msm_g1_pre(ctx, srs, first, d_scalars, n, out_xy);
+    }
     if (srs->n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "MSM larger than 2^31 points");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

@@ -51,9 +51,14 @@ class KzgKey:
         self.ctx, self.srs, self.g0 = ctx, srs, np.asarray(g0_xy, dtype=np.uint64).reshape(12)
 
     @staticmethod
-    def mock_setup(ctx, tau: int, g0, size: int) -> "KzgKey":  # kzg.rs:84-97
+    def mock_setup(ctx, tau: int, g0, size: int, precompute_c: int = 0) -> "KzgKey":  # kzg.rs:84-97
+        """precompute_c > 0: also build the fixed-base window table of the SRS (gkr_srs_precompute) -- proving-key
+        preprocessing that pays from about 2^19 points per commitment"""
         g0_xy = H.g1_to_limbs(g0)
-        return KzgKey(ctx, g.Srs.mock_setup(ctx, to_limb1(tau), g0_xy, size), g0_xy)
+        srs = g.Srs.mock_setup(ctx, to_limb1(tau), g0_xy, size)
+        if precompute_c:
+            srs.precompute(precompute_c)
+        return KzgKey(ctx, srs, g0_xy)
 
     @property
     def size(self):

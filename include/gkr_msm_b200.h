@@ -228,6 +228,10 @@ int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t f
 int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
                      const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
 int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
+/* Proving-key preprocessing (not part of a proof): fixed-base window table T[k][i] = 2^(c k) P_i of an affine SRS, (ceil(255 / c) - 1) n
+ * more points in HBM.  With it gkr_msm_g1 sends all windows of a scalar into ONE set of 2^c buckets (13 instead of 16 additions per
+ * 255-bit scalar at c = 20, no per-window reductions, no Horner tail).  Used for MSMs with at least 4 * 2^c / windows points. */
+int gkr_srs_precompute(gkr_ctx* ctx, gkr_srs* srs, int c);
 /* Commitment MSM split by point range over the GPUs of one box (csrc/msm_team.cu).  One process per GPU, every
  * rank holds the same SRS.  The leader (rank 0, `create` = 1, opened first) attaches the team to its context: from then on
  * every gkr_msm_g1 of at least 2^18 points over affine bases is cut into `world` slices; the workers answer from

@@ -135,6 +135,9 @@ def test_msm_large_closed_form(ctx, log_n):
     srs = g.Srs.mock_setup(ctx, to_limbs([tau])[0], H.g1_to_limbs(CV.G1_GEN), n)
     sc = ctx.synth(1234 + log_n, n)
     got = res_to_point(srs.msm(sc))
+    if log_n == 20:  # the same through the fixed-base window table (c = 20: what the 2^20-point prover uses)
+        srs.precompute(20)
+        assert res_to_point(srs.msm(sc)) == got
     vals = from_limbs_fast(sc.download())
     acc, pw = 0, 1
     for v in vals:
@@ -149,6 +152,32 @@ def test_msm_large_closed_form(ctx, log_n):
         acc2 = (acc2 + v * pw) % P
         pw = pw * tau % P
     assert got2 == CV.g1_mul(acc2, CV.G1_GEN)
+
+
+@pytest.mark.parametrize("n,c", [(5000, 12), (70000, 14), (300, 12)])
+def test_msm_fixed_base_table_equals_plain(ctx, n, c):
+    """gkr_srs_precompute: the one-bucket-set MSM over T[k][i] = 2^(c k) P_i gives the same point as the windowed MSM and
+    as the closed form over the mock SRS; small / offset calls fall back or index the table correctly."""
+    from gkr_msm_b200 import hostmath as H
+
+    tau = 0x1F2E3D4C5B6A79880123456789ABCDEF
+    srs = g.Srs.mock_setup(ctx, to_limbs([tau])[0], H.g1_to_limbs(CV.G1_GEN), n)
+    sc = ctx.synth(99 + n, n)
+    plain = srs.msm(sc)
+    plain_part = srs.msm(sc, n=n - 7, first=5)
+    srs.precompute(c)
+    assert np.array_equal(srs.msm(sc), plain)
+    assert np.array_equal(srs.msm(sc, n=n - 7, first=5), plain_part)
+    vals = from_limbs_fast(sc.download())
+    acc, pw = 0, 1
+    for v in vals:
+        acc = (acc + v * pw) % P
+        pw = pw * tau % P
+    assert res_to_point(plain) == CV.g1_mul(acc, CV.G1_GEN)
+    # zeros, ones and r - 1 as scalars
+    edge = ctx.upload(to_limbs([0, 1, P - 1] * (n // 3) + [0] * (n % 3)))
+    srs2 = g.Srs.mock_setup(ctx, to_limbs([tau])[0], H.g1_to_limbs(CV.G1_GEN), n)
+    assert np.array_equal(srs.msm(edge), srs2.msm(edge))
 
 
 def from_limbs_fast(arr):

@@ -14,12 +14,15 @@ from gkr_msm_b200 import hostmath as H  # noqa: E402
 from gkr_msm_b200.fieldutil import to_limb1  # noqa: E402
 
 ctx = g.Context(0)
+PRE = int(os.environ.get("MSM_PRE_C", "0"))  # fixed-base window table (gkr_srs_precompute) with this window, 0 = none
 for log_n in [int(a) for a in sys.argv[1:]] or [16, 18, 20, 22]:
     n = 1 << log_n
     t0 = time.perf_counter()
     srs = g.Srs.mock_setup(ctx, to_limb1(0x1234567890ABCDEF1234567), H.g1_to_limbs(H.G1_GEN), n)
     ctx.sync()
     t_srs = time.perf_counter() - t0
+    if PRE:
+        srs.precompute(PRE)
     sc = ctx.synth(77, n)
     srs.msm(sc)  # warm-up
     ts = []
