@@ -937,6 +937,27 @@ def g1_sum(points_xy) -> np.ndarray:
     return out
 
 
+def binary_msm_prepare(ctx: Context, bases: "Srs", gamma: int) -> "Srs":
+    """prepare_bases (src/binary_msm.rs:44-50) on the device: per chunk of `gamma` bases its 2^gamma - 1 subset sums, affine."""
+    ctx.lib.gkr_binary_msm_prepare.restype = C.c_int
+    ctx.lib.gkr_binary_msm_prepare.argtypes = [_vp, _vp, C.c_uint32, C.POINTER(_vp)]
+    h = _vp()
+    ctx.check(ctx.lib.gkr_binary_msm_prepare(ctx.h, bases.h, gamma, C.byref(h)))
+    out = Srs.__new__(Srs)
+    out.ctx, out.h, out.n = ctx, h, int(ctx.lib.gkr_srs_len(h))
+    return out
+
+
+def binary_msm(ctx: Context, prepared: "Srs", gamma: int, coefs) -> np.ndarray:
+    """binary_msm (src/binary_msm.rs:19-29): coefs = prepare_coefs' bytes, one per chunk; affine result (12,) uint64."""
+    ctx.lib.gkr_binary_msm.restype = C.c_int
+    ctx.lib.gkr_binary_msm.argtypes = [_vp, _vp, C.c_uint32, _vp, C.c_uint64, _vp]
+    co = np.ascontiguousarray(coefs, dtype=np.uint8).reshape(-1)
+    out = np.zeros(12, np.uint64)
+    ctx.check(ctx.lib.gkr_binary_msm(ctx.h, prepared.h, gamma, _ptr(co), co.shape[0], _ptr(out)))
+    return out
+
+
 class MsmTeam:
     """Commitment MSMs split by point range over the GPUs of one box (csrc/msm_team.cu).  rank 0 = leader (creates the
     shared segment and attaches the team to its context), ranks > 0 call serve(srs) and answer until the leader quits."""

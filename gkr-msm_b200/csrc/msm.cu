@@ -1173,3 +1173,102 @@ extern "C" int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_wind
     gkr::g1h::horner_windows(h.data(), c, n_windows, out_xy);
     return GKR_OK;
 }
+
+
+// ---- binary_msm (old API): commitments to bit columns  (src/binary_msm.rs:19-54, gkr_msm_simple.rs:62-68) ---
+// prepare_bases: every chunk of `gamma` consecutive bases becomes the table of its 2^gamma - 1 non-empty subset sums (affine),
+//   entry i - 1 = sum of chunk[len - 1 - idx] over the set bits idx of i   (prepare_chunk zips 0..gamma with chunk.iter().rev());
+// binary_msm: coefs[k] in [0, 2^gamma) selects entry coefs[k] - 1 of chunk k (0: nothing); the result is the plain sum.
+__global__ void __launch_bounds__(128) binmsm_prepare_kernel(const G1Aff* bases, uint64_t n, uint32_t gamma, uint64_t n_chunks, G1Aff* out) {
+    const uint32_t per = (1u << gamma) - 1;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks * per; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t k = t / per;
+        const uint32_t i = (uint32_t)(t % per) + 1;
+        const uint64_t b0 = k * gamma;
+        const uint32_t len = (uint32_t)(b0 + gamma <= n ? gamma : n - b0);
+        G1X acc = g1x_inf();
+        for (uint32_t idx = 0; idx < len; idx++)
+            if ((i >> idx) & 1u) g1x_madd_i(acc, bases[b0 + len - 1 - idx]);
+        G1Aff r;
+        if (g1x_is_inf(acc)) {
+            r.x = fq_zero(); r.y = fq_zero();
+        } else {
+            const Fq izzz = fq_inv(acc.ZZZ);
+            const Fq u = fq_mul(acc.ZZ, izzz);  // (ZZ / ZZZ)^2 == 1 / ZZ
+            r.x = fq_mul(acc.X, fq_sqr(u));
+            r.y = fq_mul(acc.Y, izzz);
+        }
+        out[t] = r;
+    }
+}
+// strided partial sums of the selected table entries, one partial per block
+__global__ void __launch_bounds__(256) binmsm_sum_kernel(const G1Aff* table, uint32_t per, const uint8_t* coefs, uint64_t n_chunks, G1X* partial) {
+    extern __shared__ unsigned char smem_raw[];
+    G1X* sh = reinterpret_cast<G1X*>(smem_raw);
+    G1X acc = g1x_inf();
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_chunks; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = coefs[k];
+        if (c) g1x_madd_i(acc, table[k * per + (c - 1)]);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    msm_group_tree(sh, threadIdx.x, blockDim.x, true);
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+extern "C" int gkr_binary_msm_prepare(gkr_ctx* ctx, const gkr_srs* bases, uint32_t gamma, gkr_srs** prepared) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!bases || !prepared || bases->kind != 0 || gamma == 0 || gamma > 8) return ctx->fail(GKR_ERR_ARG, "gkr_binary_msm_prepare: affine bases, 1 <= gamma <= 8");
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n_chunks = (bases->n + gamma - 1) / gamma, per = ((uint64_t)1 << gamma) - 1;
+    gkr_srs* s = new gkr_srs();
+    s->ctx = ctx;
+    s->kind = 0;
+    s->n = n_chunks * per;
+    cudaError_t e = gkr_malloc_async(&s->d, sizeof(G1Aff) * std::max<uint64_t>(s->n, 1), ctx->stream);
+    if (e != cudaSuccess) { delete s; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
+    if (s->n) {
+        unsigned g = (unsigned)std::min<uint64_t>((s->n + 127) / 128, (uint64_t)ctx->num_sms * 16);
+        binmsm_prepare_kernel<<<g, 128, 0, ctx->stream>>>((const G1Aff*)bases->d, bases->n, gamma, n_chunks, (G1Aff*)s->d);
+        ctx->launches++;
+    }
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { gkr_srs_free(s); return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
+    *prepared = s;
+    return GKR_OK;
+}
+
+extern "C" int gkr_binary_msm(gkr_ctx* ctx, const gkr_srs* prepared, uint32_t gamma, const uint8_t* coefs, uint64_t n_chunks, uint64_t* out_xy) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!prepared || !out_xy || (!coefs && n_chunks) || prepared->kind != 0 || gamma == 0 || gamma > 8) return ctx->fail(GKR_ERR_ARG, "gkr_binary_msm: bad arguments");
+    const uint32_t per = (1u << gamma) - 1;
+    if (n_chunks * per != prepared->n) return ctx->fail(GKR_ERR_ARG, "gkr_binary_msm: coefs.len() != bases.len()");  // binary_msm.rs:21
+    for (uint64_t k = 0; k < n_chunks; k++)
+        if (coefs[k] > per) return ctx->fail(GKR_ERR_ARG, "gkr_binary_msm: coefficient out of range (the reference indexes out of bounds)");
+    std::memset(out_xy, 0, 96);
+    if (n_chunks == 0) return GKR_OK;
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n_chunks + 255) / 256, (uint64_t)ctx->num_sms * 2));
+    uint8_t* d_coefs = nullptr;
+    G1X* partial = nullptr;
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_coefs, n_chunks, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&partial, sizeof(G1X) * (blocks + 1), st));
+    int rc = gkr_stage_upload(ctx, d_coefs, coefs, n_chunks);
+    gkr::G1XH h;
+    if (rc == GKR_OK) {
+        binmsm_sum_kernel<<<blocks, 256, sizeof(G1X) * 256, st>>>((const G1Aff*)prepared->d, per, d_coefs, n_chunks, partial);
+        msm_window_tree_kernel<<<1, 256, sizeof(G1X) * 256, st>>>(partial, blocks, partial + blocks);
+        ctx->launches += 2;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&h, partial + blocks, sizeof(G1X), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+    }
+    gkr_free_async(d_coefs, st);
+    gkr_free_async(partial, st);
+    if (rc) return rc;
+    gkr::g1h::to_affine(h, out_xy);
+    return GKR_OK;
+}

@@ -228,6 +228,11 @@ int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t f
 int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
                      const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
 int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
+/* Old API: commitments to bit columns, src/binary_msm.rs:19-54 (CommitmentKey::commit_bitvec,
+ * gkr_msm_simple.rs:62-68).  gkr_binary_msm_prepare = prepare_bases: per chunk of `gamma` bases the 2^gamma - 1 subset sums, affine,
+ * laid out [chunk][i - 1]; gkr_binary_msm = binary_msm over prepare_coefs' bytes (HOST array, one per chunk; 0 selects nothing). */
+int gkr_binary_msm_prepare(gkr_ctx* ctx, const gkr_srs* bases, uint32_t gamma, gkr_srs** prepared);
+int gkr_binary_msm(gkr_ctx* ctx, const gkr_srs* prepared, uint32_t gamma, const uint8_t* coefs, uint64_t n_chunks, uint64_t* out_xy);
 /* Proving-key preprocessing (not part of a proof): fixed-base window table T[k][i] = 2^(c k) P_i of an affine SRS, (ceil(255 / c) - 1) n
  * more points in HBM.  With it gkr_msm_g1 sends all windows of a scalar into ONE set of 2^c buckets (13 instead of 16 additions per
  * 255-bit scalar at c = 20, no per-window reductions, no Horner tail).  Used for MSMs with at least 4 * 2^c / windows points. */

@@ -80,3 +80,40 @@ def running_sum_commit(buckets):
         running = CV.g1_add(running, buckets[ln - i - 1])
         acc = CV.g1_add(acc, running)
     return acc
+
+
+# ---- old API: binary_msm (src/binary_msm.rs:13-54) -------------------------------------------------------------------
+def into_u8(bits):  # binary_msm.rs:13-17: the first bit of the chunk is the most significant
+    s = 0
+    for b in list(bits)[:8]:
+        s = (s << 1) + (1 if b else 0)
+    return s
+
+
+def prepare_coefs(bits, gamma):  # binary_msm.rs:52-54
+    bits = list(bits)
+    return [into_u8(bits[i:i + gamma]) for i in range(0, len(bits), gamma)]
+
+
+def prepare_chunk(chunk, gamma):  # binary_msm.rs:32-43: entry i - 1 = sum of chunk[len - 1 - idx] over the set bits idx of i
+    out = []
+    for i in range(1, 1 << gamma):
+        acc = None
+        for idx, b in zip(range(gamma), reversed(chunk)):
+            if (1 << idx) & i:
+                acc = CV.g1_add(acc, b)
+        out.append(acc)
+    return out
+
+
+def prepare_bases(bases, gamma):  # binary_msm.rs:44-50
+    return [prepare_chunk(bases[i:i + gamma], gamma) for i in range(0, len(bases), gamma)]
+
+
+def binary_msm(coefs, pbases):  # binary_msm.rs:19-29
+    assert len(coefs) == len(pbases)
+    acc = None
+    for base, idx in zip(pbases, coefs):
+        if idx != 0:
+            acc = CV.g1_add(acc, base[idx - 1])
+    return acc

@@ -194,3 +194,23 @@ def test_gamma_wrapper_works():
     gamma = rng.randrange(P)
     out = gate.exec(a)
     assert G.GammaWrapper(gate, gamma).exec(a) == sum(pow(gamma, i, P) * x for i, x in enumerate(out)) % P
+
+
+def test_binary_msm_oracle_matches_reference_property():
+    """binary_msm.rs:62-96 (bin_msm, bin_msm_gamma_3) restated: binary_msm(prepare_coefs, prepare_bases) == sum of the selected bases"""
+    import random
+
+    from oracle.pyref import commitments as OC
+    from oracle.pyref import curves as CV
+
+    rng = random.Random(8)
+    for num, gamma in [(20, 8), (20, 3), (5, 4)]:
+        bits = [rng.random() < 0.5 for _ in range(num)]
+        bases = [CV.g1_mul(rng.randrange(1, CV.G1_ORDER), CV.G1_GEN) for _ in range(num)]
+        res = OC.binary_msm(OC.prepare_coefs(bits, gamma), OC.prepare_bases(bases, gamma))
+        expected = None
+        for c, b in zip(bits, bases):
+            if c:
+                expected = CV.g1_add(expected, b)
+        assert res == expected
+    assert OC.into_u8([True, False, True]) == 5
