@@ -229,3 +229,29 @@ def test_fast_fold_equals_montgomery_fold_at_scale(ctx, kind):
         assert np.array_equal(a, b)
     assert np.array_equal(runs[0][1], runs[1][1])
     assert np.array_equal(runs[0][2], runs[1][2])
+
+
+@pytest.mark.parametrize("so_kind,gate,ntab", [(g.SO_PLAIN, g.GATE_PROD3, 3), (g.SO_EQ_GAMMA, g.GATE_AFF_L1, 5), (g.SO_EQ_GAMMA, g.GATE_PRJ_L3, 5)])
+def test_c_oracle_parity_across_kernel_switch(ctx, so_kind, gate, ntab):
+    """2^15 entries: the first rounds run the throughput kernel, the rounds of <= 4096 items the block-cooperative small-round
+    kernel (dense_kernel.cuh) -- every round polynomial and the final evaluations bit-exact against the C oracle."""
+    from oracle import coracle
+
+    nv = 15
+    tabs = [ctx.synth(40 + j, 1 << nv) for j in range(ntab)]
+    host = [coracle.synth_table(40 + j, 1 << nv) for j in range(ntab)]
+    gam = coracle.synth_table(5, 16) if so_kind == g.SO_EQ_GAMMA else None
+    claim = ctx.gate_sum(so_kind, gate, tabs, consts=gam)
+    assert np.array_equal(claim, coracle.gate_sum(1 if so_kind == g.SO_EQ_GAMMA else 0, gate, host, consts=gam))
+    so = ctx.dense_so(so_kind, gate, tabs, nv, claim, consts=gam)
+    ch = coracle.synth_table(6, nv)
+    ch[:, 2:] = 0  # 128-bit challenges: the fast folds
+    ch[7] = coracle.synth_table(8, 1)[0]  # and one full-width challenge
+    evs = []
+    for r in range(nv):
+        evs.append(so.unipoly().copy())
+        so.bind(ch[r])
+    oev, ofe = coracle.dense_sumcheck(1 if so_kind == g.SO_EQ_GAMMA else 0, gate, host, nv, claim, ch, consts=gam)
+    for r in range(nv):
+        assert np.array_equal(evs[r], oev[r]), f"round {r}"
+    assert np.array_equal(so.final_evals(), ofe)
