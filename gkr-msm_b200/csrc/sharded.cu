@@ -144,6 +144,36 @@ extern "C" int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exc
         for (uint32_t j = 0; j < P; j++) frh_to_limbs(fe[j], mine.data() + 4 * j);
         rc = gkr_exchange_allgather(ex, mine.data(), P, all.data());
         if (rc) return ctx->fail(rc, "final gather failed");
+        if (so_kind == GKR_SO_PLAIN && gate == GKR_GATE_PROD3 && P == 3) {
+            // the last log2(world) rounds over world x 3 values on the HOST: same arithmetic as the device object
+            // (sumcheck.rs:277-332, 160-163), without the uploads, the object and g more launches
+            std::vector<std::vector<gkr::FrH>> tb(3, std::vector<gkr::FrH>(world));
+            for (uint32_t j = 0; j < 3; j++)
+                for (int q = 0; q < world; q++) tb[j][q] = frh_from_limbs(all.data() + ((size_t)q * P + j) * 4);
+            for (int k = 0; k < g; k++) {
+                const size_t half = tb[0].size() / 2;
+                gkr::FrH sums[3] = {gkr::frh::ZERO, gkr::frh::ZERO, gkr::frh::ZERO};
+                for (size_t i = 0; i < half; i++) {
+                    gkr::FrH a[3], d[3];
+                    for (int j = 0; j < 3; j++) {
+                        a[j] = tb[j][2 * i + 1];
+                        d[j] = gkr::frh::sub(tb[j][2 * i + 1], tb[j][2 * i]);
+                    }
+                    for (int sidx = 0; sidx < 3; sidx++) {
+                        if (sidx)
+                            for (int j = 0; j < 3; j++) a[j] = gkr::frh::add(a[j], d[j]);
+                        sums[sidx] = gkr::frh::add(sums[sidx], gkr::frh::mul(gkr::frh::mul(a[0], a[1]), a[2]));
+                    }
+                }
+                gkr::FrH x = round_io(sums);
+                for (int j = 0; j < 3; j++) {
+                    for (size_t i = 0; i < half; i++)
+                        tb[j][i] = gkr::frh::add(tb[j][2 * i], gkr::frh::mul(x, gkr::frh::sub(tb[j][2 * i + 1], tb[j][2 * i])));
+                    tb[j].resize(half);
+                }
+            }
+            for (int j = 0; j < 3; j++) fe[j] = tb[j][0];
+        } else {
         std::vector<gkr_table*> tabs(P, nullptr);
         std::vector<uint64_t> col((size_t)4 * world);
         for (uint32_t j = 0; j < P && rc == GKR_OK; j++) {
@@ -167,6 +197,7 @@ extern "C" int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exc
         delete tail;
         for (auto* tb : tabs) gkr_table_free(tb);
         if (rc) return rc;
+        }
     }
     if (out_claim) frh_to_limbs(claim, out_claim);
     if (out_point)
