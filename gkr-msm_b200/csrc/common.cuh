@@ -85,6 +85,8 @@ struct gkr_ctx {
     }
     // pinned staging ring for small parameter uploads (one truly asynchronous H2D copy per object instead of a dozen
     // pageable ones, no synchronisation until the ring wraps)
+    // kernel-selection thresholds (defaults measured on B200; GKR_DENSE_SMALL_MAX / GKR_DEG2_COMPACT_MAX override them for experiments)
+    uint64_t dense_small_max = 4096, deg2_compact_max = 32768;
     gkr_msm_team* team = nullptr;        // leader only: large gkr_msm_g1 calls are shared with the worker ranks
     uint64_t team_min_n = (uint64_t)1 << 18;
     std::shared_ptr<Deg2Layout> deg2_layout;  // reused by consecutive VecVec objects over the same rows

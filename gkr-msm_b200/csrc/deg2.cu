@@ -373,7 +373,7 @@ class Deg2SO : public gkr_so {
         a.o = ctx->round_out(slot);
         const uint64_t want = std::max<uint64_t>(1, (2 * n_pairs + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS);  // two lanes per pair
         // latency flavour for rounds that fit in about one wave of blocks, throughput flavour above
-        const bool compact = n_pairs * (uint64_t)n_blocks <= GKR_DEG2_COMPACT_MAX_PAIRS;
+        const bool compact = n_pairs * (uint64_t)n_blocks <= ctx->deg2_compact_max;
         // compact + ragged: extra blocks at the tail of every slice for the padding term, one row per thread (only the y == 0
         // ones work), so that T overlaps the gate evaluations instead of following them
         const uint64_t pad_blocks = (is_vecvec && compact) ? std::min<uint64_t>(128, (nrows + GKR_REDUCE_THREADS - 1) / GKR_REDUCE_THREADS) : 0;

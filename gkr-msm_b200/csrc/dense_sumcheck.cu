@@ -68,7 +68,7 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
         blocks_per_sm = std::max(b, 1);
     }
     if constexpr (MODE != 2) {
-        if (args.n_items <= GKR_DENSE_SMALL_MAX) {  // small round: the block-cooperative kernel
+        if (args.n_items <= ctx->dense_small_max) {  // small round: the block-cooperative kernel
             unsigned grid = (unsigned)std::max<uint64_t>(1, (args.n_items + GKR_DENSE_SMALL_QB - 1) / GKR_DENSE_SMALL_QB);
             *n_blocks_out = grid;
             {
