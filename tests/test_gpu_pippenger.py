@@ -124,3 +124,34 @@ def test_pippenger_full_size_properties(ctx, d, x, nbits, clm):
     with pytest.raises(AssertionError):
         PP.verify_pippenger(ProofTranscript2.start_verifier(b"fgstglsp", bytes(bad)), cfg, dense_output,
                             (list(dclaims[0]), list(dclaims[1])), okey, expected)
+
+
+@pytest.mark.parametrize("kind", ["zeros", "ones", "same", "one-hot"])
+@pytest.mark.parametrize("d,x,nbits,clm", [(2, 3, 6, 0), (3, 5, 16, 1)])
+def test_pippenger_degenerate_scalars(ctx, kind, d, x, nbits, clm):
+    """Collisions and empty buckets: all scalars zero / all-ones / identical / a single non-zero one -- every point of a digit
+    row lands in ONE bucket (counters run up to 2^x - 1, all other bucket rows are empty).  Device proof == oracle proof, and
+    the oracle verifier recovers the MSM (the identity for the zero scalars)."""
+    rng = random.Random(7000 + 10 * d + x)
+    cfg = PP.pippenger_config(d, x, nbits, clm)
+    n = 1 << x
+    points = [CV.te_random_point(rng) for _ in range(n)]
+    coefs = {"zeros": [0] * n, "ones": [(1 << nbits) - 1] * n, "same": [rng.randrange(1 << nbits)] * n, "one-hot": [0] * (n - 1) + [5]}[kind]
+    r = [rng.randrange(P) for _ in range(cfg["y_logsize"])]
+    nv = x + clm
+    tau = rng.randrange(1, P)
+    g0 = CV.g1_mul(rng.randrange(1, P), CV.G1_GEN)
+    okey = PP.KnucklesKey(PP.KzgKey(tau, g0, 2 * (1 << nv) - 1), nv, 2)
+    tp = ProofTranscript2.start_prover(b"fgstglsp")
+    odense, oclaims = PP.run_pippenger(tp, points, coefs, cfg, r, okey)
+    oproof = tp.end()
+    kzg = DPP.KzgKey.mock_setup(ctx, tau, g0, 2 * (1 << nv) - 1)
+    key = DPP.KnucklesKey(ctx, kzg, nv, 2)
+    points_xy = np.stack([to_limbs([p[0] for p in points]), to_limbs([p[1] for p in points])])
+    tr = g.Transcript(b"fgstglsp")
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr, kzg.srs, kzg.g0, key.dev, points_xy, coefs_to_u64(coefs), d, x, nbits, clm, to_limbs(r))
+    assert tr.proof() == oproof
+    assert [from_limbs(t) for t in ndense] == odense
+    expected = CV.te_msm(points, coefs)
+    tv = ProofTranscript2.start_verifier(b"fgstglsp", tr.proof())
+    assert PP.verify_pippenger(tv, cfg, odense, oclaims, okey, expected) == expected
