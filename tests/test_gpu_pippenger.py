@@ -46,7 +46,8 @@ def test_scalar_digits():
             assert [int(v) for v in got[y]] == [(c >> (y * d)) & ((1 << d) - 1) for c in coefs]
 
 
-@pytest.mark.parametrize("d,x,nbits,clm", [(2, 3, 6, 0), (2, 3, 8, 1), (3, 4, 7, 0), (2, 2, 8, 2), (3, 5, 16, 1)])
+@pytest.mark.parametrize("d,x,nbits,clm", [(2, 3, 6, 0), (2, 3, 8, 1), (3, 4, 7, 0), (2, 2, 8, 2), (3, 5, 16, 1),
+                                           (3, 3, 6, 0), (4, 4, 8, 1), (2, 5, 9, 0), (3, 3, 24, 3)])  # x == d, y_size not a power of two, clm == y_logsize
 def test_pippenger_device_vs_oracle(ctx, d, x, nbits, clm):
     rng = random.Random(1000 * d + 100 * x + 10 * nbits + clm)
     cfg, points, coefs, r, okey = make_instance(rng, d, x, nbits, clm)
@@ -155,3 +156,19 @@ def test_pippenger_degenerate_scalars(ctx, kind, d, x, nbits, clm):
     expected = CV.te_msm(points, coefs)
     tv = ProofTranscript2.start_verifier(b"fgstglsp", tr.proof())
     assert PP.verify_pippenger(tv, cfg, odense, oclaims, okey, expected) == expected
+
+
+def test_pippenger_single_digit_row_is_rejected_like_the_reference(ctx):
+    """nbits <= d_logsize gives y_size = 1, y_logsize = 0: the reference panics in LogupMainphase::new ("logsizes must be
+    non-increasing", logup_mainphase.rs) -- the oracle raises, the device entry returns an error status instead of a proof"""
+    rng = random.Random(3)
+    d, x, nbits, clm = 3, 4, 3, 0
+    with pytest.raises(AssertionError):
+        cfg, points, coefs, r, okey = make_instance(random.Random(3), d, x, nbits, clm)
+        PP.run_pippenger(ProofTranscript2.start_prover(b"fgstglsp"), points, coefs, cfg, r, okey)
+    cfg, points, coefs, r, okey = make_instance(rng, d, x, nbits, clm)
+    kzg = DPP.KzgKey.mock_setup(ctx, okey.kzg.tau, okey.kzg.g0, 2 * (1 << x) - 1)
+    key = DPP.KnucklesKey(ctx, kzg, x, 2)
+    points_xy = np.stack([to_limbs([p[0] for p in points]), to_limbs([p[1] for p in points])])
+    with pytest.raises(g.GkrError):
+        g.run_pippenger_native(ctx, g.Transcript(b"fgstglsp"), kzg.srs, kzg.g0, key.dev, points_xy, coefs_to_u64(coefs), d, x, nbits, clm, to_limbs(r))
