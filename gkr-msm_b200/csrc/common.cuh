@@ -27,8 +27,13 @@ struct GkrSlot {
     Fr part[GKR_MAX_BLOCKS * GKR_MAX_DEG];
 };
 
+// Launches of more than this many blocks fold their per-block partials on the DEVICE (last block, second stage) and publish
+// one result; smaller launches let the host fold the few partials (one PCIe write per block, no second stage).
+#define GKR_HOST_FOLD_MAX_BLOCKS 8
+
 struct RoundOut {  // kernel-side view of a slot
     Fr* part;
+    Fr* dev_part;  // device scratch for the per-block partials of large launches
     uint32_t* flag;
     unsigned int* ticket;
     uint32_t seq;
@@ -59,6 +64,7 @@ struct gkr_ctx {
     RoundOut round_out(int slot) {  // next launch on this slot
         RoundOut o;
         o.part = slots_dev[slot].part;
+        o.dev_part = partials;
         o.flag = (uint32_t*)&slots_dev[slot].flag;
         o.ticket = slot_tickets + slot;
         o.seq = ++slot_seq[slot];
@@ -244,24 +250,61 @@ __device__ __forceinline__ void block_reduce_fr(Fr* acc, Fr* smem /* [N * warps]
 }
 
 // Block-level sums go straight to the host-mapped slot; the last block to take a ticket publishes the sequence number.
+// Launches of more than GKR_HOST_FOLD_MAX_BLOCKS blocks park their partials in device memory instead and the last block
+// folds them (hundreds of partials cost the host ~10 us per round and one PCIe write + system fence per block).
 template <int N>
 __device__ __forceinline__ void grid_reduce_to_host(Fr* acc, Fr* smem, const RoundOut& o) {
     block_reduce_fr<N>(acc, smem);
-    if (threadIdx.x == 0) {
-        const unsigned int n_blocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned int n_blocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (n_blocks <= GKR_HOST_FOLD_MAX_BLOCKS) {
+        if (threadIdx.x == 0) {
 #pragma unroll
-        for (int s = 0; s < N; s++) o.part[(size_t)bid * N + s] = acc[s];
-        __threadfence_system();
-        bool last = true;
-        if (n_blocks > 1) {
-            unsigned int tk = atomicAdd(o.ticket, 1u);
-            last = (tk == n_blocks - 1);
-            if (last) *o.ticket = 0;
-        }
-        if (last) {
+            for (int s = 0; s < N; s++) o.part[(size_t)bid * N + s] = acc[s];
             __threadfence_system();
-            *(volatile uint32_t*)o.flag = o.seq;
+            bool last = true;
+            if (n_blocks > 1) {
+                unsigned int tk = atomicAdd(o.ticket, 1u);
+                last = (tk == n_blocks - 1);
+                if (last) *o.ticket = 0;
+            }
+            if (last) {
+                __threadfence_system();
+                *(volatile uint32_t*)o.flag = o.seq;
+            }
         }
+        return;
+    }
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < N; s++) o.dev_part[(size_t)bid * N + s] = acc[s];
+        __threadfence();
+        unsigned int tk = atomicAdd(o.ticket, 1u);
+        is_last = (tk == n_blocks - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+#pragma unroll
+    for (int s = 0; s < N; s++) acc[s] = fr_zero();
+    for (unsigned int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
+#pragma unroll
+        for (int s = 0; s < N; s++) {
+            const Fr* p = &o.dev_part[(size_t)b * N + s];
+            Fr v;
+            asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(v.l[0]), "=r"(v.l[1]), "=r"(v.l[2]), "=r"(v.l[3]), "=r"(v.l[4]), "=r"(v.l[5]), "=r"(v.l[6]), "=r"(v.l[7])
+                         : "l"(p));
+            acc[s] = fr_add(acc[s], v);
+        }
+    }
+    block_reduce_fr<N>(acc, smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < N; s++) o.part[s] = acc[s];
+        *o.ticket = 0;
+        __threadfence_system();
+        *(volatile uint32_t*)o.flag = o.seq;
     }
 }
 

@@ -95,6 +95,7 @@ void gkr_big_cache_release(cudaStream_t s) {
 }
 
 int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out) {
+    if (n_blocks > GKR_HOST_FOLD_MAX_BLOCKS) n_blocks = 1;  // large launches fold their partials on the device (grid_reduce_to_host)
     GkrSlot* s = &ctx->slots_host[slot];
     const uint32_t seq = ctx->slot_seq[slot];
     uint64_t spins = 0;
