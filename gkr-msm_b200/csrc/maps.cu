@@ -204,29 +204,41 @@ std::vector<MapBlock> expand(const Stack& s, bool split, int bundle) {
     return out;
 }
 
-struct DevArrays {  // small device-side argument arrays of one map launch
+// small device-side argument arrays of one map launch: ONE allocation and ONE staged (pinned ring) upload, so that a map call
+// neither issues five pageable copies nor has to synchronise before its host vectors go out of scope
+struct DevArrays {
     gkr_ctx* ctx;
+    unsigned char* base = nullptr;
+    std::vector<unsigned char> host;
     const Fr** in = nullptr;
     Fr** out = nullptr;
     MapBlock* blocks = nullptr;
     Fr* pads = nullptr;
     uint32_t* offs = nullptr;
+    size_t o_in = 0, o_out = 0, o_blocks = 0, o_pads = 0, o_offs = 0;
+    explicit DevArrays(gkr_ctx* c) : ctx(c) {}
     ~DevArrays() {
-        cudaStream_t s = ctx->stream;
-        if (in) gkr_free_async(in, s);
-        if (out) gkr_free_async(out, s);
-        if (blocks) gkr_free_async(blocks, s);
-        if (pads) gkr_free_async(pads, s);
-        if (offs) gkr_free_async(offs, s);
+        if (base) gkr_free_async(base, ctx->stream);
+    }
+    template <class T>
+    size_t put(const std::vector<T>& v) {
+        size_t off = (host.size() + 31) & ~(size_t)31;
+        host.resize(off + std::max<size_t>(sizeof(T) * v.size(), 1));
+        if (!v.empty()) std::memcpy(host.data() + off, v.data(), sizeof(T) * v.size());
+        return off;
+    }
+    int upload() {
+        GKR_CUDA_OK(ctx, gkr_malloc_async(&base, host.size(), ctx->stream));
+        int rc = gkr_stage_upload(ctx, base, host.data(), host.size());
+        if (rc) return rc;
+        in = (const Fr**)(base + o_in);
+        out = (Fr**)(base + o_out);
+        blocks = (MapBlock*)(base + o_blocks);
+        pads = (Fr*)(base + o_pads);
+        offs = (uint32_t*)(base + o_offs);
+        return GKR_OK;
     }
 };
-
-template <class T>
-int to_device(gkr_ctx* ctx, const std::vector<T>& h, T** d) {
-    GKR_CUDA_OK(ctx, gkr_malloc_async(d, sizeof(T) * std::max<size_t>(h.size(), 1), ctx->stream));
-    if (!h.empty()) GKR_CUDA_OK(ctx, cudaMemcpyAsync(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
-    return GKR_OK;
-}
 
 int launch_map(gkr_ctx* ctx, MapArgs& a, int n_blocks) {
     if (a.n == 0) return GKR_OK;
@@ -277,10 +289,11 @@ extern "C" int gkr_map_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t*
     std::vector<const Fr*> ins(n_in);
     for (uint32_t j = 0; j < n_in; j++) ins[j] = in[j]->d;
     std::vector<MapBlock> blocks = expand(st, split, (int)bundle_size);
-    DevArrays d{ctx};
-    int rc = to_device(ctx, ins, &d.in);
-    if (!rc) rc = to_device(ctx, outs, &d.out);
-    if (!rc) rc = to_device(ctx, blocks, &d.blocks);
+    DevArrays d(ctx);
+    d.o_in = d.put(ins);
+    d.o_out = d.put(outs);
+    d.o_blocks = d.put(blocks);
+    int rc = d.upload();
     if (rc) return rc;
     MapArgs a{};
     a.in = d.in;
@@ -291,7 +304,6 @@ extern "C" int gkr_map_dense(gkr_ctx* ctx, const int* part_gate, const uint32_t*
     a.seg = seg;
     rc = launch_map(ctx, a, (int)blocks.size());
     if (rc) return rc;
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
     if (n_out) *n_out = (uint32_t)n_tables;
     return GKR_OK;
 }
@@ -380,12 +392,13 @@ extern "C" int gkr_map_vecvec(gkr_ctx* ctx, const int* part_gate, const uint32_t
     std::vector<MapBlock> blocks = expand(st, split, (int)bundle_size);
     std::vector<uint32_t> offs(off_old);
     offs.insert(offs.end(), off_new.begin(), off_new.end());
-    DevArrays d{ctx};
-    int rc = to_device(ctx, ins, &d.in);
-    if (!rc) rc = to_device(ctx, outs, &d.out);
-    if (!rc) rc = to_device(ctx, blocks, &d.blocks);
-    if (!rc) rc = to_device(ctx, pad_tab, &d.pads);
-    if (!rc) rc = to_device(ctx, offs, &d.offs);
+    DevArrays d(ctx);
+    d.o_in = d.put(ins);
+    d.o_out = d.put(outs);
+    d.o_blocks = d.put(blocks);
+    d.o_pads = d.put(pad_tab);
+    d.o_offs = d.put(offs);
+    int rc = d.upload();
     if (rc) return rc;
     MapArgs a{};
     a.in = d.in;
@@ -413,7 +426,6 @@ extern "C" int gkr_map_vecvec(gkr_ctx* ctx, const int* part_gate, const uint32_t
         ctx->launches++;
         GKR_CUDA_OK(ctx, cudaGetLastError());
     }
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     if (n_out) *n_out = (uint32_t)n_tables;
     return GKR_OK;
 }

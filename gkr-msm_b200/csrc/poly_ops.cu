@@ -168,14 +168,16 @@ extern "C" int gkr_table_lincomb(gkr_ctx* ctx, uint32_t n_terms, gkr_table* cons
     if (rc) return rc;
     LinTerm* d_terms = nullptr;
     GKR_CUDA_OK(ctx, gkr_malloc_async(&d_terms, sizeof(LinTerm) * std::max<uint32_t>(n_terms, 1), ctx->stream));
-    if (n_terms) GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_terms, terms.data(), sizeof(LinTerm) * n_terms, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_terms) {  // staged through the pinned ring: no pageable copy, no synchronisation before `terms` goes out of scope
+        int rcs = gkr_stage_upload(ctx, d_terms, terms.data(), sizeof(LinTerm) * n_terms);
+        if (rcs) return rcs;
+    }
     if (out_len) {
         unsigned g = (unsigned)std::min<uint64_t>((out_len + 255) / 256, (uint64_t)ctx->num_sms * 8);
         lincomb_kernel<<<g, 256, 0, ctx->stream>>>((*out)->d, out_len, d_terms, (int)n_terms);
         ctx->launches++;
         GKR_CUDA_OK(ctx, cudaGetLastError());
     }
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     gkr_free_async(d_terms, ctx->stream);
     return GKR_OK;
 }
