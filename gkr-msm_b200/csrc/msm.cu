@@ -573,8 +573,12 @@ extern "C" int gkr_srs_upload(gkr_ctx* ctx, const uint64_t* points, uint64_t n, 
     s->kind = projective ? 1 : 0;
     size_t bytes = (size_t)n * s->stride();
     cudaError_t e = gkr_malloc_async(&s->d, std::max<size_t>(bytes, 16), ctx->stream);
-    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(s->d, points, bytes, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && bytes && bytes <= ((size_t)1 << 20)) {
+        if (gkr_stage_upload(ctx, s->d, points, bytes)) e = cudaErrorUnknown;  // a handful of points (commitment combinations): pinned ring
+    } else {
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(s->d, points, bytes, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
     if (e != cudaSuccess) {
         delete s;
         return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));

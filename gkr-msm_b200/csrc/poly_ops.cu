@@ -56,8 +56,12 @@ extern "C" int gkr_u32_upload(gkr_ctx* ctx, const uint32_t* vals, uint64_t n, gk
     b->ctx = ctx;
     b->n = n;
     cudaError_t e = gkr_malloc_async(&b->d, sizeof(uint32_t) * std::max<uint64_t>(n, 1), ctx->stream);
-    if (e == cudaSuccess && n) e = cudaMemcpyAsync(b->d, vals, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess && n && sizeof(uint32_t) * n <= ((size_t)1 << 20)) {
+        if (gkr_stage_upload(ctx, b->d, vals, sizeof(uint32_t) * n)) e = cudaErrorUnknown;  // small: pinned ring, no synchronisation
+    } else {
+        if (e == cudaSuccess && n) e = cudaMemcpyAsync(b->d, vals, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
     if (e != cudaSuccess) { delete b; return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e)); }
     *out = b;
     return GKR_OK;

@@ -263,6 +263,7 @@ extern "C" int gkr_table_upload(gkr_ctx* ctx, const uint64_t* limbs, uint64_t n,
     if (!limbs && n) return ctx->fail(GKR_ERR_ARG, "null host buffer");
     int rc = gkr_table_alloc(ctx, n, out);
     if (rc) return rc;
+    if (n && sizeof(Fr) * n <= ((size_t)1 << 20)) return gkr_stage_upload(ctx, (*out)->d, limbs, sizeof(Fr) * n);  // small: pinned ring, truly asynchronous
     if (n) GKR_CUDA_OK(ctx, cudaMemcpyAsync((*out)->d, limbs, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
     return GKR_OK;
 }
@@ -409,7 +410,7 @@ int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& m
 
 int gkr_stage_upload(gkr_ctx* ctx, void* d_dst, const void* src, size_t n) {
     if (n == 0) return GKR_OK;
-    const size_t RING = (size_t)16 << 20;
+    const size_t RING = (size_t)64 << 20;  // a 2^20-point proof stages ~20 MB of parameters: the ring wraps (one stream synchronisation) every few proofs
     if (!ctx->stage_host) {
         GKR_CUDA_OK(ctx, cudaHostAlloc(&ctx->stage_host, RING, cudaHostAllocDefault));
         ctx->stage_size = RING;
@@ -441,7 +442,10 @@ extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, con
     if (rc) return rc;
     Fr* d_point = nullptr;
     GKR_CUDA_OK(ctx, gkr_malloc_async(&d_point, sizeof(Fr) * std::max<uint32_t>(n, 1), ctx->stream));
-    if (n) GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_point, point, sizeof(Fr) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) {
+        int rcs = gkr_stage_upload(ctx, d_point, point, sizeof(Fr) * n);
+        if (rcs) return rcs;
+    }
     rc = eq_build(ctx, d_point, n, fr_from_host(m), (*out)->d);
     gkr_free_async(d_point, ctx->stream);
     if (rc) {
