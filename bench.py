@@ -224,10 +224,10 @@ def run_ours(args, rank, world, local_rank):
         ach = alg_bytes / (avg_ms * 1e-3) / 1e9
         kernel_ms = sum(ms for (_, _, ms) in launches_timed) / args.steps
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 from the committed ncu --set full capture
-        # (profiles/r01_ncu_full_dense_round_prod3_fold_eval.csv): 1.610762 GB + 0.780815 GB per launch; other sizes: not captured
-        traffic = 1610762000 + 780814592 if log_n == 24 else None
+        # (profiles/r01c_ncu_full_dense_round_prod3_fold_eval.csv): 1.610745 GB + 0.780195 GB per launch; other sizes: not captured
+        traffic = 1610745000 + 780194560 if log_n == 24 else None
         roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01_ncu_full_dense_round_prod3_fold_eval.csv (ncu --set full, one launch)",
+                    "traffic_source": "profiles/r01c_ncu_full_dense_round_prod3_fold_eval.csv (ncu --set full, one launch)",
                     "kernel": "dense_round_kernel<SoProd3, fold+eval> (first fused round)", "avg_launch_ms": avg_ms,
                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                     "share_of_kernel_time": avg_ms / kernel_ms if kernel_ms else None,
