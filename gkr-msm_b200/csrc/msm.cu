@@ -677,13 +677,16 @@ static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, 
             const int c1 = c - seg_log, seg_log1 = 3;
             const uint32_t segs1 = 1u << (c1 - seg_log1), stride = segs + segs1;
             const uint64_t n_threads1 = (uint64_t)W * segs1;
-            GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * ((uint64_t)W * stride + n_threads + W), st));
+            GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * ((uint64_t)W * stride + n_threads + W + 9 * (uint64_t)W), st));
             G1X* runs = seg_out + (uint64_t)W * stride;
             wsums = runs + n_threads;
+            G1X* parts = wsums + W;
             msm_segment_level0_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, stride, runs);
             msm_segment_kernel<<<(unsigned)((n_threads1 + 127) / 128), 128, 0, st>>>(runs, c1, seg_log1, n_threads1, seg_out + segs, stride);
-            msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, stride, wsums);
-            ctx->launches += 3;
+            // stride = 9 * segs1 entries per window: nine blocks per window sum segs1 entries each, then one block the nine partials
+            msm_window_tree_kernel<<<9 * W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs1, parts);
+            msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(parts, 9, wsums);
+            ctx->launches += 4;
         } else {
             GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * (n_threads + W), st));
             wsums = seg_out + n_threads;
