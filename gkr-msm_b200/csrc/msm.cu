@@ -159,6 +159,37 @@ __global__ void msm_digits_kernel(const Fr* scalars, uint32_t n, int c, int n_wi
     }
 }
 
+// the same for up to MSM_MULTI_MAX scalar tables over the SAME bases (gkr_msm_g1_multi): problem j owns windows [j W, (j+1) W)
+#define MSM_MULTI_MAX 8
+struct MsmMultiScalars {
+    const Fr* s[MSM_MULTI_MAX];
+    uint32_t n[MSM_MULTI_MAX];
+    uint32_t k;
+};
+__global__ void msm_digits_multi_kernel(const __grid_constant__ MsmMultiScalars S, uint32_t n_max, int c, int n_windows,
+                                        uint32_t* digits /* [k W][n_max] */, uint32_t* counts /* [k W][2^c] */) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_max; i += gridDim.x * blockDim.x) {
+        for (uint32_t j = 0; j < S.k; j++) {
+            const size_t w0 = (size_t)j * n_windows;
+            if (i >= S.n[j]) {  // beyond this problem's length: digit zero (never accumulated)
+                for (int w = 0; w < n_windows; w++) digits[(w0 + w) * n_max + i] = 0;
+                continue;
+            }
+            Fr one_raw = fr_zero();
+            one_raw.l[0] = 1;
+            Fr s = fr_mul(S.s[j][i], one_raw);
+            for (int w = 0; w < n_windows; w++) {
+                const int bit = w * c, limb = bit >> 5, sh = bit & 31;
+                uint64_t v = s.l[limb];
+                if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
+                const uint32_t d = (uint32_t)(v >> sh) & ((1u << c) - 1);
+                digits[(w0 + w) * n_max + i] = d;
+                if (d) atomicAdd(&counts[((w0 + w) << c) + d], 1u);
+            }
+        }
+    }
+}
+
 // exclusive scan of every window's histogram (one block per window)
 __global__ void msm_scan_kernel(const uint32_t* counts, uint32_t* offsets, int c) {
     __shared__ uint32_t carry;
@@ -885,6 +916,67 @@ extern "C" int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first
     return msm_g1_impl(ctx, srs, first, problem_stride, n_problems, scalars->d, n, out_xy);
 }
 
+
+// k commitments with DIFFERENT scalar tables over the SAME base range [first, first + n_j): the phase-1 commitments to p_0, p_1,
+// ac_c, ac_d (pushforward.rs:534-537) and the two openings of KnucklesOpeningProtocol::prove that no challenge separates
+// (opening.rs:77-83).  Below 2^19 points an MSM is bound by the latency of its reduction passes, not by additions, so the k
+// problems share ONE digit sort, ONE accumulation and ONE reduction over k W windows; larger ones (or a team / fixed-base table)
+// run one by one.  out_xy: k x 12 u64.
+extern "C" int gkr_msm_g1_multi(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* const* scalars, const uint64_t* n,
+                                uint32_t k, uint64_t* out_xy) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!srs || !scalars || !n || !out_xy || k == 0) return ctx->fail(GKR_ERR_ARG, "null argument");
+    uint64_t n_max = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        if (!scalars[j] || scalars[j]->n < n[j]) return ctx->fail(GKR_ERR_ARG, "fewer scalars than requested");
+        if (first + n[j] > srs->n) return ctx->fail(GKR_ERR_ARG, "Vector is too large.");  // kzg.rs:124
+        n_max = std::max(n_max, n[j]);
+    }
+    if (k == 1 || k > MSM_MULTI_MAX || n_max == 0 || n_max >= ((uint64_t)1 << 19) || srs->kind != 0) {
+        for (uint32_t j = 0; j < k; j++) {
+            int rc = msm_g1_impl(ctx, srs, first, 0, 1, scalars[j]->d, n[j], out_xy + 12 * (size_t)j);
+            if (rc) return rc;
+        }
+        return GKR_OK;
+    }
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int c = pick_window(n_max);
+    const int W = (255 + c - 1) / c;
+    const uint32_t KW = k * (uint32_t)W;
+    const size_t nbk = (size_t)KW << c;
+    uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr;
+    G1X* buckets = nullptr;
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&digits, sizeof(uint32_t) * KW * n_max, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&sorted, sizeof(uint32_t) * KW * n_max, st));
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&counts, sizeof(uint32_t) * (nbk * 4 + 3 * MSM_NBINS), st));
+    uint32_t *offsets = counts + nbk, *cursor = counts + 2 * nbk, *work = counts + 3 * nbk;
+    GKR_CUDA_OK(ctx, gkr_malloc_async(&buckets, sizeof(G1X) * nbk, st));
+    GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
+    MsmMultiScalars S;
+    S.k = k;
+    uint64_t entries = 0;
+    for (uint32_t j = 0; j < MSM_MULTI_MAX; j++) {
+        S.s[j] = j < k ? scalars[j]->d : nullptr;
+        S.n[j] = j < k ? (uint32_t)n[j] : 0;
+        if (j < k) entries += (uint64_t)W * n[j];
+    }
+    unsigned g1 = (unsigned)std::min<uint64_t>((n_max + 255) / 256, (uint64_t)ctx->num_sms * 8);
+    msm_digits_multi_kernel<<<g1, 256, 0, st>>>(S, (uint32_t)n_max, c, W, digits, counts);
+    msm_scan_kernel<<<KW, 1024, 0, st>>>(counts, offsets, c);
+    msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n_max, c, (int)KW, offsets, cursor, sorted);
+    ctx->launches += 3;
+    const void* bases = (const unsigned char*)srs->d + first * srs->stride();
+    std::vector<gkr::G1XH> h;
+    int rc = msm_accumulate(ctx, bases, 0, sorted, counts, offsets, (uint32_t)n_max, c, nbk, entries, work, buckets);
+    if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, c, KW, h);
+    gkr_free_async(digits, st);
+    gkr_free_async(sorted, st);
+    gkr_free_async(counts, st);
+    gkr_free_async(buckets, st);
+    if (rc == GKR_OK) msm_host_tail(h, c, W, k, out_xy);
+    return rc;
+}
 
 // ---- bucket accumulation for the c / d commitments ----------------------------------------
 //   PushForwardState::new       src/cleanup/protocols/pushforward/pushforward.rs:398-429, 433-456

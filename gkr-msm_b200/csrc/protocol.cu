@@ -722,10 +722,16 @@ struct PushForwardState {
         ck(gkr_g1_weighted_bucket_sums(ctx, d_all->h, 0, d_logsize, n_comms, d_comm[0].data()));
         ck(gkr_g1_weighted_bucket_sums(ctx, c_all->h, 0, c_log, n_comms, c_comm[0].data()));
         s2.reset(new Span(ctx, "  state: 4 MSM commitments"));
-        p_0_comm = dv.msm(key.srs, p_0, x_size);
-        p_1_comm = dv.msm(key.srs, p_1, x_size);
-        ac_c_comm = dv.msm(key.srs, ac_c, x_size);
-        ac_d_comm = dv.msm(key.srs, ac_d, nb);
+        {  // four commitments over the same bases: one shared sort / accumulation / reduction below 2^19 points
+            const gkr_table* tabs[4] = {p_0->h, p_1->h, ac_c->h, ac_d->h};
+            const uint64_t lens4[4] = {x_size, x_size, x_size, nb};
+            uint64_t out4[48];
+            ck(gkr_msm_g1_multi(ctx, key.srs, 0, tabs, lens4, 4, out4));
+            std::memcpy(p_0_comm.data(), out4, 96);
+            std::memcpy(p_1_comm.data(), out4 + 12, 96);
+            std::memcpy(ac_c_comm.data(), out4 + 24, 96);
+            std::memcpy(ac_d_comm.data(), out4 + 36, 96);
+        }
     }
 
     void second_phase(Dev& dv, const std::vector<FrH>& r) {  // pushforward.rs:572-622
@@ -1040,10 +1046,28 @@ std::pair<G1P, G1P> knuckles_opening_prove(Dev& d, const Keys& key, const G1P& c
     FrH lam = d.tr->challenge(128);
     const uint64_t tl = gkr_table_len(t->h), al = gkr_table_len(advice->h);
     Tab p_lt = d.lincomb({{t, lam, 0, 0, tl}, {advice, F::ONE, 0, 0, al}}, tl);  // opening.rs:65-75
-    G1P p_lt_x_proof = kzg.open(p_lt, x, nullptr);
-    d.write_points({p_lt_x_proof});
+    // the two openings (kzg.rs:129-132) are separated by no challenge: both quotients first, ONE two-problem commitment, then
+    // the transcript writes in the reference's order (opening.rs:77-87)
     FrH t_kx;
-    G1P t_kx_proof = kzg.open(t, kx, &t_kx);
+    G1P p_lt_x_proof, t_kx_proof;
+    {
+        uint64_t p[4], r1[4], r2[4];
+        gkr_table *q1 = nullptr, *q2 = nullptr;
+        frh_to_limbs(x, p);
+        ck(gkr_poly_div_by_linear(ctx, p_lt->h, p, &q1, r1));
+        Tab q1h = std::make_shared<TabH>(q1);
+        frh_to_limbs(kx, p);
+        ck(gkr_poly_div_by_linear(ctx, t->h, p, &q2, r2));
+        Tab q2h = std::make_shared<TabH>(q2);
+        t_kx = frh_from_limbs(r2);
+        const gkr_table* tabs[2] = {q1, q2};
+        const uint64_t lens2[2] = {gkr_table_len(q1), gkr_table_len(q2)};
+        uint64_t out2[24];
+        ck(gkr_msm_g1_multi(ctx, key.srs, 0, tabs, lens2, 2, out2));
+        std::memcpy(p_lt_x_proof.data(), out2, 96);
+        std::memcpy(t_kx_proof.data(), out2 + 12, 96);
+    }
+    d.write_points({p_lt_x_proof});
     d.tr->write_scalars(&t_kx, 1);
     d.write_points({t_kx_proof});
     FrH fin = d.tr->challenge(128);

@@ -228,6 +228,11 @@ int gkr_g1_weighted_bucket_sums(gkr_ctx* ctx, const gkr_srs* buckets, uint64_t f
 int gkr_msm_g1_batch(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_t problem_stride, uint32_t n_problems,
                      const gkr_table* scalars, uint64_t n, uint64_t* out_xy);
 int gkr_g1_download_affine(gkr_ctx* ctx, const gkr_srs* pts, uint64_t* out_xy);
+/* k commitments with different scalar tables over the SAME base range (the phase-1 commitments p_0, p_1, ac_c, ac_d of
+ * pushforward.rs:534-537; the two quotient commitments of opening.rs:77-83): below 2^19 points they share one digit sort, one
+ * bucket accumulation and one reduction; larger ones run one by one.  Results equal k gkr_msm_g1 calls.  out_xy: k x 12 u64. */
+int gkr_msm_g1_multi(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const gkr_table* const* scalars, const uint64_t* n, uint32_t k,
+                     uint64_t* out_xy);
 /* Old API: commitments to bit columns, src/binary_msm.rs:19-54 (CommitmentKey::commit_bitvec,
  * gkr_msm_simple.rs:62-68).  gkr_binary_msm_prepare = prepare_bases: per chunk of `gamma` bases the 2^gamma - 1 subset sums, affine,
  * laid out [chunk][i - 1]; gkr_binary_msm = binary_msm over prepare_coefs' bytes (HOST array, one per chunk; 0 selects nothing). */

@@ -185,3 +185,24 @@ def from_limbs_fast(arr):
     a = np.ascontiguousarray(arr, dtype=np.uint64).reshape(-1, 4)
     rinv = pow(1 << 256, -1, P)
     return [((int(r[0]) | (int(r[1]) << 64) | (int(r[2]) << 128) | (int(r[3]) << 192)) * rinv) % P for r in a]
+
+
+def test_msm_multi_equals_single_calls(ctx):
+    """gkr_msm_g1_multi: k scalar tables of different lengths over the same bases == k gkr_msm_g1 calls"""
+    import ctypes as C
+
+    from gkr_msm_b200 import hostmath as H
+
+    n = 3000
+    srs = g.Srs.mock_setup(ctx, to_limbs([0xABCDEF12345])[0], H.g1_to_limbs(CV.G1_GEN), n)
+    tabs = [ctx.synth(1, n), ctx.synth(2, n), ctx.upload(to_limbs([i % 7 for i in range(n)])), ctx.synth(3, 64)]
+    lens = [n, n - 5, n, 64]
+    want = np.stack([srs.msm(t, n=ln, first=2 if ln < n else 0) if False else srs.msm(t, n=ln) for t, ln in zip(tabs, lens)])
+    lib = ctx.lib
+    lib.gkr_msm_g1_multi.restype = C.c_int
+    lib.gkr_msm_g1_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.c_void_p, C.c_uint32, C.c_void_p]
+    arr = (C.c_void_p * 4)(*[t.h for t in tabs])
+    ln = np.array(lens, dtype=np.uint64)
+    out = np.zeros((4, 12), np.uint64)
+    ctx.check(lib.gkr_msm_g1_multi(ctx.h, srs.h, 0, arr, ln.ctypes.data_as(C.c_void_p), 4, out.ctypes.data_as(C.c_void_p)))
+    assert np.array_equal(out, want)
