@@ -4,7 +4,7 @@
 //   lens[y][b]    = bucket sizes
 //   pidx          = the bucket contents back to back, every bucket padded to even length with 0xffffffff -- the gather
 //                   index of the bucket images (VecVecPolynomial::new pads odd rows, vecvec.rs:179-189)
-// The host version (gkr_pushforward_bucketize, capi.cu) stays as the reference-shaped fallback and as the test oracle of
+// The host version (gkr_pushforward_bucketize, capi.cu) stays as the index-only host variant for digit widths above 13 bits (pure integer bookkeeping, no field arithmetic) and as the test oracle of
 // this one; on the device only the scalars (32 B each) cross PCIe instead of three y_size x n index matrices.
 //
 // Stable ranks without sorting: the x range is cut into chunks of CHUNK consecutive scalars; one WARP walks one chunk in
