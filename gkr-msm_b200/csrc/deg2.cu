@@ -100,6 +100,27 @@ __global__ void vv_to_dense_kernel(const __grid_constant__ VvToDenseArgs A) {
     }
 }
 
+// all eq levels after the first in ONE launch (one block walks the levels in order): an object over n row variables used to
+// issue n - 1 tiny launches / device copies at construction
+struct EqLevels {
+    uint64_t off[33], size[33];
+    uint8_t single[33];  // level is the one-entry table `singles[b]` (all remaining row variables are padding)
+    uint32_t n;
+    const Fr* singles;
+};
+__global__ void __launch_bounds__(1024) eq_levels_kernel(Fr* d_eq, const __grid_constant__ EqLevels L) {
+    for (uint32_t b = 1; b < L.n; b++) {
+        if (L.single[b]) {
+            if (threadIdx.x == 0) d_eq[L.off[b]] = L.singles[b];
+        } else {
+            const Fr* in = d_eq + L.off[b - 1];
+            Fr* out = d_eq + L.off[b];
+            for (uint64_t i = threadIdx.x; i < L.size[b]; i += blockDim.x) out[i] = fr_add(in[2 * i], in[2 * i + 1]);
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void eq_halve_kernel(Fr* out, const Fr* in, uint64_t n_out) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (uint64_t)gridDim.x * blockDim.x)
         out[i] = fr_add(in[2 * i], in[2 * i + 1]);
@@ -621,7 +642,9 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     d_tabs[2] = (const Fr**)(d_params + o_t2);
 
     GKR_CUDA_OK(ctx, gkr_malloc_async(&d_eq, sizeof(Fr) * std::max<uint64_t>(eq_total, 1), s));
+    const bool fused_levels = n_sparse >= 2 && n_sparse <= 33 && lvl_size[1] <= 16384;
     for (uint32_t b = 0; b < n_sparse; b++) {
+        if (b >= 1 && fused_levels) break;
         uint32_t lvl = m_row >= b ? m_row - b : 0;
         if (lvl <= npad) {
             GKR_CUDA_OK(ctx, cudaMemcpyAsync(d_eq + eq_off[b], d_single + b, sizeof(Fr), cudaMemcpyDeviceToDevice, s));
@@ -635,6 +658,20 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
             ctx->launches++;
             GKR_CUDA_OK(ctx, cudaGetLastError());
         }
+    }
+    if (fused_levels) {
+        EqLevels L;
+        L.n = n_sparse;
+        L.singles = d_single;
+        for (uint32_t b = 0; b < 33; b++) {
+            const uint32_t lvl = (b < n_sparse && m_row >= b) ? m_row - b : 0;
+            L.off[b] = b < n_sparse ? eq_off[b] : 0;
+            L.size[b] = b < n_sparse ? lvl_size[b] : 0;
+            L.single[b] = (b < n_sparse && lvl <= npad) ? 1 : 0;
+        }
+        eq_levels_kernel<<<1, 1024, 0, s>>>(d_eq, L);
+        ctx->launches++;
+        GKR_CUDA_OK(ctx, cudaGetLastError());
     }
     if (is_vecvec) {
         GKR_CUDA_OK(ctx, gkr_malloc_async(&d_rowcoef, sizeof(Fr) << col, s));
