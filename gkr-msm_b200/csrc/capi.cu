@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "so.hpp"
 #include "transcript.hpp"
+#include "host_g1.hpp"
 
 int gkr_dense_gate_sum_impl(gkr_ctx* ctx, int so_kind, int gate, uint32_t gate_param, const gkr::FrH* consts, uint32_t n_consts,
                             gkr_table* const* tables, uint32_t n_polys, gkr::FrH* out);
@@ -219,5 +220,15 @@ extern "C" int gkr_pushforward_bucketize(const uint64_t* coefs, uint64_t n, uint
             for (uint32_t y = t; y < y_size; y += nt) do_row(y);
         });
     for (auto& t : th) t.join();
+    return GKR_OK;
+}
+
+
+// host only: the 48-byte compressed G1 encoding the prover writes into the proof (ark-bls12-381 0.4 = zcash / IETF format,
+// proof_transcript.rs:52-69) of an affine point given as 12 u64 Montgomery limbs (all zero = infinity).  Exposed so that the
+// wire format of the C++ host layer can be pinned against the published encoding of the generator without a device.
+extern "C" int gkr_host_g1_serialize(const uint64_t* xy, uint8_t* out48) {
+    if (!xy || !out48) return GKR_ERR_ARG;
+    gkr::g1h::serialize_compressed(xy, out48);
     return GKR_OK;
 }

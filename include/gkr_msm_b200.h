@@ -258,6 +258,8 @@ void gkr_msm_team_close(gkr_ctx* ctx, gkr_msm_team* team);
 /* test hook, host only: the O(windows) tail of every MSM (Horner over the extended-Jacobian window sums X, Y, ZZ, ZZZ --
  * 24 u64 each -- with c doublings per window, then one inversion to affine) runs on the CPU; see csrc/host_g1.hpp. */
 int gkr_host_g1_horner(const uint64_t* window_sums, int c, int n_windows, uint64_t* out_xy);
+/* host only: 48-byte compressed encoding (ark-bls12-381 / zcash format) of an affine point, as written into the proof */
+int gkr_host_g1_serialize(const uint64_t* xy, uint8_t* out48);
 
 /* ---- univariate / element-wise table algebra -----------------------------------------
  * gkr_u32buf: digit / counter arrays resident on the device.

@@ -135,3 +135,31 @@ def test_g1_sum_combines_partial_commitments():
         want = CV.g1_add(want, p)
     assert H.g1_from_limbs(got) == want
     assert not g.g1_sum(np.zeros((3, 12), np.uint64)).any()
+
+
+def test_cpp_g1_wire_format_matches_published_generator_encoding():
+    """csrc/host_g1.hpp::serialize_compressed (what gkr_run_pippenger writes into the proof) against the published compressed
+    encoding of the BLS12-381 G1 generator, the infinity encoding, and the oracle on random points"""
+    import ctypes as C
+
+    from gkr_msm_b200 import hostmath as H
+    from oracle.pyref import curves as CV
+    from oracle.pyref import pippenger as PP
+
+    lib = g.load_library()
+    lib.gkr_host_g1_serialize.restype = C.c_int
+    lib.gkr_host_g1_serialize.argtypes = [C.c_void_p, C.c_void_p]
+
+    def ser(pt):
+        xy = np.ascontiguousarray(H.g1_to_limbs(pt), dtype=np.uint64).reshape(12)
+        out = np.zeros(48, np.uint8)
+        assert lib.gkr_host_g1_serialize(xy.ctypes.data, out.ctypes.data) == 0
+        return out.tobytes()
+
+    assert ser(CV.G1_GEN).hex() == "97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb"
+    assert ser(None) == bytes([0xC0]) + bytes(47)
+    rng = random.Random(12)
+    for _ in range(8):
+        pt = CV.g1_mul(rng.randrange(1, P), CV.G1_GEN)
+        assert ser(pt) == PP.g1_serialize(pt) == H.g1_serialize(pt)
+        assert ser(CV.g1_neg(pt)) == PP.g1_serialize(CV.g1_neg(pt))

@@ -214,3 +214,36 @@ def test_binary_msm_oracle_matches_reference_property():
                 expected = CV.g1_add(expected, b)
         assert res == expected
     assert OC.into_u8([True, False, True]) == 5
+
+
+def test_published_curve_parameters_and_wire_format():
+    """Third-party facts the restatement depends on, pinned against the PUBLISHED values (not derived from the oracle):
+    BLS12-381 base / scalar field moduli and G1 generator (IETF pairing-friendly-curves draft, zkcrypto/bls12_381), the
+    standard 48-byte compressed encoding of that generator and of the point at infinity (the format ark-bls12-381 0.4 writes
+    into the proof, proof_transcript.rs:52-69), and the Bandersnatch parameters of ark-ed-on-bls12-381-bandersnatch 0.4
+    (a = -5, d, prime-subgroup generator and order; Masson-Sanso-Zhang, 'Bandersnatch', table 1)."""
+    from oracle.pyref import curves as CV
+    from oracle.pyref import pippenger as PP
+    from oracle.pyref.field import FQ_MODULUS, P
+
+    assert FQ_MODULUS == 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    assert P == 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    gx = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
+    gy = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
+    assert CV.G1_GEN == (gx, gy) and CV.G1_ORDER == P
+    assert (gy * gy - gx * gx * gx - 4) % FQ_MODULUS == 0
+    assert CV.g1_mul(P, CV.G1_GEN) is None and CV.g1_mul(P - 1, CV.G1_GEN) == CV.g1_neg(CV.G1_GEN)
+    assert PP.g1_serialize(CV.G1_GEN).hex() == ("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac58"
+                                                 "6c55e83ff97a1aeffb3af00adb22c6bb")
+    assert PP.g1_serialize(None) == bytes([0xC0]) + bytes(47)
+    assert PP.g1_serialize(CV.g1_neg(CV.G1_GEN))[0] == 0xB7  # the other root of y: sign flag set
+    for pt in (CV.G1_GEN, CV.g1_neg(CV.G1_GEN), CV.g1_mul(12345, CV.G1_GEN), None):
+        assert PP.g1_deserialize(PP.g1_serialize(pt)) == pt
+    # Bandersnatch over Fr
+    assert CV.TE_A % P == P - 5
+    assert CV.TE_D == 45022363124591815672509500913686876175488063829319466900776701791074614335719
+    assert CV.TE_D == 0x6389C12633C267CBC66E3BF86BE3B6D8CB66677177E54F92B369F2F5188D58E7
+    assert CV.TE_GEN == (18886178867200960497001835917649091219057080094937609519140440539760939937304,
+                         19188667384257783945677642223292697773471335439753913231509108946878080696678)
+    assert CV.TE_SUBGROUP_ORDER == 13108968793781547619861935127046491459309155893440570251786403306729687672801
+    assert CV.te_on_curve(CV.TE_GEN)
