@@ -208,6 +208,20 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     return GKR_OK;
 }
 
+// Long-running provers: hand the cached large blocks (gkr_malloc_async) and the idle part of the stream-ordered pool back to
+// the driver, e.g. between proofs of very different sizes.  Synchronises the context stream.
+extern "C" int gkr_ctx_trim(gkr_ctx* ctx) {
+    if (!ctx) return GKR_ERR_ARG;
+    GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    ctx->deg2_layout.reset();
+    gkr_big_cache_release(ctx->stream);
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    GKR_CUDA_OK(ctx, cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    GKR_CUDA_OK(ctx, cudaMemPoolTrimTo(pool, 0));
+    return GKR_OK;
+}
+
 extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);

@@ -61,6 +61,8 @@ typedef enum gkr_gate_id {
 /* ---- context ------------------------------------------------------------------------------- */
 int gkr_ctx_create(int device, gkr_ctx** out);
 void gkr_ctx_destroy(gkr_ctx* ctx);
+/* release the cached large device blocks and the idle part of the memory pool (between proofs of very different sizes) */
+int gkr_ctx_trim(gkr_ctx* ctx);
 const char* gkr_last_error(const gkr_ctx* ctx);
 int gkr_ctx_sync(gkr_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's `gpu_launches`) */

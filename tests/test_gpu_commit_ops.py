@@ -174,3 +174,17 @@ def test_bucketize_device_equals_host(ctx, n, y_size, d):
             off += ln
     exp = np.concatenate(exp) if exp else np.zeros(0, np.uint32)
     assert np.array_equal(dpo, exp)
+
+
+def test_ctx_trim_keeps_the_context_usable(ctx):
+    """gkr_ctx_trim hands cached blocks back to the driver; objects created afterwards work as before"""
+    import ctypes as C
+
+    t = ctx.synth(3, 1 << 18)  # 8 MiB: goes through the large-block cache
+    before = t.download()[:4].copy()
+    t.free()
+    ctx.lib.gkr_ctx_trim.restype = C.c_int
+    ctx.lib.gkr_ctx_trim.argtypes = [C.c_void_p]
+    ctx.check(ctx.lib.gkr_ctx_trim(ctx.h))
+    t2 = ctx.synth(3, 1 << 18)
+    assert np.array_equal(t2.download()[:4], before)
