@@ -63,7 +63,6 @@ def _sig(lib):
     f("gkr_ctx_set_fast_fold", C.c_int, _vp, C.c_int)
     f("gkr_ctx_host_stats", C.c_int, _vp, _vp, C.c_int)
     f("gkr_ctx_timing_read", C.c_int, _vp, _vp, _vp, _vp, C.c_int)
-    f("gkr_bench_modmul", C.c_int, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double))
     f("gkr_table_upload", C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp))
     f("gkr_table_download", C.c_int, _vp, _vp, _vp)
     f("gkr_table_alloc", C.c_int, _vp, C.c_uint64, C.POINTER(_vp))
@@ -183,11 +182,6 @@ class Context:
         ms = np.zeros(max_n, np.float32)
         n = self.lib.gkr_ctx_timing_read(self.h, _ptr(kid), _ptr(items), _ptr(ms), max_n)
         return [(int(kid[i]), int(items[i]), float(ms[i])) for i in range(n)]
-
-    def bench_modmul(self, ilp=2, threads=128, blocks_per_sm=8, iters=2000) -> float:
-        out = C.c_double(0)
-        self.check(self.lib.gkr_bench_modmul(self.h, ilp, threads, blocks_per_sm, iters, C.byref(out)))
-        return out.value
 
     # -- tables ------------------------------------------------------------------------------
     def upload(self, limbs) -> "Table":

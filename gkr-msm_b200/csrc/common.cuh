@@ -93,6 +93,7 @@ struct gkr_ctx {
     // pageable ones, no synchronisation until the ring wraps)
     // kernel-selection thresholds (defaults measured on B200; GKR_DENSE_SMALL_MAX / GKR_DEG2_COMPACT_MAX override them for experiments)
     uint64_t dense_small_max = 4096, deg2_compact_max = 32768;
+    int dense_flavor = 0;  // large dense rounds: 0 register kernel (dense_kernel.cuh), 1 node-split kernel (dense_split_kernel.cuh); GKR_DENSE_FLAVOR
     gkr_msm_team* team = nullptr;        // leader only: large gkr_msm_g1 calls are shared with the worker ranks
     uint64_t team_min_n = (uint64_t)1 << 18;
     std::shared_ptr<Deg2Layout> deg2_layout;  // reused by consecutive VecVec objects over the same rows

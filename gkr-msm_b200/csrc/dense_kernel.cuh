@@ -196,3 +196,120 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_small_kernel(const _
         for (int k = 0; k < 8; k++) acc[s].l[k] = (node == (uint32_t)s) ? mine.l[k] : 0u;
     grid_reduce_to_host<DEG>(acc, smem, A.o);
 }
+
+
+// ---- staged variant: tables flow HBM -> shared memory by cp.async (LDGSTS), one tile ahead ----------------------------
+// The register kernel above runs at 12 warps / SM, and every warp stalls on its own 256-bit table loads (ncu: long
+// scoreboard 1.6 cycles per issue at 39 % issue-active).  Here the loads never touch the register file: each WARP owns a
+// private shared-memory tile per table (32 items x ELEMS elements = 4 KiB for quads), filled by 16-byte cp.async copies
+// that are issued one whole iteration before the data is consumed -- table j of the next tile is requested as soon as
+// table j of the current one has been read into registers, so the copy overlaps the remaining folds and all gate
+// evaluations of the current tile.  No block-wide barrier: a tile is produced and consumed by the same warp
+// (cp.async.wait_group + __syncwarp).  Shared-memory layout: 16-byte chunk c of a tile sits at position
+// c ^ ((c >> 3) & 7) (the 128-byte XOR swizzle), which makes both the lane-contiguous cp.async writes and the
+// "lane t reads ITS 128 / 64 bytes" LDS.128 reads bank-conflict free.
+// Requires n_items % 32 == 0 (whole tiles); launch_dense_round falls back to the register kernel otherwise.
+#define GKR_STAGED_WARPS (GKR_REDUCE_THREADS / 32)
+
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int ELEMS>
+__device__ __forceinline__ void staged_issue_tile(uint32_t tile_smem, const Fr* gsrc, uint32_t lane) {
+    // tile = 32 * ELEMS elements = 64 * ELEMS chunks of 16 B; lane copies chunks lane, lane + 32, ...
+    const char* g = reinterpret_cast<const char*>(gsrc);
+#pragma unroll
+    for (int k = 0; k < 2 * ELEMS; k++) {
+        const uint32_t c = lane + 32 * k;
+        cp_async16(tile_smem + 16 * (c ^ ((c >> 3) & 7)), g + 16 * c);
+    }
+}
+__device__ __forceinline__ Fr staged_read_elem(const uint4* tile, uint32_t elem) {
+    const uint32_t c0 = 2 * elem, c1 = c0 + 1;
+    const uint32_t sw = (c0 >> 3) & 7;
+    const uint4 lo = tile[c0 ^ sw], hi = tile[c1 ^ sw];
+    Fr r;
+    r.l[0] = lo.x; r.l[1] = lo.y; r.l[2] = lo.z; r.l[3] = lo.w;
+    r.l[4] = hi.x; r.l[5] = hi.y; r.l[6] = hi.z; r.l[7] = hi.w;
+    return r;
+}
+
+template <class SO, int MODE, bool FAST, int MINB = 3>
+__global__ void __launch_bounds__(GKR_REDUCE_THREADS, MINB) dense_round_staged_kernel(const __grid_constant__ DenseRoundArgs A) {
+    static_assert(MODE == 0 || MODE == 1, "staged kernel: eval / fold+eval rounds only");
+    constexpr int P = SO::P, NACC = SO::DEG;
+    constexpr int ELEMS = MODE == 1 ? 4 : 2;              // table elements per item
+    constexpr uint32_t TILE_BYTES = 32 * ELEMS * 32;      // one warp, one table
+    extern __shared__ __align__(128) unsigned char staged_smem[];
+    __shared__ Fr smem[NACC * (GKR_REDUCE_THREADS / 32)];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* my = staged_smem + (size_t)warp * P * TILE_BYTES;
+    const uint32_t my_addr = (uint32_t)__cvta_generic_to_shared(my);
+
+    WideAccs<NACC, false> W;
+    W.init(nullptr);
+
+    const uint64_t n_tiles = A.n_items >> 5;
+    const uint64_t tile_stride = (uint64_t)gridDim.x * GKR_STAGED_WARPS;
+    uint64_t tile = (uint64_t)blockIdx.x * GKR_STAGED_WARPS + warp;
+    if (tile < n_tiles) {
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            staged_issue_tile<ELEMS>(my_addr + j * TILE_BYTES, A.in[j] + (uint64_t)ELEMS * 32 * tile, lane);
+            cp_async_commit();
+        }
+    }
+    for (; tile < n_tiles; tile += tile_stride) {
+        const uint64_t next = tile + tile_stride;
+        const uint64_t i = (tile << 5) + lane;
+        Fr a[P], d[P];
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            cp_async_wait<P - 1>();
+            __syncwarp();
+            const uint4* t4 = reinterpret_cast<const uint4*>(my + j * TILE_BYTES);
+            Fr e[ELEMS];
+#pragma unroll
+            for (int k = 0; k < ELEMS; k++) e[k] = staged_read_elem(t4, ELEMS * lane + k);
+            __syncwarp();
+            if (next < n_tiles) staged_issue_tile<ELEMS>(my_addr + j * TILE_BYTES, A.in[j] + (uint64_t)ELEMS * 32 * next, lane);
+            cp_async_commit();
+            Fr lo, hi;
+            if constexpr (MODE == 1) {
+                if (FAST) {
+                    lo = fr_fold128(e[0], fr_sub(e[1], e[0]), A.t128);
+                    hi = fr_fold128(e[ELEMS - 2], fr_sub(e[ELEMS - 1], e[ELEMS - 2]), A.t128);
+                } else {
+                    lo = fr_add(e[0], fr_mul(A.t, fr_sub(e[1], e[0])));
+                    hi = fr_add(e[ELEMS - 2], fr_mul(A.t, fr_sub(e[ELEMS - 1], e[ELEMS - 2])));
+                }
+                Fr* dst = A.out[j] + 2 * i;
+                dst[0] = lo;
+                dst[1] = hi;
+            } else {
+                lo = e[0];
+                hi = e[1];
+            }
+            a[j] = hi;
+            d[j] = fr_sub(hi, lo);
+        }
+        W.template mac<SO>(0, a, A.consts);
+#pragma unroll
+        for (int s = 1; s < SO::DEG; s++) {
+#pragma unroll
+            for (int j = 0; j < P; j++) a[j] = fr_add(a[j], d[j]);
+            W.template mac<SO>(s, a, A.consts);
+        }
+    }
+    cp_async_wait<0>();
+    Fr acc[NACC];
+#pragma unroll
+    for (int s = 0; s < NACC; s++) acc[s] = W.reduce(s);
+    grid_reduce_to_host<NACC>(acc, smem, A.o);
+}

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "gates.cuh"
 #include "dense_kernel.cuh"
+#include "dense_split_kernel.cuh"
 #include "so.hpp"
 
 // out[j][i] = in[j][2i] + t (in[j][2i+1] - in[j][2i])   -- used for the last round (one pair -> one value)
@@ -74,6 +75,28 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
             {
                 GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : GKR_K_DENSE_FOLD_EVAL, args.n_items);
                 dense_small_kernel<SO, MODE, FAST><<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(args);
+            }
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+            return GKR_OK;
+        }
+    }
+    if constexpr (MODE != 2 && SO::DEG <= 4) {
+        if (ctx->dense_flavor == 1) {  // node-split kernel: one warp per evaluation node
+            static int split_blocks_per_sm = 0;
+            constexpr int threads = 32 * SO::DEG;
+            if (split_blocks_per_sm == 0) {
+                int b = 0;
+                GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_split_kernel<SO, MODE, FAST>, threads, 0));
+                split_blocks_per_sm = std::max(b, 1);
+            }
+            uint64_t want = (args.n_items + 31) / 32;
+            uint64_t cap = std::min<uint64_t>((uint64_t)ctx->num_sms * split_blocks_per_sm, GKR_MAX_BLOCKS);
+            unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+            *n_blocks_out = grid;
+            {
+                GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : GKR_K_DENSE_FOLD_EVAL, args.n_items);
+                dense_round_split_kernel<SO, MODE, FAST><<<grid, threads, 0, ctx->stream>>>(args);
             }
             ctx->launches++;
             GKR_CUDA_OK(ctx, cudaGetLastError());

@@ -177,6 +177,7 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e);
     ctx->num_sms = prop.multiProcessorCount;
     { const char* nf = getenv("GKR_NO_FAST_FOLD"); ctx->no_fast_fold = nf && nf[0] == '1'; }
+    { const char* v = getenv("GKR_DENSE_FLAVOR"); if (v) ctx->dense_flavor = atoi(v); }
     { const char* v = getenv("GKR_DENSE_SMALL_MAX"); if (v && atoll(v) >= 0) ctx->dense_small_max = (uint64_t)atoll(v); }
     { const char* v = getenv("GKR_DEG2_COMPACT_MAX"); if (v && atoll(v) >= 0) ctx->deg2_compact_max = (uint64_t)atoll(v); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);
@@ -508,53 +509,4 @@ extern "C" int gkr_ctx_timing_read(gkr_ctx* ctx, int* kernel_id, uint64_t* n_ite
     }
     ctx->timed.clear();
     return n;
-}
-
-// ---- integer-pipe microbenchmark: ILP independent chains of dependent Montgomery multiplications -----------
-template <int ILP>
-__global__ void modmul_bench_kernel(Fr* out, int iters) {
-    Fr x[ILP], y;
-    for (int k = 0; k < ILP; k++) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) x[k].l[i] = (threadIdx.x + 1) * (i + 3 + k) + blockIdx.x;
-        x[k].l[7] &= 0x3fffffffu;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) y.l[i] = 0x9e3779b9u * (i + 1) + threadIdx.x;
-    y.l[7] &= 0x3fffffffu;
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int k = 0; k < ILP; k++) x[k] = fr_mul(x[k], y);
-    }
-    Fr acc = x[0];
-    for (int k = 1; k < ILP; k++) acc = fr_add(acc, x[k]);
-    if (acc.l[0] == 0x12345678u && acc.l[5] == 77u) out[blockIdx.x * blockDim.x + threadIdx.x] = acc;  // keep the work alive
-}
-
-// Runs `iters` x ILP multiplications per thread on a grid filling the device; returns modmul/s.
-extern "C" int gkr_bench_modmul(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* modmul_per_s) {
-    if (!ctx || !modmul_per_s) return GKR_ERR_ARG;
-    Fr* out = nullptr;
-    int grid = ctx->num_sms * blocks_per_sm;
-    GKR_CUDA_OK(ctx, cudaMalloc(&out, sizeof(Fr) * (size_t)grid * threads));
-    cudaEvent_t a, b;
-    cudaEventCreate(&a);
-    cudaEventCreate(&b);
-    for (int rep = 0; rep < 2; rep++) {
-        cudaEventRecord(a, ctx->stream);
-        if (ilp == 1) modmul_bench_kernel<1><<<grid, threads, 0, ctx->stream>>>(out, iters);
-        else if (ilp == 2) modmul_bench_kernel<2><<<grid, threads, 0, ctx->stream>>>(out, iters);
-        else modmul_bench_kernel<4><<<grid, threads, 0, ctx->stream>>>(out, iters);
-        cudaEventRecord(b, ctx->stream);
-        ctx->launches++;
-    }
-    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, a, b);
-    cudaEventDestroy(a);
-    cudaEventDestroy(b);
-    cudaFree(out);
-    int eff_ilp = ilp == 1 ? 1 : (ilp == 2 ? 2 : 4);
-    *modmul_per_s = (double)grid * threads * (double)iters * eff_ilp / (ms * 1e-3);
-    return GKR_OK;
 }

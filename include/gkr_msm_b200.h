@@ -70,8 +70,8 @@ uint64_t gkr_ctx_launch_count(const gkr_ctx* ctx);
 /* raw cudaStream_t of the context (so callers can record CUDA events on the launching stream) */
 void* gkr_ctx_stream(gkr_ctx* ctx);
 int gkr_version(void);
-/* measurement hooks (bench.py only): per-launch CUDA-event timing on the context stream, and an
- * integer-pipe probe (chains of dependent Montgomery multiplications) giving the modmul/s ceiling. */
+/* measurement hook (bench.py only): per-launch CUDA-event timing on the context stream.  The integer-pipe probes and
+ * the kernel-variant lab live in a separate measurement-only library (csrc/lab/, `make lab`), not in this one. */
 int gkr_ctx_timing_enable(gkr_ctx* ctx, int on);
 /* test hook: on = 0 makes DenseSumcheckObjectSO::bind always use the full Montgomery product instead of the
  * 128-bit-challenge fold (both are bit-exact; tests compare them at sizes the oracle cannot reach). Default on. */
@@ -80,7 +80,6 @@ int gkr_ctx_set_fast_fold(gkr_ctx* ctx, int on);
  * round results, number of waits, kernels launched}; reset != 0 clears the first three. */
 int gkr_ctx_host_stats(gkr_ctx* ctx, uint64_t out[4], int reset);
 int gkr_ctx_timing_read(gkr_ctx* ctx, int* kernel_id, uint64_t* n_items, float* ms, int max_n);
-int gkr_bench_modmul(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* modmul_per_s);
 
 /* ---- dense tables: `Vec<Fr>` resident in HBM ---------------------------------------------------
  * Ownership mirrors the reference: sumcheck objects take their tables by value

@@ -2,6 +2,9 @@
 verify_pippenger): the device prover's proof bytes, output tables, claims and final pairing pair are identical to the
 oracle restatement's on the same points / scalars / SRS, and the oracle VERIFIER accepts the device-made proof and
 recovers the expected MSM (the reference's own end-to-end test, src/cleanup/protocols/pippenger.rs:621-645)."""
+import hashlib
+import json
+import os
 import random
 
 import numpy as np
@@ -19,6 +22,10 @@ from tests.test_oracle_pippenger import make_instance
 from tests.util import from_limbs, to_limbs
 
 pytestmark = pytest.mark.gpu
+
+# digests minted by the INDEPENDENT C++ prover (oracle/c/pippenger_oracle.cpp via tests/golden/make_golden_large.py, which never
+# imports the product package): the byte-level target of the device prover at the BASELINE sizes
+LARGE_GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pippenger_large.json")))
 
 
 def coefs_to_u64(coefs):
@@ -108,6 +115,14 @@ def test_pippenger_full_size_properties(ctx, d, x, nbits, clm):
     tr2 = g.Transcript(b"fgstglsp")  # C++ host orchestration: same proof, outputs and pairing pair
     ndense, nevs, npair = g.run_pippenger_native(ctx, tr2, key.kzg.srs, key.kzg.g0, key.dev, points_xy, coefs_u64, d, x, nbits, clm, to_limbs(r))
     assert tr2.proof() == proof
+    # BYTE PARITY at this size: the proof, the output tables, the claims and the deferred pairing pair are exactly what the
+    # independent CPU prover produced from the same seeded inputs (tests/golden/pippenger_large.json)
+    gold = LARGE_GOLDEN[f"pippenger_d{d}_x{x}_n{nbits}_c{clm}"]
+    assert len(proof) == gold["proof_len"]
+    assert hashlib.sha256(proof).hexdigest() == gold["proof_sha256"], "device proof differs from the independent CPU prover's"
+    assert hashlib.sha256(np.ascontiguousarray(ndense).tobytes()).hexdigest() == gold["dense_output_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(nevs).tobytes()).hexdigest() == gold["claim_evs_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(npair).tobytes()).hexdigest() == gold["pair_sha256"]
     assert all(np.array_equal(a, t.download()) for a, t in zip(ndense, ddense))
     assert from_limbs(nevs) == list(dclaims[1])
     assert np.array_equal(npair[0], dpair[0]) and np.array_equal(npair[1], dpair[1])
@@ -172,3 +187,38 @@ def test_pippenger_single_digit_row_is_rejected_like_the_reference(ctx):
     points_xy = np.stack([to_limbs([p[0] for p in points]), to_limbs([p[1] for p in points])])
     with pytest.raises(g.GkrError):
         g.run_pippenger_native(ctx, g.Transcript(b"fgstglsp"), kzg.srs, kzg.g0, key.dev, points_xy, coefs_to_u64(coefs), d, x, nbits, clm, to_limbs(r))
+
+
+@pytest.mark.parametrize("d,x,nbits,clm", [(8, 10, 253, 2), (10, 12, 128, 0), (4, 9, 64, 1), (7, 8, 252, 0), (6, 11, 100, 3), (9, 9, 31, 1)])
+def test_pippenger_device_vs_cpp_oracle_live(ctx, d, x, nbits, clm):
+    """Sizes and shapes the python prover cannot reach, checked BYTE FOR BYTE against the independent C++ prover run live
+    (oracle/c/pippenger_oracle.cpp, pinned to oracle/pyref in tests/test_pippenger_oracle.py): full-width scalars with
+    y_size = 32 and clm = 2 (the shape of BASELINE config[3]), d = 10 (config[2]), x == d, y_size not a power of two, clm = 3,
+    byte-truncated odd bit widths (pippenger.rs:464-466)."""
+    from oracle import pippenger_oracle as PO
+    from oracle.pyref.field import fq_vec_to_mont_u64
+    rng = np.random.default_rng(5000 + 1000 * d + 10 * x + clm)
+    n = 1 << x
+    cfg = DPP.pippenger_config(d, x, nbits, clm)
+    k0, step = 0xABCDEF + x, 0x9E3779B97F4A7C15
+    points_xy = PO.te_arithmetic_progression(k0, step, n)
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, nbits // 8:] = 0
+    coefs_u64 = raw.view(np.uint64).reshape(n, 4)
+    r = [int.from_bytes(rng.bytes(32), "little") % P for _ in range(cfg["y_logsize"])]
+    tau = int.from_bytes(rng.bytes(32), "little") % P
+    nv = x + clm
+    okey = PO.Key(to_limbs([tau])[0], fq_vec_to_mont_u64([CV.G1_GEN[0], CV.G1_GEN[1]]).reshape(12), nv, to_limbs([2])[0])
+    want = PO.run_pippenger(okey, points_xy, coefs_u64, to_limbs(r), d, x, nbits, clm)
+    key = DPP.KnucklesKey(ctx, DPP.KzgKey.mock_setup(ctx, tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    # the two keys hold the same SRS points
+    got_srs = key.kzg.srs.download_affine()
+    for i in (0, 1, n, 2 * (1 << nv) - 2):
+        assert np.array_equal(np.asarray(got_srs[i]).reshape(12), okey.point(i))
+    okey.close()
+    tr = g.Transcript(b"fgstglsp")
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr, key.kzg.srs, key.kzg.g0, key.dev, points_xy, coefs_u64, d, x, nbits, clm, to_limbs(r))
+    assert tr.proof() == want["proof"], "device proof differs from the independent CPU prover's"
+    assert np.array_equal(ndense, want["dense_output"])
+    assert np.array_equal(nevs, want["claim_evs"])
+    assert np.array_equal(npair, want["pair"])
