@@ -107,6 +107,7 @@ def cpu_port_run(log_n: int, reps: int, min_seconds: float = 0.0):
     sumchecks over 2^log_n x 3 tables.  Returns (evals_per_s, seconds_per_step, threads)."""
     from oracle import coracle
 
+    coracle.use_native()
     n = 1 << log_n
     tabs = [coracle.synth_table(SEED + j, n) for j in range(P_TABLES)]
     claim = coracle.gate_sum(0, 10, tabs)
@@ -132,27 +133,84 @@ def use_all_host_threads():
     return n
 
 
+def cpu_prover_run(x: int, d: int, nbits: int = 128, clm: int = 0, seed: int = 7):
+    """The whole `examples/pippenger` prover on the host cores: oracle/c/pippenger_oracle.cpp (C++ / OpenMP restatement of
+    benchutils::run_pippenger, pinned byte-for-byte to the python oracle and -- through tests/golden/pippenger_large.json --
+    to the device prover), built with -march=native on this machine when gcc is here.  Same synthetic inputs as the GPU leg
+    (tools/bench_pippenger.py): arithmetic-progression points, uniform nbits-bit scalars, mock SRS.  Key setup is NOT timed
+    (neither is build_pippenger_data in the reference's bench, benches/pippenger.rs:40-45)."""
+    from oracle import pippenger_oracle as PO
+    from oracle.pyref import curves as CV
+    from oracle.pyref.field import P as R_MOD
+    from oracle.pyref.field import fq_vec_to_mont_u64, fr_vec_to_mont_u64
+
+    native = True
+    PO.lib(native)
+    rng = np.random.default_rng(seed)
+    n = 1 << x
+    pts = PO.te_arithmetic_progression(0x1234567 + seed, 0x9E3779B97F4A7C15, n)
+    raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    b = raw.view(np.uint8).reshape(n, 32).copy()
+    b[:, nbits // 8:] = 0
+    coefs = b.view(np.uint64).reshape(n, 4)
+    y_size = (nbits + d - 1) // d
+    yl = (y_size - 1).bit_length()
+    r = [int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(yl)]
+    tau = int.from_bytes(rng.bytes(32), "little") % R_MOD
+    t0 = time.perf_counter()
+    key = PO.Key(fr_vec_to_mont_u64([tau])[0], fq_vec_to_mont_u64([CV.G1_GEN[0], CV.G1_GEN[1]]).reshape(12), x + clm, fr_vec_to_mont_u64([2])[0], native=native)
+    t_setup = time.perf_counter() - t0
+    out = PO.run_pippenger(key, pts, coefs, fr_vec_to_mont_u64(r), d, x, nbits, clm)
+    key.close()
+    threads = PO.num_threads(native)
+    return {"value": out["seconds"]["total"] * 1e3, "unit": "ms", "cores": threads, "kind": "port",
+            "sample": f"oracle/c/pippenger_oracle.cpp (C++/OpenMP port of benchutils::run_pippenger), one proof at x={x}, d={d}, {nbits} bit, clm {clm}, "
+                      f"{threads} threads, build {os.path.basename(key.l._path)}; SRS setup {t_setup:.1f} s not included",
+            "phases_s": out["seconds"], "proof_bytes": len(out["proof"]),
+            "note": "the Rust reference's `--features parallel` build is not measurable in this image (no cargo, nightly + un-vendored git deps)"}
+
+
+def cpu_prover_baselines(budget_s: float):
+    """x = 16 (BASELINE config[0]) always; the 2^20-point shape only when its extrapolated time fits the budget"""
+    res = {}
+    try:
+        res["pippenger_prove"] = cpu_prover_run(16, 8)
+        est20 = res["pippenger_prove"]["value"] * 1e-3 * 14.0  # 13 x the incidences + a 16 x larger opening
+        if est20 <= budget_s:
+            res["pippenger_prove_2e20"] = cpu_prover_run(20, 10)
+        else:
+            res["pippenger_prove_2e20"] = {"skipped": f"extrapolated {est20:.0f} s of CPU time exceeds the {budget_s:.0f} s budget (--cpu-prover-budget)"}
+    except Exception as e:  # pragma: no cover
+        res["error"] = repr(e)
+    return res
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is a Rust crate
-    (nightly + un-vendored git deps) that cannot be built in this image, so this arm times the oracle's C
-    port of the same algorithm (oracle/c/gkr_oracle.c) on all host threads -- rank 0 only."""
+    (nightly + un-vendored git deps) that cannot be built in this image, so this arm times the oracle's C / C++
+    ports of the same algorithms on all host threads -- rank 0 only:
+      metric line : oracle/c/gkr_oracle.c, the dense sumcheck object, on the SAME 2^log_n x 3 workload as the GPU arm
+      extra keys  : oracle/c/pippenger_oracle.cpp, the whole prover (the first half of BASELINE.json's metric)"""
     if rank != 0:
         return
     use_all_host_threads()
-    log_n = args.ref_log_n
-    for _ in range(args.warmup):
+    log_n = args.ref_log_n if args.ref_log_n > 0 else args.log_n
+    for _ in range(min(args.warmup, 1)):
         cpu_port_run(log_n, 1)
-    val, sec, threads, reps = cpu_port_run(log_n, args.steps)
+    val, sec, threads, reps = cpu_port_run(log_n, min(args.steps, 5))
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": reps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u256 (BLS12-381 Fr, 4x64-bit Montgomery limbs)", "data": "synthetic",
-        "config": {"workload": f"dense Prod3 sumcheck, P=3 tables x 2^{args.log_n} Fr (config[1])",
-                   "sample": f"each step = one full sumcheck over 2^{log_n} x 3 tables (bounded sample of the 2^{args.log_n} workload)"},
+        "config": {"workload": f"dense Prod3 sumcheck, P=3 tables x 2^{args.log_n} Fr (config[1])", "same_size_as_gpu_arm": log_n == args.log_n,
+                   "sample": f"each step = one full sumcheck over 2^{log_n} x 3 tables",
+                   "what": "reference PORT (oracle/c/gkr_oracle.c, OpenMP): the Rust crate cannot be built in this image"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"full Prod3 sumcheck, 2^{log_n} x 3 tables, median of {reps} runs, OpenMP {threads} threads"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if not args.no_pippenger:
+        line["pippenger_cpu"] = cpu_prover_baselines(args.cpu_prover_budget)
     print(json.dumps(line), flush=True)
 
 
@@ -214,31 +272,76 @@ def run_ours(args, rank, world, local_rank):
     total_units = elem_rounds(log_n + (world.bit_length() - 1))
     value = total_units / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel: the first fused fold+eval launch (2^log_n -> 2^(log_n-1)) -----
+    # ---- roofline: every (kernel, size) group of the timed launches; the DOMINANT kernel is the longest one -------------
     peak, peak_src = load_peaks()
-    dom = [ms for (kid, items, ms) in launches_timed if kid == 1 and items == (n >> 2)]
-    alg_bytes = 48 * P_TABLES * n  # 32 B read + 16 B written per table element
+    groups = {}
+    for (kid, items, ms) in launches_timed:
+        groups.setdefault((kid, items), []).append(ms)
+    KNAME = {0: "dense round kernel, eval only (round 0)", 1: "dense round kernel, fused fold(k) + eval(k+1)", 2: "dense gate sum", 3: "dense fold"}
+    # wide (32x32+64 -> 64 bit) multiply-adds per item, from the generator's operation counts (tools/gen_field.py):
+    #   fold by a 128-bit challenge 56, Montgomery product 112, unreduced multiply-accumulate 64
+    #   eval only : 3 nodes x (112 + 64)                       = 528 per pair-triple
+    #   fused     : 6 folds x 56 + 3 nodes x (112 + 64)         = 864 per quad-triple
+    WIDE = {0: 528, 1: 864}
+    roofline_all = []
+    for (kid, items), mss in groups.items():
+        if kid not in (0, 1):
+            continue
+        avg_ms = sum(mss) / len(mss)
+        # algorithmic bytes: eval reads 2 x 32 B per pair and table; fused reads 4 x 32 B and writes 2 x 32 B per quad and table
+        alg = (64 if kid == 0 else 192) * P_TABLES * items
+        roofline_all.append({"kernel": KNAME[kid], "items": items, "launches": len(mss), "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg,
+                             "achieved_gbs": alg / (avg_ms * 1e-3) / 1e9, "frac_hbm": alg / (avg_ms * 1e-3) / 1e9 / peak,
+                             "wide_mads_per_launch": WIDE[kid] * items, "achieved_wide_mads_per_s": WIDE[kid] * items / (avg_ms * 1e-3)})
+    roofline_all.sort(key=lambda e: -e["avg_launch_ms"])
+    kernel_ms = sum(ms for (_, _, ms) in launches_timed) / args.steps
     roofline = None
-    if dom:
-        avg_ms = sum(dom) / len(dom)
-        ach = alg_bytes / (avg_ms * 1e-3) / 1e9
-        kernel_ms = sum(ms for (_, _, ms) in launches_timed) / args.steps
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at 2^24 from the committed ncu --set full capture
-        # (profiles/r01c_ncu_full_dense_round_prod3_fold_eval.csv): 1.610745 GB + 0.780195 GB per launch; other sizes: not captured
-        traffic = 1610745000 + 780194560 if log_n == 24 else None
-        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": "profiles/r01c_ncu_full_dense_round_prod3_fold_eval.csv (ncu --set full, one launch)",
-                    "kernel": "dense_round_kernel<SoProd3, fold+eval> (first fused round)", "avg_launch_ms": avg_ms,
-                    "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                    "share_of_kernel_time": avg_ms / kernel_ms if kernel_ms else None,
-                    "kernel_ms_per_step": kernel_ms, "modmul_per_launch": 12 * (n >> 2)}
+    if roofline_all:
+        dom = roofline_all[0]
+        roofline = {"bound": "hbm", "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_hbm"], "traffic": None,
+                    "kernel": dom["kernel"] + f", {dom['items']} items (the LONGEST launch of the step)", "avg_launch_ms": dom["avg_launch_ms"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "peak_source": peak_src,
+                    "share_of_kernel_time": dom["avg_launch_ms"] / kernel_ms if kernel_ms else None, "kernel_ms_per_step": kernel_ms,
+                    "note": "both large dense kernels are bound by the 32-bit multiplier pipe before HBM (int_pipe below); "
+                            "the fused fold+eval round is the HBM-relevant one (roofline_all[1])"}
+        # whole step against HBM: 96 * P * 2^n algorithmic bytes over the step time
+        roofline["whole_step"] = {"algorithmic_bytes": 96 * P_TABLES * n, "achieved_gbs": 96 * P_TABLES * n / (ms_step * 1e-3) / 1e9,
+                                  "frac_hbm": 96 * P_TABLES * n / (ms_step * 1e-3) / 1e9 / peak}
+        # measured DRAM traffic of the dominant kernels: only from an ncu capture of THIS build (profiles/r02_traffic.json records
+        # the sha256 of the kernel sources it was taken from); stale captures are not reported
         try:
-            mm = ctx.bench_modmul(ilp=2, threads=128, blocks_per_sm=8, iters=1000)
-            roofline["int_pipe"] = {"achieved_modmul_per_s": 12 * (n >> 2) / (avg_ms * 1e-3), "peak_modmul_per_s": mm,
-                                    "frac": 12 * (n >> 2) / (avg_ms * 1e-3) / mm,
-                                    "how": "peak = chains of dependent 8x32-bit Montgomery multiplications, ILP 2, 8 blocks x 128 thr per SM"}
+            import hashlib
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            h = hashlib.sha256()
+            for f in tj["sources"]:
+                h.update(open(os.path.join(ROOT, f), "rb").read())
+            if h.hexdigest() == tj["sources_sha256"] and tj.get("log_n") == log_n:
+                for e in roofline_all:
+                    key = "eval" if e["kernel"].startswith("dense round kernel, eval") else "fused"
+                    if e["items"] == tj[key]["items"]:
+                        e["traffic"] = tj[key]["dram_bytes"]
+                roofline["traffic"] = roofline_all[0].get("traffic")
+                roofline["traffic_source"] = tj["source"]
+            else:
+                roofline["traffic_source"] = "no ncu capture of this exact kernel build (profiles/r02_traffic.json is older than the sources)"
+        except Exception:
+            roofline["traffic_source"] = "no ncu capture recorded for this build"
+        # multiplier-pipe roofline: achieved wide multiply-adds per second over the measured peak of the same instruction
+        try:
+            from tools import lablib
+            pk = max(lablib.imad_wide_peak(ctx, ilp=ilp) for ilp in (8, 16))
+            for e in roofline_all:
+                e["frac_int_pipe"] = e["achieved_wide_mads_per_s"] / pk
+            roofline["int_pipe"] = {"achieved_wide_mads_per_s": dom["achieved_wide_mads_per_s"], "peak_wide_mads_per_s": pk,
+                                    "frac": dom["achieved_wide_mads_per_s"] / pk,
+                                    "how": "peak = IMAD.WIDE.U32 probe, 8-16 independent accumulators per thread, 8 x 256 threads per SM "
+                                           "(csrc/lab/kernel_lab.cu); achieved = static multiply-add count of the field routines x items / "
+                                           "measured launch time.  The kernels issue carry-chained IMAD.WIDE.U32.X plus ~1.3 non-multiply "
+                                           "integer instructions per multiply-add, so the fraction understates how busy the pipe is "
+                                           "(ncu: sm__inst_executed_pipe_fmaheavy, profiles/)"}
         except Exception as e:  # pragma: no cover
             roofline["int_pipe"] = {"error": str(e)}
+        roofline["roofline_all"] = roofline_all
 
     # ---- end-to-end arm: host (pinned) tables in, round messages + final evals out -------------------
     job.prepare_host_inputs()
@@ -263,6 +366,50 @@ def run_ours(args, rank, world, local_rank):
            "d2h_bytes_per_step": job.d2h_bytes * world, "ms_per_step": e2e_ms_step, "wall_ms_per_step": wall / args.e2e_steps,
            "steps": args.e2e_steps}
 
+    # ---- N > 1: strong-scaling leg (the SAME 2^log_n total table split over the ranks) next to the weak one above --------
+    strong = None
+    if world > 1 and log_n - (world.bit_length() - 1) >= 10:
+        ln_local = log_n - (world.bit_length() - 1)
+        sjob = ShardedProd3Sumcheck(ctx, log_n_local=ln_local, rank=rank, world=world, dist=dist, seed=SEED, exchange=job.exchange)
+        for _ in range(3):
+            sjob.prove_resident()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            sjob.prove_resident()
+        s1.record(stream)
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        s_ms = float(t.item()) / args.steps
+        strong = {"total_log_n": log_n, "log_n_per_gpu": ln_local, "ms_per_step": s_ms, "value": elem_rounds(log_n) / (s_ms * 1e-3), "unit": UNIT,
+                  "what": f"strong scaling: ONE 2^{log_n} x 3 sumcheck split by top index bits over {world} GPUs; compare with the 1-GPU ms_per_step of the "
+                          "weak line (same total work).  Limiter: the ~20 small rounds and the per-round host exchange are latency, not bandwidth"}
+        del sjob
+
+    # ---- N > 1: the whole prover with the commitment MSMs split by point range over the ranks (csrc/msm_team.cu) -----------
+    pip20_multi = None
+    if world > 1 and not args.no_pippenger and not args.no_pippenger_2e20:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("bench_pippenger", os.path.join(ROOT, "tools", "bench_pippenger.py"))
+        bp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bp)
+        tname = f"/gkr_team_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        pa = argparse.Namespace(x_logsize=20, d_logsize=10, nbits=128, clm=0, reps=4, seed=7, profile=False, python_host=False, gpus=world,
+                                team_worker=rank, team_name=tname, team_tau="%x" % bp.srs_tau(7))
+        try:
+            if rank == 0:
+                r = bp.run(pa, ctx=ctx, team_name=tname)
+                pip20_multi = {"prove_ms": r["prove_ms_best"], "prove_ms_median": statistics.median(r["prove_ms_all"][1:]), "prove_ms_all": r["prove_ms_all"],
+                               "config": f"x_logsize 20, d_logsize 10, nbits 128, clm 0 on {world} GPUs", "proof_bytes": r["proof_bytes"],
+                               "multi_gpu": r["multi_gpu"], "gpu_launches_rank0": r["gpu_launches"]}
+            else:
+                bp.team_worker(pa, ctx=ctx)
+        except Exception as e:  # pragma: no cover
+            pip20_multi = {"error": repr(e)}
+        barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -271,9 +418,12 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         use_all_host_threads()
-        val, sec, threads, reps = cpu_port_run(args.ref_log_n, 3, min_seconds=10.0)
+        ref_ln = args.ref_log_n if args.ref_log_n > 0 else log_n
+        val, sec, threads, reps = cpu_port_run(ref_ln, 3, min_seconds=5.0)
         cpu = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle C port (OpenMP), full Prod3 sumcheck over 2^{args.ref_log_n} x 3 tables, median of {reps} runs ({sec:.3f} s each)"}
+               "sample": f"oracle C port (oracle/c/gkr_oracle.c, OpenMP, -march=native when gcc is on the box), full Prod3 sumcheck over 2^{ref_ln} x 3 tables "
+                         f"(the GPU arm's size: {ref_ln == log_n}), median of {reps} runs ({sec:.3f} s each)",
+               "note": "the Rust reference's `--features parallel` rayon build is not measurable in this image (no cargo)"}
 
     # ---- secondary: the whole `examples/pippenger` prover: BASELINE config[0] (x=16, d=8, 128 bit, clm 0) and the 2^20-point
     # shape of config[2] (x=20, d=10, 128 bit) on this one GPU -- "GKR-MSM prove ms @2^20 pts/128-bit" of BASELINE.json's metric
@@ -299,6 +449,17 @@ def run_ours(args, rank, world, local_rank):
         except Exception as e:  # pragma: no cover
             pip = pip or {"error": repr(e)}
             pip20 = pip20 or {"error": repr(e)}
+        if not args.no_cpu_baseline:  # the same prover on the host cores (oracle/c/pippenger_oracle.cpp)
+            use_all_host_threads()
+            cb = cpu_prover_baselines(args.cpu_prover_budget)
+            if isinstance(pip, dict) and "pippenger_prove" in cb:
+                pip["cpu_baseline"] = cb["pippenger_prove"]
+            if isinstance(pip20, dict) and "pippenger_prove_2e20" in cb:
+                pip20["cpu_baseline"] = cb["pippenger_prove_2e20"]
+            if "error" in cb and isinstance(pip, dict):
+                pip["cpu_baseline"] = {"error": cb["error"]}
+    if world > 1:
+        pip20 = pip20_multi
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -308,9 +469,13 @@ def run_ours(args, rank, world, local_rank):
                                f"P=3 tables x 2^{log_n} Fr per GPU (BASELINE config[1])",
                    "log_n_per_gpu": log_n, "n_tables": P_TABLES, "gate": "Prod3Fn", "rounds": log_n + (world.bit_length() - 1),
                    "parallelism": f"hypercube sharded by top index bits over {world} GPU(s)",
+                   "collective": ("none (one GPU)" if world == 1 else
+                                  "per-round partial sums (deg x 32 B per rank) all-gathered through a POSIX shared-memory segment between the ranks of the "
+                                  "box and reduced on every host (they must reach the host transcript anyway); NCCL only for rendezvous, barriers and "
+                                  "the max-over-ranks timing all-reduce; no device collective on the data path"),
                    "l2": "inputs (1.5 GiB per GPU) larger than the 126 MB L2", "transcript": "merlin on host, one challenge per round"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "pippenger_prove": pip, "pippenger_prove_2e20": pip20,
+        "pippenger_prove": pip, "pippenger_prove_2e20": pip20, "strong_scaling": strong,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -324,7 +489,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=24)
-    ap.add_argument("--ref-log-n", type=int, default=20)
+    ap.add_argument("--ref-log-n", type=int, default=0, help="size of the CPU arm's sumcheck (0: the GPU arm's --log-n)")
+    ap.add_argument("--cpu-prover-budget", type=float, default=150.0, help="seconds of CPU time allowed for the x=20 whole-prover baseline")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pippenger", action="store_true")

@@ -16,7 +16,7 @@
 #define GKR_MAX_DEG 4           // max number of accumulated evaluation points per round
 #define GKR_REDUCE_THREADS 128  // block size of the sumcheck round kernels
 #define GKR_MAX_BLOCKS 1024     // upper bound on the grid of a round kernel (one partial per block and accumulator)
-#define GKR_RESULT_SLOTS 64     // live sumcheck objects per context
+#define GKR_RESULT_SLOTS 128    // live sumcheck objects per context (128 KiB of pinned, mapped host memory each)
 
 // Result channel of one sumcheck object, in pinned host memory mapped into the device address space.  Every block of a
 // round kernel writes its partial sums here; the last block (device ticket) publishes `flag = seq`.  The host spins on
@@ -93,7 +93,10 @@ struct gkr_ctx {
     // pageable ones, no synchronisation until the ring wraps)
     // kernel-selection thresholds (defaults measured on B200; GKR_DENSE_SMALL_MAX / GKR_DEG2_COMPACT_MAX override them for experiments)
     uint64_t dense_small_max = 4096, deg2_compact_max = 32768;
-    int dense_flavor = 0;  // large dense rounds: 0 register kernel (dense_kernel.cuh), 1 node-split kernel (dense_split_kernel.cuh); GKR_DENSE_FLAVOR
+    // large dense rounds (GKR_DENSE_FLAVOR): 2 (default) cp.async-staged kernel for fused rounds of <= 4 tables, register kernel otherwise;
+    // 0 register kernel only; 1 node-split kernel (dense_split_kernel.cuh, measured slower: kept for the lab)
+    int dense_flavor = 2;
+    uint64_t dense_staged_min = (uint64_t)1 << 13;  // items (quads) from which the staged kernel is used (GKR_DENSE_STAGED_MIN)
     gkr_msm_team* team = nullptr;        // leader only: large gkr_msm_g1 calls are shared with the worker ranks
     uint64_t team_min_n = (uint64_t)1 << 18;
     std::shared_ptr<Deg2Layout> deg2_layout;  // reused by consecutive VecVec objects over the same rows

@@ -29,7 +29,7 @@ void gkr_result_slot_release(gkr_ctx* ctx, int slot);
 int gkr_eq_build_device(gkr_ctx* ctx, const Fr* d_point, uint32_t n, const Fr& mult, Fr* d_out);
 
 // defined in deg2_compact.cu: the same kernel built with the out-of-line multiplier
-int gkr_launch_deg2_round_compact(const Deg2RoundArgs& a, dim3 grid, unsigned threads, cudaStream_t stream);
+int gkr_launch_deg2_round_compact(int uniform_gate, const Deg2RoundArgs& a, dim3 grid, unsigned threads, cudaStream_t stream);
 
 // ragged fold (VecVecPolynomial::bind_21): grid.y = table
 struct VvFoldArgs {
@@ -338,6 +338,7 @@ class Deg2SO : public gkr_so {
     int cur_set = 0;
     Deg2Block* d_blocks = nullptr;
     int n_blocks = 0;
+    int uniform_gate = -1;  // base gate shared by every gate block of the stack (-1: mixed -> generic kernel)
     Fr* d_gammas = nullptr;
     Fr* d_pads = nullptr;  // [2P]: row pads then col pads
     bool cached = false, sums_pending = false;
@@ -407,9 +408,9 @@ class Deg2SO : public gkr_so {
         if (grid.x == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (2 * n_pairs + 31) / 32 * 32));
         pending_blocks = grid.x * grid.y;
         if (compact) {
-            gkr_launch_deg2_round_compact(a, grid, threads, ctx->stream);
+            gkr_launch_deg2_round_compact(uniform_gate, a, grid, threads, ctx->stream);
         } else {
-            deg2_inline::deg2_round_kernel<<<grid, threads, 0, ctx->stream>>>(a);
+            deg2_inline::launch_deg2_round(uniform_gate, a, grid, threads, ctx->stream);
         }
         ctx->launches++;
         GKR_CUDA_OK(ctx, cudaGetLastError());
@@ -547,6 +548,10 @@ int Deg2SO::setup(const std::vector<const Fr*>& inputs) {
     // gate program, gammas, pads
     std::vector<Deg2Block> blocks = expand_blocks(gs);
     n_blocks = (int)blocks.size();
+    uniform_gate = blocks.empty() ? -1 : blocks[0].gate;
+    for (const auto& b : blocks)
+        if (b.gate != uniform_gate) uniform_gate = -1;
+    { const char* v = getenv("GKR_DEG2_GENERIC"); if (v && v[0] == '1') uniform_gate = -1; }  // test hook: force the generic kernel
     std::vector<Fr> g(gs.n_outs);
     for (int i = 0; i < gs.n_outs; i++) g[i] = fr_from_host(gamma_pows[i]);
     std::vector<Fr> pads(2 * P);

@@ -4,7 +4,7 @@
 #define GKR_COMPACT_FIELD
 #include "deg2_kernel.cuh"
 
-int gkr_launch_deg2_round_compact(const Deg2RoundArgs& a, dim3 grid, unsigned threads, cudaStream_t stream) {
-    deg2_compact::deg2_round_kernel<<<grid, threads, 0, stream>>>(a);
+int gkr_launch_deg2_round_compact(int uniform_gate, const Deg2RoundArgs& a, dim3 grid, unsigned threads, cudaStream_t stream) {
+    deg2_compact::launch_deg2_round(uniform_gate, a, grid, threads, stream);
     return 0;
 }

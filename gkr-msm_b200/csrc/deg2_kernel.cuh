@@ -103,6 +103,12 @@ __device__ __forceinline__ Fr deg2_block_round(const Deg2RoundArgs& A, const Deg
 }
 
 // grid = (x: pair lanes, y: gate blocks).  All blocks reduce into the same three sums.
+// GSEL >= 0: every gate block of the launch is the same base gate (true for all stacks of the reference except
+// Stacked(affine L1, Repeated(BitCheck, 2)): TRI_L1 decomposes into three PRJ_L1 blocks, Repeated(g, n) into n blocks of
+// g), so the kernel holds ONE inlined gate instead of a 9-way switch over all of them -- round 1's generic kernel was
+// ~40 k SASS instructions and spent 4.6 cycles per issue waiting for instruction fetch on mid-size rounds
+// (profiles/r01_ncu_full_deg2_inline_round.csv).  GSEL < 0: the generic kernel (mixed stacks).
+template <int GSEL>
 __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __grid_constant__ Deg2RoundArgs A) {
     __shared__ Fr smem[3 * (GKR_REDUCE_THREADS / 32)];
     Fr mine = fr_zero();
@@ -144,6 +150,9 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
             }
         }
         Fr v = fr_zero();
+        if constexpr (GSEL >= 0) {
+            v = deg2_block_round<GSEL>(A, blk, active, q, role, row, idx, w);
+        } else
         switch (blk.gate) {
             case GATE_AFF_L1: v = deg2_block_round<GATE_AFF_L1>(A, blk, active, q, role, row, idx, w); break;
             case GATE_AFF_L2: v = deg2_block_round<GATE_AFF_L2>(A, blk, active, q, role, row, idx, w); break;
@@ -200,6 +209,24 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
         }
     }
     grid_reduce_to_host<3>(acc, smem, A.o);
+}
+
+// host side: pick the instantiation (uniform_gate < 0: generic)
+static inline void launch_deg2_round(int uniform_gate, const Deg2RoundArgs& a, dim3 grid, unsigned threads, cudaStream_t stream) {
+    switch (uniform_gate) {
+#define GKR_DEG2_CASE(G) case G: deg2_round_kernel<G><<<grid, threads, 0, stream>>>(a); break;
+        GKR_DEG2_CASE(GATE_AFF_L1)
+        GKR_DEG2_CASE(GATE_AFF_L2)
+        GKR_DEG2_CASE(GATE_AFF_L3)
+        GKR_DEG2_CASE(GATE_PRJ_L1)
+        GKR_DEG2_CASE(GATE_PRJ_L2)
+        GKR_DEG2_CASE(GATE_PRJ_L3)
+        GKR_DEG2_CASE(GATE_BITCHECK)
+        GKR_DEG2_CASE(GATE_LOGUP_LAYER)
+        GKR_DEG2_CASE(GATE_ADD_INVERSES)
+#undef GKR_DEG2_CASE
+        default: deg2_round_kernel<-1><<<grid, threads, 0, stream>>>(a); break;
+    }
 }
 
 }  // namespace GKR_DEG2_NS

@@ -81,6 +81,32 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
             return GKR_OK;
         }
     }
+    if constexpr (MODE == 1 && SO::P <= 4) {
+        // fused fold+eval rounds over whole 32-item tiles: tables staged HBM -> shared memory by cp.async one tile ahead
+        // (dense_round_staged_kernel; measured 0.672 -> 0.649 ms on the 2^24 x 3 Prod3 round).  dense_flavor 0 disables it.
+        if (ctx->dense_flavor != 0 && ctx->dense_flavor != 1 && args.n_items % 32 == 0 && args.n_items >= ctx->dense_staged_min) {
+            static int staged_blocks_per_sm = 0;
+            constexpr size_t smem = (size_t)GKR_STAGED_WARPS * SO::P * 32 * 4 * 32;
+            if (staged_blocks_per_sm == 0) {
+                GKR_CUDA_OK(ctx, cudaFuncSetAttribute(dense_round_staged_kernel<SO, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int b = 0;
+                GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_staged_kernel<SO, MODE, FAST>, GKR_REDUCE_THREADS, smem));
+                staged_blocks_per_sm = std::max(b, 1);
+            }
+            // two waves of blocks: the grid-stride tiles of a block that starts late even out the tail
+            uint64_t want = (args.n_items / 32 + GKR_STAGED_WARPS - 1) / GKR_STAGED_WARPS;
+            uint64_t cap = std::min<uint64_t>((uint64_t)ctx->num_sms * staged_blocks_per_sm * 2, GKR_MAX_BLOCKS);
+            unsigned grid = (unsigned)std::max<uint64_t>(1, std::min(want, cap));
+            *n_blocks_out = grid;
+            {
+                GkrLaunchTimer timer(ctx, GKR_K_DENSE_FOLD_EVAL, args.n_items);
+                dense_round_staged_kernel<SO, MODE, FAST><<<grid, GKR_REDUCE_THREADS, smem, ctx->stream>>>(args);
+            }
+            ctx->launches++;
+            GKR_CUDA_OK(ctx, cudaGetLastError());
+            return GKR_OK;
+        }
+    }
     if constexpr (MODE != 2 && SO::DEG <= 4) {
         if (ctx->dense_flavor == 1) {  // node-split kernel: one warp per evaluation node
             static int split_blocks_per_sm = 0;

@@ -178,6 +178,7 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     { const char* nf = getenv("GKR_NO_FAST_FOLD"); ctx->no_fast_fold = nf && nf[0] == '1'; }
     { const char* v = getenv("GKR_DENSE_FLAVOR"); if (v) ctx->dense_flavor = atoi(v); }
+    { const char* v = getenv("GKR_DENSE_STAGED_MIN"); if (v && atoll(v) >= 0) ctx->dense_staged_min = (uint64_t)atoll(v); }
     { const char* v = getenv("GKR_DENSE_SMALL_MAX"); if (v && atoll(v) >= 0) ctx->dense_small_max = (uint64_t)atoll(v); }
     { const char* v = getenv("GKR_DEG2_COMPACT_MAX"); if (v && atoll(v) >= 0) ctx->deg2_compact_max = (uint64_t)atoll(v); }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e);

@@ -39,14 +39,14 @@ def mont_add_many(rows) -> np.ndarray:
 class ShardedProd3Sumcheck:
     P = 3
 
-    def __init__(self, ctx: g.Context, log_n_local: int, rank: int = 0, world: int = 1, dist=None, seed: int = 1):
+    def __init__(self, ctx: g.Context, log_n_local: int, rank: int = 0, world: int = 1, dist=None, seed: int = 1, exchange=None):
         assert world & (world - 1) == 0, "world size must be a power of two"
         self.ctx, self.log_n, self.rank, self.world, self.dist, self.seed = ctx, log_n_local, rank, world, dist, seed
         n = 1 << log_n_local
         self.n = n
         self.tables = [ctx.synth(seed + j, n, first_index=rank * n) for j in range(self.P)]
-        self.exchange = None
-        if world > 1:
+        self.exchange = exchange
+        if world > 1 and exchange is None:
             name = f"/gkr_msm_b200_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
             if rank == 0:
                 self.exchange = g.Exchange(name, rank, world, create=True)

@@ -19,6 +19,22 @@ def build():
     return LIB
 
 
+def use_native() -> bool:
+    """bench.py's CPU legs: switch to a -march=native build made on THIS machine (the reference's README builds with
+    target-cpu=native); keeps the portable prebuilt library when gcc is missing or the library is already loaded."""
+    global LIB
+    if _lib is not None:
+        return LIB.endswith(".native.so")
+    native = os.path.join(_HERE, "c", "libgkr_oracle.native.so")
+    try:
+        if not os.path.exists(native):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "c/libgkr_oracle.native.so"])
+        LIB = native
+        return True
+    except Exception:
+        return False
+
+
 def lib():
     global _lib
     if _lib is None:

@@ -1,3 +1,4 @@
+import gc
 import os
 import sys
 
@@ -18,3 +19,12 @@ def ctx():
     c = g.Context(0)  # raises loudly when there is no GPU / no built extension: no CPU fallback
     yield c
     c.close()
+
+
+@pytest.fixture(autouse=True)
+def _collect_between_tests():
+    """device objects are released by __del__; objects caught in reference cycles (ctx <-> object) wait for the cyclic
+    collector, and a context has a bounded number of result slots -- collect after every test so a long parametrised
+    run (or one slowed down by compute-sanitizer) never runs out"""
+    yield
+    gc.collect()

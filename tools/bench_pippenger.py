@@ -20,22 +20,31 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 
-def team_worker(args):
+def srs_tau(seed: int) -> int:
+    """tau of the mock SRS: its own stream, so the worker ranks of a multi-GPU run derive it without generating the inputs"""
+    from gkr_msm_b200.fieldutil import R_MOD
+    return int.from_bytes(np.random.default_rng(seed ^ 0x7A5).bytes(32), "little") % R_MOD
+
+
+def team_worker(args, ctx=None):
     """rank > 0 of `--gpus N`: same SRS on cuda:rank, then serve slices of the leader's commitment MSMs (csrc/msm_team.cu)"""
     import gkr_msm_b200 as g
     from gkr_msm_b200 import hostmath as H
     from gkr_msm_b200 import pippenger as DPP
 
-    ctx = g.Context(args.team_worker)
+    own = ctx is None
+    ctx = ctx or g.Context(args.team_worker)
     nv = args.x_logsize + args.clm
     kzg = DPP.KzgKey.mock_setup(ctx, int(args.team_tau, 16), H.G1_GEN, 2 * (1 << nv) - 1)
-    team = g.MsmTeam(ctx, args.team_name, args.team_worker, args.gpus, 2 * (1 << nv))
+    team = g.MsmTeam(ctx, args.team_name, args.team_worker, args.gpus, 2 * (1 << nv), open_timeout_s=300.0)
     team.serve(kzg.srs, idle_timeout_s=300.0)
     team.close()
-    ctx.close()
+    if own:
+        ctx.close()
 
 
-def run(args, ctx=None):
+def run(args, ctx=None, team_name=None):
+    """team_name: under torchrun the worker ranks already exist (bench.py): lead the team of that name instead of spawning"""
     import gkr_msm_b200 as g
     from gkr_msm_b200 import hostmath as H
     from gkr_msm_b200 import pippenger as DPP
@@ -61,7 +70,7 @@ def run(args, ctx=None):
     ctx = ctx or g.Context(0)
     t0 = time.perf_counter()
     nv = xl + clm
-    tau = int.from_bytes(rng.bytes(32), "little") % R_MOD
+    tau = srs_tau(args.seed)
     pre_c = getattr(args, "precompute_c", -1)
     if pre_c < 0:
         pre_c = 20 if nv >= 20 else 0  # fixed-base window table of the SRS: measured to pay from 2^21-point commitments (16.4 -> 15.2 ms)
@@ -72,11 +81,12 @@ def run(args, ctx=None):
     team, workers = None, []
     if getattr(args, "gpus", 1) > 1:  # commitment MSMs split by point range over N GPUs: this process leads, N - 1 workers serve
         import subprocess
-        name = f"/gkr_msm_team_{os.getpid()}"
+        name = team_name or f"/gkr_msm_team_{os.getpid()}"
         team = g.MsmTeam(ctx, name, 0, args.gpus, 2 * (1 << nv))
-        for rk in range(1, args.gpus):
-            workers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--x-logsize", str(xl), "--clm", str(clm), "--gpus", str(args.gpus),
-                                             "--team-worker", str(rk), "--team-name", name, "--team-tau", "%x" % tau]))
+        if team_name is None:
+            for rk in range(1, args.gpus):
+                workers.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--x-logsize", str(xl), "--clm", str(clm), "--gpus", str(args.gpus),
+                                                 "--team-worker", str(rk), "--team-name", name, "--team-tau", "%x" % tau]))
         team.wait_ready(timeout_s=300.0)
 
     times, proof_len, launches = [], 0, 0
