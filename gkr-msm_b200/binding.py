@@ -437,6 +437,23 @@ class Transcript:
             raise GkrError(rc, "raw_challenge")
         return bytes(buf)
 
+    # -- old API (src/transcript.rs:78-101) --
+    def append_scalars_old(self, limbs):
+        a = _limbs(limbs).reshape(-1, 4)
+        self.lib.gkr_transcript_append_scalars_old.argtypes = [_vp, _vp, C.c_uint32]
+        rc = self.lib.gkr_transcript_append_scalars_old(self.h, _ptr(a), a.shape[0])
+        if rc:
+            raise GkrError(rc, "append_scalars_old: non-canonical element")
+
+    def challenge_scalar_old(self, label: bytes) -> np.ndarray:
+        out = np.zeros(4, np.uint64)
+        buf = (C.c_uint8 * len(label)).from_buffer_copy(label) if label else None
+        self.lib.gkr_transcript_challenge_scalar_old.argtypes = [_vp, _vp, C.c_size_t, _vp]
+        rc = self.lib.gkr_transcript_challenge_scalar_old(self.h, buf, len(label), _ptr(out))
+        if rc:
+            raise GkrError(rc, "challenge_scalar_old")
+        return out
+
     def proof(self) -> bytes:
         n = int(self.lib.gkr_transcript_proof_len(self.h))
         buf = (C.c_uint8 * max(n, 1))()

@@ -1,4 +1,5 @@
 // extern "C" surface declared in include/gkr_msm_b200.h: thin argument checking + dispatch.
+#include <atomic>
 #include "common.cuh"
 #include "so.hpp"
 #include "transcript.hpp"
@@ -108,6 +109,31 @@ extern "C" int gkr_transcript_raw_challenge(gkr_transcript* t, uint8_t* out, siz
     return GKR_OK;
 }
 
+// old API transcript (src/transcript.rs:78-101, `impl TranscriptReceiver / TranscriptSender for merlin::Transcript`)
+extern "C" int gkr_transcript_append_message(gkr_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t len) {
+    if (!t || (!label && label_len) || (!msg && len)) return GKR_ERR_ARG;
+    t->t.append_labeled(label, label_len, msg, len);
+    return GKR_OK;
+}
+extern "C" int gkr_transcript_append_scalars_old(gkr_transcript* t, const uint64_t* limbs, uint32_t n) {
+    if (!t || (!limbs && n)) return GKR_ERR_ARG;
+    std::vector<gkr::FrH> v = load_frs(limbs, n);
+    for (auto& x : v) {  // append_scalars: one message per scalar, label b"" (transcript.rs:78-89)
+        if (!frh_canonical(x)) return GKR_ERR_ARG;
+        uint8_t buf[32];
+        gkr::frh::to_bytes_le(x, buf);
+        t->t.append_labeled(nullptr, 0, buf, 32);
+    }
+    return GKR_OK;
+}
+extern "C" int gkr_transcript_challenge_scalar_old(gkr_transcript* t, const uint8_t* label, size_t label_len, uint64_t out[4]) {
+    if (!t || !out || (!label && label_len)) return GKR_ERR_ARG;
+    uint8_t buf[64];  // challenge_scalar: 64 bytes -> from_le_bytes_mod_order (transcript.rs:96-101)
+    t->t.challenge_labeled(label, label_len, buf, 64);
+    frh_to_limbs(gkr::frh::from_le_bytes_mod_order(buf, 64), out);
+    return GKR_OK;
+}
+
 extern "C" size_t gkr_transcript_proof_len(const gkr_transcript* t) { return t ? t->t.proof.size() : 0; }
 
 extern "C" int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out) {
@@ -118,12 +144,12 @@ extern "C" int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out) {
 
 // GenericSumcheckProtocol::prove  (src/cleanup/protocols/sumcheck.rs:101-123)
 // GKR_TRACE: where the host time of the round loop goes (printed by gkr_sumcheck_prove_stats_dump)
-static uint64_t g_sc_ns[4] = {0, 0, 0, 0};  // unipoly (launch-to-result wait included), interpolation + transcript, bind, final_evals
-static uint64_t g_sc_rounds = 0;
+static std::atomic<uint64_t> g_sc_ns[4];  // unipoly (launch-to-result wait included), interpolation + transcript, bind, final_evals
+static std::atomic<uint64_t> g_sc_rounds{0};
 extern "C" void gkr_sumcheck_prove_stats_dump(void) {
     if (!g_sc_rounds) return;
     fprintf(stderr, "  [gkr_sumcheck_prove] %llu rounds: unipoly %.2f ms, interpolate+transcript %.2f ms, bind %.2f ms, final_evals %.2f ms\n",
-            (unsigned long long)g_sc_rounds, g_sc_ns[0] / 1e6, g_sc_ns[1] / 1e6, g_sc_ns[2] / 1e6, g_sc_ns[3] / 1e6);
+            (unsigned long long)g_sc_rounds.load(), g_sc_ns[0].load() / 1e6, g_sc_ns[1].load() / 1e6, g_sc_ns[2].load() / 1e6, g_sc_ns[3].load() / 1e6);
     g_sc_rounds = 0;
     for (int i = 0; i < 4; i++) g_sc_ns[i] = 0;
 }

@@ -129,14 +129,11 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
         uint32_t row = 0;
         uint64_t idx = q;
         if (active) {
-#ifdef GKR_COMPACT_FIELD
-            if (A.pair_off && A.one_pair_rows) {
+            if (A.pair_off && A.one_pair_rows) {  // every row holds one pair: row == pair index, no search (both flavours)
                 row = (uint32_t)q;
                 idx = 0;
                 w = fr_mul(A.eq[0], A.rowcoef[row]);
-            } else
-#endif
-            if (A.pair_off) {
+            } else if (A.pair_off) {
                 uint32_t lo = 0, hi = A.nrows;  // largest r with pair_off[r] <= q (empty rows repeat an offset)
                 while (hi - lo > 1) {
                     uint32_t mid = (lo + hi) >> 1;

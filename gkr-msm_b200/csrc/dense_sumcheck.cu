@@ -10,6 +10,7 @@
 // block straight into pinned host memory; the challenge travels as a kernel argument, so a round costs
 // one launch and one stream synchronisation and nothing table-sized ever crosses PCIe.
 #include <algorithm>
+#include <atomic>
 #include "common.cuh"
 #include "gates.cuh"
 #include "dense_kernel.cuh"
@@ -62,11 +63,11 @@ static int dispatch_dense_so(gkr_ctx* ctx, int so_kind, int gate, uint32_t param
 
 template <class SO, int MODE, bool FAST = false>
 static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t* n_blocks_out) {
-    static int blocks_per_sm = 0;
+    static std::atomic<int> blocks_per_sm{0};  // same value whichever thread computes it first
     if (blocks_per_sm == 0) {
         int b = 0;
         GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_kernel<SO, MODE, FAST>, GKR_REDUCE_THREADS, 0));
-        blocks_per_sm = std::max(b, 1);
+        blocks_per_sm.store(std::max(b, 1));
     }
     if constexpr (MODE != 2) {
         if (args.n_items <= ctx->dense_small_max) {  // small round: the block-cooperative kernel
@@ -85,13 +86,13 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
         // fused fold+eval rounds over whole 32-item tiles: tables staged HBM -> shared memory by cp.async one tile ahead
         // (dense_round_staged_kernel; measured 0.672 -> 0.649 ms on the 2^24 x 3 Prod3 round).  dense_flavor 0 disables it.
         if (ctx->dense_flavor != 0 && ctx->dense_flavor != 1 && args.n_items % 32 == 0 && args.n_items >= ctx->dense_staged_min) {
-            static int staged_blocks_per_sm = 0;
+            static std::atomic<int> staged_blocks_per_sm{0};
             constexpr size_t smem = (size_t)GKR_STAGED_WARPS * SO::P * 32 * 4 * 32;
             if (staged_blocks_per_sm == 0) {
                 GKR_CUDA_OK(ctx, cudaFuncSetAttribute(dense_round_staged_kernel<SO, MODE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int b = 0;
                 GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_staged_kernel<SO, MODE, FAST>, GKR_REDUCE_THREADS, smem));
-                staged_blocks_per_sm = std::max(b, 1);
+                staged_blocks_per_sm.store(std::max(b, 1));
             }
             // two waves of blocks: the grid-stride tiles of a block that starts late even out the tail
             uint64_t want = (args.n_items / 32 + GKR_STAGED_WARPS - 1) / GKR_STAGED_WARPS;
@@ -109,12 +110,12 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
     }
     if constexpr (MODE != 2 && SO::DEG <= 4) {
         if (ctx->dense_flavor == 1) {  // node-split kernel: one warp per evaluation node
-            static int split_blocks_per_sm = 0;
+            static std::atomic<int> split_blocks_per_sm{0};
             constexpr int threads = 32 * SO::DEG;
             if (split_blocks_per_sm == 0) {
                 int b = 0;
                 GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, dense_round_split_kernel<SO, MODE, FAST>, threads, 0));
-                split_blocks_per_sm = std::max(b, 1);
+                split_blocks_per_sm.store(std::max(b, 1));
             }
             uint64_t want = (args.n_items + 31) / 32;
             uint64_t cap = std::min<uint64_t>((uint64_t)ctx->num_sms * split_blocks_per_sm, GKR_MAX_BLOCKS);

@@ -162,50 +162,47 @@ static inline FrH from_le_bytes_mod_order(const uint8_t* b, size_t n) {
     return acc;
 }
 
-// 1 / prod_{j != i} (i - j) for the nodes 0..n-1, computed once per n (n <= 8)
-static inline const FrH* lagrange_inv_denominators(int n) {
-    static FrH cache[9][8];
-    static bool ready[9] = {false, false, false, false, false, false, false, false, false};
-    if (!ready[n]) {
-        for (int i = 0; i < n; i++) {
-            FrH den = ONE;
-            for (int j = 0; j < n; j++) {
-                if (j == i) continue;
-                FrH d = (i > j) ? from_u64((uint64_t)(i - j)) : neg(from_u64((uint64_t)(j - i)));
-                den = mul(den, d);
-            }
-            cache[n][i] = inverse(den);
-        }
-        ready[n] = true;
-    }
-    return cache[n];
-}
-
-// Lagrange basis polynomials of the nodes 0..n-1 in coefficient form, computed once per n (n <= 8):
-// basis[i][k] = coefficient of X^k in prod_{j != i} (X - j) / prod_{j != i} (i - j)
-static inline const FrH (*lagrange_basis_coeffs(int n))[8] {
-    static FrH cache[9][8][8];
-    static bool ready[9] = {false, false, false, false, false, false, false, false, false};
-    if (!ready[n]) {
-        const FrH* inv_den = lagrange_inv_denominators(n);
-        for (int i = 0; i < n; i++) {
-            std::vector<FrH> num(1, ONE);
-            for (int j = 0; j < n; j++) {
-                if (j == i) continue;
-                std::vector<FrH> nw(num.size() + 1, ZERO);
-                FrH fj = from_u64((uint64_t)j);
-                for (size_t k = 0; k < num.size(); k++) {
-                    nw[k] = sub(nw[k], mul(fj, num[k]));
-                    nw[k + 1] = add(nw[k + 1], num[k]);
+// Lagrange data of the nodes 0..n-1 for every n <= 8, built ONCE by a function-local static (thread-safe initialisation since
+// C++11: two threads proving concurrently on first use cannot observe a half-written table):
+//   inv_den[n][i]  = 1 / prod_{j != i} (i - j)
+//   basis[n][i][k] = coefficient of X^k in prod_{j != i} (X - j) / prod_{j != i} (i - j)
+struct LagrangeTables {
+    FrH inv_den[9][8];
+    FrH basis[9][8][8];
+    LagrangeTables() {
+        for (int n = 1; n <= 8; n++) {
+            for (int i = 0; i < n; i++) {
+                FrH den = ONE;
+                for (int j = 0; j < n; j++) {
+                    if (j == i) continue;
+                    FrH d = (i > j) ? from_u64((uint64_t)(i - j)) : neg(from_u64((uint64_t)(j - i)));
+                    den = mul(den, d);
                 }
-                num.swap(nw);
+                inv_den[n][i] = inverse(den);
             }
-            for (int k = 0; k < n; k++) cache[n][i][k] = mul(num[k], inv_den[i]);
+            for (int i = 0; i < n; i++) {
+                std::vector<FrH> num(1, ONE);
+                for (int j = 0; j < n; j++) {
+                    if (j == i) continue;
+                    std::vector<FrH> nw(num.size() + 1, ZERO);
+                    FrH fj = from_u64((uint64_t)j);
+                    for (size_t k = 0; k < num.size(); k++) {
+                        nw[k] = sub(nw[k], mul(fj, num[k]));
+                        nw[k + 1] = add(nw[k + 1], num[k]);
+                    }
+                    num.swap(nw);
+                }
+                for (int k = 0; k < n; k++) basis[n][i][k] = mul(num[k], inv_den[n][i]);
+            }
         }
-        ready[n] = true;
     }
-    return cache[n];
+};
+static inline const LagrangeTables& lagrange_tables() {
+    static const LagrangeTables t;
+    return t;
 }
+static inline const FrH* lagrange_inv_denominators(int n) { return lagrange_tables().inv_den[n]; }
+static inline const FrH (*lagrange_basis_coeffs(int n))[8] { return lagrange_tables().basis[n]; }
 
 // coefficients (low -> high) of the unique polynomial of degree < n through (i, evals[i]): UniPoly::from_evals(..).as_vec()
 static inline void interpolate_coeffs_into(const FrH* evals, int n, FrH* coeffs) {

@@ -1063,28 +1063,67 @@ __device__ __forceinline__ uint32_t rows_bucket(const uint32_t* idx, uint64_t k,
     *pidx = x + ((y & ((1u << clm) - 1)) << xl);
     return ((y >> clm) << group_log) | idx[k];
 }
-__global__ void g1_rows_hist_kernel(const uint32_t* idx, uint64_t n, uint32_t xl, uint32_t clm, uint32_t group_log, uint32_t* counts, int* bad) {
+// x_lo / x_hi: only the points x_lo <= x < x_hi of every digit row (the x-range one GPU of a team owns, msm_team.cu)
+__device__ __forceinline__ bool rows_in_range(uint64_t k, uint32_t xl, uint32_t x_lo, uint32_t x_hi) {
+    const uint32_t x = (uint32_t)(k & (((uint64_t)1 << xl) - 1));
+    return x >= x_lo && x < x_hi;
+}
+__global__ void g1_rows_hist_kernel(const uint32_t* idx, uint64_t n, uint32_t xl, uint32_t clm, uint32_t group_log, uint32_t* counts, int* bad,
+                                    uint32_t x_lo, uint32_t x_hi) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        if (!rows_in_range(k, xl, x_lo, x_hi)) continue;
         if (idx[k] >> group_log) { *bad = 1; continue; }
         uint32_t p;
         atomicAdd(&counts[rows_bucket(idx, k, xl, clm, group_log, &p)], 1u);
     }
 }
 __global__ void g1_rows_scatter_kernel(const uint32_t* idx, uint64_t n, uint32_t xl, uint32_t clm, uint32_t group_log, const uint32_t* offsets,
-                                       uint32_t* cursor, uint32_t* sorted) {
+                                       uint32_t* cursor, uint32_t* sorted, uint32_t x_lo, uint32_t x_hi) {
     for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        if (!rows_in_range(k, xl, x_lo, x_hi)) continue;
         if (idx[k] >> group_log) continue;
         uint32_t p;
         const uint32_t b = rows_bucket(idx, k, xl, clm, group_log, &p);
         sorted[offsets[b] + atomicAdd(&cursor[b], 1u)] = p;
     }
 }
+int gkr_team_bucket_sums(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* d_idx, uint64_t n, uint32_t x_logsize, uint32_t clm, uint32_t group_log,
+                         gkr_srs** out, bool* handled);  // msm_team.cu
+__global__ void g1x_accumulate_kernel(G1X* acc, const G1X* part, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        G1X a = acc[i];
+        g1x_add(a, part[i]);
+        acc[i] = a;
+    }
+}
+// acc[i] += part[i] over n XYZZ bucket sums resident on the device (team leader: partial sums of the other GPUs)
+int gkr_g1x_accumulate(gkr_ctx* ctx, void* d_acc, const void* d_part, uint64_t n) {
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->num_sms * 8));
+    g1x_accumulate_kernel<<<grid, 128, 0, ctx->stream>>>((G1X*)d_acc, (const G1X*)d_part, n);
+    ctx->launches++;
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    return GKR_OK;
+}
+size_t gkr_g1x_bytes() { return sizeof(G1X); }
+void* gkr_srs_device_ptr(gkr_srs* s) { return s->d; }
+
+int gkr_g1_bucket_sums_rows_range(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* d_idx, uint64_t n, uint32_t x_logsize, uint32_t clm,
+                                  uint32_t group_log, uint32_t x_lo, uint32_t x_hi, bool allow_team, gkr_srs** out);
+
 extern "C" int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const gkr_u32buf* idx, uint32_t x_logsize, uint32_t clm, uint32_t group_log,
                                        gkr_srs** out) {
     if (!ctx) return GKR_ERR_ARG;
     if (!srs || !idx || !out || x_logsize > 30 || clm > 16 || group_log > 30) return ctx->fail(GKR_ERR_ARG, "bad argument");
+    return gkr_g1_bucket_sums_rows_range(ctx, srs, idx->d, idx->n, x_logsize, clm, group_log, 0, 1u << x_logsize, true, out);
+}
+
+// The bucket accumulation of PushForwardState::new (pushforward.rs:398-429) restricted to the points x_lo <= x < x_hi of every
+// digit row.  allow_team: when a team is attached (msm_team.cu) the x-range is split over its GPUs and the partial bucket
+// sums are added here -- group addition commutes, so the sums are the same points.
+int gkr_g1_bucket_sums_rows_range(gkr_ctx* ctx, const gkr_srs* srs, const uint32_t* d_idx, uint64_t n, uint32_t x_logsize, uint32_t clm,
+                                  uint32_t group_log, uint32_t x_lo, uint32_t x_hi, bool allow_team, gkr_srs** out) {
     if (srs->kind != 0) return ctx->fail(GKR_ERR_ARG, "bucket sums need affine bases");
-    const uint64_t n = idx->n, x_size = (uint64_t)1 << x_logsize;
+    const uint64_t x_size = (uint64_t)1 << x_logsize;
     if (n == 0 || n % x_size) return ctx->fail(GKR_ERR_ARG, "index matrix is not a whole number of rows");
     if (n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many incidences");
     const uint64_t rows = n / x_size;
@@ -1093,6 +1132,16 @@ extern "C" int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const g
     const uint64_t n_buckets = n_groups << group_log;
     if (n_buckets >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "too many buckets");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    if (allow_team && ctx->team && x_lo == 0 && x_hi == x_size) {  // split the x-range over the GPUs of the team
+        bool handled = false;
+        gkr_srs* r = nullptr;
+        int trc = gkr_team_bucket_sums(ctx, srs, d_idx, n, x_logsize, clm, group_log, &r, &handled);
+        if (handled) {
+            if (trc) return trc;
+            *out = r;
+            return GKR_OK;
+        }
+    }
     cudaStream_t st = ctx->stream;
     int c = 0;
     while (((uint64_t)1 << c) < n_buckets) c++;
@@ -1111,9 +1160,9 @@ extern "C" int gkr_g1_bucket_sums_rows(gkr_ctx* ctx, const gkr_srs* srs, const g
     uint32_t* work = counts + 3 * nbk + 1;
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (nbk * 3 + 1), st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
-    g1_rows_hist_kernel<<<g1, 256, 0, st>>>(idx->d, n, x_logsize, clm, group_log, counts, d_bad);
+    g1_rows_hist_kernel<<<g1, 256, 0, st>>>(d_idx, n, x_logsize, clm, group_log, counts, d_bad, x_lo, x_hi);
     msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, c);
-    g1_rows_scatter_kernel<<<g1, 256, 0, st>>>(idx->d, n, x_logsize, clm, group_log, offsets, cursor, sorted);
+    g1_rows_scatter_kernel<<<g1, 256, 0, st>>>(d_idx, n, x_logsize, clm, group_log, offsets, cursor, sorted, x_lo, x_hi);
     ctx->launches += 3;
     int rc = msm_accumulate(ctx, srs->d, 0, sorted, counts, offsets, (uint32_t)n, c, nbk, n, work, (G1X*)res->d);
     int bad = 0;

@@ -45,6 +45,13 @@ extern "C" int gkr_exchange_open(const char* name, int rank, int world, int crea
         close(fd);
         return GKR_ERR_ARG;
     }
+    if (!create) {  // opened before the creator's ftruncate: touching the mapping would SIGBUS -- report "not ready" instead
+        struct stat st;
+        if (fstat(fd, &st) != 0 || (size_t)st.st_size < sizeof(ExShared)) {
+            close(fd);
+            return GKR_ERR_ARG;
+        }
+    }
     void* p = mmap(nullptr, sizeof(ExShared), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
     if (p == MAP_FAILED) return GKR_ERR_ARG;

@@ -252,12 +252,13 @@ extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
 extern "C" const char* gkr_last_error(const gkr_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 extern "C" int gkr_ctx_sync(gkr_ctx* ctx) {
+    if (!ctx) return GKR_ERR_ARG;
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     return GKR_OK;
 }
 
-extern "C" uint64_t gkr_ctx_launch_count(const gkr_ctx* ctx) { return ctx->launches; }
-extern "C" void* gkr_ctx_stream(gkr_ctx* ctx) { return (void*)ctx->stream; }
+extern "C" uint64_t gkr_ctx_launch_count(const gkr_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" void* gkr_ctx_stream(gkr_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 // ---- tables ----------------------------------------------------------------------------------------
 extern "C" int gkr_table_alloc(gkr_ctx* ctx, uint64_t n, gkr_table** out) {
@@ -276,6 +277,7 @@ extern "C" int gkr_table_alloc(gkr_ctx* ctx, uint64_t n, gkr_table** out) {
 }
 
 extern "C" int gkr_table_upload(gkr_ctx* ctx, const uint64_t* limbs, uint64_t n, gkr_table** out) {
+    if (!ctx) return GKR_ERR_ARG;
     if (!limbs && n) return ctx->fail(GKR_ERR_ARG, "null host buffer");
     int rc = gkr_table_alloc(ctx, n, out);
     if (rc) return rc;
@@ -285,6 +287,7 @@ extern "C" int gkr_table_upload(gkr_ctx* ctx, const uint64_t* limbs, uint64_t n,
 }
 
 extern "C" int gkr_table_download(gkr_ctx* ctx, const gkr_table* t, uint64_t* limbs_out) {
+    if (!ctx) return GKR_ERR_ARG;
     if (!t || !limbs_out) return ctx->fail(GKR_ERR_ARG, "null argument");
     if (t->n) GKR_CUDA_OK(ctx, cudaMemcpyAsync(limbs_out, t->d, sizeof(Fr) * t->n, cudaMemcpyDeviceToHost, ctx->stream));
     GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -457,10 +460,19 @@ extern "C" int gkr_eq_table(gkr_ctx* ctx, const uint64_t* point, uint32_t n, con
     int rc = gkr_table_alloc(ctx, (uint64_t)1 << n, out);
     if (rc) return rc;
     Fr* d_point = nullptr;
-    GKR_CUDA_OK(ctx, gkr_malloc_async(&d_point, sizeof(Fr) * std::max<uint32_t>(n, 1), ctx->stream));
+    if (gkr_malloc_async(&d_point, sizeof(Fr) * std::max<uint32_t>(n, 1), ctx->stream) != cudaSuccess) {
+        gkr_table_free(*out);
+        *out = nullptr;
+        return ctx->fail(GKR_ERR_CUDA, "eq table: out of device memory");
+    }
     if (n) {
         int rcs = gkr_stage_upload(ctx, d_point, point, sizeof(Fr) * n);
-        if (rcs) return rcs;
+        if (rcs) {  // nothing leaks on the staging failure path
+            gkr_free_async(d_point, ctx->stream);
+            gkr_table_free(*out);
+            *out = nullptr;
+            return rcs;
+        }
     }
     rc = eq_build(ctx, d_point, n, fr_from_host(m), (*out)->d);
     gkr_free_async(d_point, ctx->stream);

@@ -167,6 +167,10 @@ class ProofTranscript2 {
         proof.insert(proof.end(), msg, msg + n);
     }
     void raw_challenge(uint8_t* out, size_t n) { merlin.challenge_bytes(nullptr, 0, out, n); }
+    // old API (src/transcript.rs:78-101): labelled merlin messages that are NOT part of a proof byte string, and labelled
+    // 64-byte challenges
+    void append_labeled(const uint8_t* label, size_t ln, const uint8_t* msg, size_t n) { merlin.append_message(label, ln, msg, n); }
+    void challenge_labeled(const uint8_t* label, size_t ln, uint8_t* out, size_t n) { merlin.challenge_bytes(label, ln, out, n); }
     void write_scalars(const FrH* v, size_t n) {  // ark-serialize compressed Fr: 32 B LE canonical value
         uint8_t small[32 * 8] = {0};
         std::vector<uint8_t> big;

@@ -310,6 +310,12 @@ int gkr_transcript_write_raw(gkr_transcript* t, const uint8_t* msg, size_t len);
 int gkr_transcript_challenge(gkr_transcript* t, uint32_t bitsize, uint64_t out[4]);
 int gkr_transcript_raw_challenge(gkr_transcript* t, uint8_t* out, size_t len);
 size_t gkr_transcript_proof_len(const gkr_transcript* t);
+/* old API transcript: `impl TranscriptReceiver / TranscriptSender for merlin::Transcript`  src/transcript.rs:78-101
+ * (benches/bintree.rs, gkr_msm_simple): labelled merlin messages outside any proof byte string; append_scalars = one message
+ * per scalar with label b""; challenge_scalar(label) = from_le_bytes_mod_order of 64 challenge bytes. */
+int gkr_transcript_append_message(gkr_transcript* t, const uint8_t* label, size_t label_len, const uint8_t* msg, size_t len);
+int gkr_transcript_append_scalars_old(gkr_transcript* t, const uint64_t* limbs, uint32_t n);
+int gkr_transcript_challenge_scalar_old(gkr_transcript* t, const uint8_t* label, size_t label_len, uint64_t out[4]);
 int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out);
 
 /* GenericSumcheckProtocol::prove   src/cleanup/protocols/sumcheck.rs:101-123

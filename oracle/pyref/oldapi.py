@@ -107,3 +107,176 @@ class FragmentedLincombFull:
 
     def final_evals(self):
         return [p[0] for p in self.polys]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Old-API protocol flow on Shape::full tables (BASELINE config[4]: benches/bintree.rs, gkr_msm_simple):
+#   merlin transcript with labels                      src/transcript.rs:78-101
+#   to_multieval, make_folded_claim, SumcheckPolyMap::{witness}, SumcheckPolyMapProver::{start, round},
+#   SumcheckPolyMapVerifier::{start, round}            src/protocol/sumcheck.rs:160-257, 317-321, 524-672
+#   Split::witness, SplitProver::round                 src/protocol/split.rs:37-85
+#   Layer, BintreeParams::unroll, BintreeProtocol::witness, BintreeProver::round, BintreeVerifier::round
+#                                                      src/protocol/bintree.rs:14-397
+#   the layer list and the driver loop                 benches/bintree.rs:20-118, 160-190
+from .field import fr_serialize, from_le_bytes_mod_order  # noqa: E402
+from .sumcheck import compress_coefficients, decompress_coefficients, eq_eval, evaluate_univar  # noqa: E402
+from .transcript import MerlinTranscript  # noqa: E402
+
+
+class OldTranscript:
+    """`impl TranscriptReceiver / TranscriptSender for merlin::Transcript` (src/transcript.rs:78-101)"""
+
+    def __init__(self, label: bytes):
+        self.m = MerlinTranscript(label)
+
+    def append_scalars(self, label, scalars):  # one message per scalar, label b"" whatever the caller passes
+        for s in scalars:
+            self.m.append_message(b"", fr_serialize(s))
+
+    def challenge_scalar(self, label: bytes) -> int:  # 64 bytes -> from_le_bytes_mod_order
+        return from_le_bytes_mod_order(self.m.challenge_bytes(label, 64))
+
+
+def split_full(p):  # FragmentedPoly::split on one Data fragment: even entries left, odd entries right (fragmented.rs:676-741)
+    return p[0::2], p[1::2]
+
+
+def evaluate_full(p, point):  # FragmentedPoly::evaluate (fragmented.rs:748-761): binds the LAST coordinate first
+    cur = list(p)
+    for f in reversed(point):
+        l, r = split_full(cur)
+        cur = [(x + f * (y - x)) % P for x, y in zip(l, r)]
+    return cur[0]
+
+
+class MapLayer:  # Layer::Mapping(PolynomialMapping)
+    def __init__(self, gate):
+        self.gate, self.num_i, self.num_o, self.degree = gate, gate.n_ins, gate.n_outs, gate.deg
+        self.is_split = False
+
+
+class SplitLayer:  # Layer::Split(n)
+    def __init__(self, n):
+        self.num_i, self.num_o, self.is_split = n, 2 * n, True
+
+
+def bintree_layers(log_num_points):
+    """benches/bintree.rs:86-108: split(2), affine L1/L2/L3, then (split(3), projective L1/L2/L3) x (log_num_points - 2)"""
+    from . import gates as G
+    layers = [SplitLayer(2), MapLayer(G.AffL1()), MapLayer(G.AffL2()), MapLayer(G.AffL3())]
+    for _ in range(log_num_points - 2):
+        layers += [SplitLayer(3), MapLayer(G.PrjL1()), MapLayer(G.PrjL2()), MapLayer(G.PrjL3())]
+    return layers
+
+
+def unroll(layers, num_vars):  # BintreeParams::unroll (bintree.rs:78-122)
+    out, last_o = [], None
+    for layer in layers:
+        if last_o is not None:
+            assert last_o == layer.num_i, "Amount of inputs differs from amount of outputs"
+        out.append((layer, num_vars))
+        if layer.is_split:
+            assert num_vars > 0, "Can not split 0-variable vector."
+            num_vars -= 1
+        last_o = layer.num_o
+    assert not out[-1][0].is_split, "Technical condition: split can not be last operation."
+    return out
+
+
+def bintree_witness(args, layers, num_vars):
+    """BintreeProtocol::witness (bintree.rs:168-185): trace = the input of every layer"""
+    assert len(args[0]) == 1 << num_vars
+    trace, output = [], [list(a) for a in args]
+    for layer, _nv in unroll(layers, num_vars):
+        trace.append(output)
+        if layer.is_split:  # Split::witness (split.rs:37-48): all left halves, then all right halves
+            ls, rs = zip(*[split_full(p) for p in output])
+            output = [list(x) for x in ls] + [list(x) for x in rs]
+        else:  # SumcheckPolyMap::witness = map_over_poly
+            n = len(output[0])
+            outs = [[0] * n for _ in range(layer.num_o)]
+            for i in range(n):
+                o = layer.gate.exec([p[i] for p in output])
+                for k in range(layer.num_o):
+                    outs[k][i] = o[k] % P
+            output = outs
+    return trace, output
+
+
+def make_folded_claim(evs, gamma_pows):  # sumcheck.rs:658-672 (one claimed point)
+    return sum(e * g for e, g in zip(evs, gamma_pows)) % P
+
+
+def bintree_prove(transcript: OldTranscript, point, evs, trace, layers, num_vars, label=b"challenge_nextround"):
+    """BintreeProver::{start, round} driven like benches/bintree.rs:177-183.  Returns (final EvalClaim (point, evs),
+    proof = per layer None (split) | (compressed round polynomials, final evaluations))."""
+    trace = list(trace)
+    params = unroll(layers, num_vars)
+    claim_point, claim_evs = list(point), list(evs)
+    proofs = []
+    while params:
+        layer, nv = params.pop()
+        polys = trace.pop()
+        if layer.is_split:  # SplitProver::round (split.rs:64-84)
+            r = transcript.challenge_scalar(label)
+            h = len(claim_evs) // 2
+            claim_evs = [(x + r * (y - x)) % P for x, y in zip(claim_evs[:h], claim_evs[h:])]
+            claim_point = claim_point + [r]  # fix_var_top
+            proofs.append(None)
+            continue
+        # SumcheckPolyMapProver (sumcheck.rs:178-257); to_multieval: every output claimed at the one point
+        assert len(polys) == layer.num_i and len(claim_point) == nv
+        gamma = transcript.challenge_scalar(label)
+        gamma_pows = make_gamma_pows_legacy(len(claim_evs), gamma)
+        claim_struct = [[(o, v) for o, v in enumerate(claim_evs)]]
+        so = FragmentedLincombFull(polys, [claim_point], make_folded_f(claim_struct, gamma_pows, layer.gate.exec, layer.num_i), layer.degree)
+        rs, round_polys = [], []
+        while True:
+            if len(rs) == nv:
+                fe = so.final_evals()[:layer.num_i]
+                transcript.append_scalars(b"sumcheck_final_evals", fe)
+                break
+            poly = so.unipoly()
+            transcript.append_scalars(b"poly", poly)
+            round_polys.append(compress_coefficients(poly))
+            r_j = transcript.challenge_scalar(label)
+            rs.insert(0, r_j)  # fix_var_bot
+            so.bind(r_j)
+        proofs.append((round_polys, fe))
+        claim_point, claim_evs = rs, fe
+    return (claim_point, claim_evs), proofs
+
+
+def bintree_verify(transcript: OldTranscript, point, evs, proofs, layers, num_vars, label=b"challenge_nextround"):
+    """BintreeVerifier::round over SumcheckPolyMapVerifier / SplitVerifier (bintree.rs:300-397, sumcheck.rs:524-652)"""
+    params = unroll(layers, num_vars)
+    proofs = list(proofs)
+    claim_point, claim_evs = list(point), list(evs)
+    while params:
+        layer, nv = params.pop()
+        proof = proofs.pop(0)
+        if layer.is_split:
+            assert proof is None
+            r = transcript.challenge_scalar(label)
+            h = len(claim_evs) // 2
+            claim_evs = [(x + r * (y - x)) % P for x, y in zip(claim_evs[:h], claim_evs[h:])]
+            claim_point = claim_point + [r]
+            continue
+        round_polys, fe = proof
+        assert len(round_polys) == nv and len(fe) == layer.num_i and len(claim_point) == nv
+        gamma = transcript.challenge_scalar(label)
+        gamma_pows = make_gamma_pows_legacy(len(claim_evs), gamma)
+        current = make_folded_claim(claim_evs, gamma_pows)
+        folded = make_folded_f([[(o, v) for o, v in enumerate(claim_evs)]], gamma_pows, layer.gate.exec, layer.num_i)
+        rs = []
+        for k in range(nv):
+            poly = decompress_coefficients(round_polys[k], current)
+            assert len(poly) == layer.degree + 2, "Verifier failure: polynomial degree incorrect"
+            transcript.append_scalars(b"poly", poly)
+            r_j = transcript.challenge_scalar(label)
+            rs.insert(0, r_j)
+            current = evaluate_univar(poly, r_j)
+        transcript.append_scalars(b"sumcheck_final_evals", fe)
+        assert folded(list(fe) + [eq_eval(claim_point, rs)]) == current, "Verifier failure: final check incorrect"
+        claim_point, claim_evs = rs, list(fe)
+    return claim_point, claim_evs

@@ -69,3 +69,77 @@ def test_device_object_serves_old_api(ctx, cls):
         so.bind(to_limb1(t))
         old.bind(t)
     assert from_limbs(so.final_evals())[:-1] == old.final_evals()
+
+
+# ---- the round-by-round old-API bintree prover (benches/bintree.rs; src/protocol/bintree.rs:467-583 restated) ------------
+def _bintree_instance(log_n, seed):
+    rng = random.Random(seed)
+    n = 1 << log_n
+    tables = [[rng.randrange(P) for _ in range(n)] for _ in range(2)]  # (x, y) columns; the gates are polynomial maps of any values
+    layers = O.bintree_layers(log_n)
+    trace, output = O.bintree_witness(tables, layers, log_n)
+    point = [rng.randrange(P)]
+    evs = [O.evaluate_full(p, point) for p in output]
+    return tables, layers, trace, output, point, evs
+
+
+@pytest.mark.parametrize("log_n", [3, 5])
+def test_old_bintree_prover_vs_verifier(log_n):
+    """prover_vs_verifier (bintree.rs:531-583): the final claims are the INPUT tables evaluated at the final point, the
+    verifier accepts and ends in the same claim and the same transcript state; a corrupted round polynomial is rejected"""
+    tables, layers, trace, output, point, evs = _bintree_instance(log_n, 500 + log_n)
+    assert len(output) == 3 and len(output[0]) == 2  # one variable left: two points that were never added together
+    tp = O.OldTranscript(b"test")
+    (fpoint, fevs), proofs = O.bintree_prove(tp, point, evs, trace, layers, log_n)
+    assert fevs == [O.evaluate_full(t, fpoint) for t in tables]
+    tv = O.OldTranscript(b"test")
+    vpoint, vevs = O.bintree_verify(tv, point, evs, proofs, layers, log_n)
+    assert (vpoint, vevs) == (fpoint, fevs)
+    assert tv.challenge_scalar(b"end") == tp.challenge_scalar(b"end")
+    bad = [p if p is None else ([list(q) for q in p[0]], list(p[1])) for p in proofs]
+    k = next(i for i, p in enumerate(bad) if p is not None and p[0])
+    bad[k][0][0][0] = (bad[k][0][0][0] + 1) % P
+    with pytest.raises(AssertionError):
+        O.bintree_verify(O.OldTranscript(b"test"), point, evs, bad, layers, log_n)
+
+
+def test_old_bintree_witness_is_the_point_sum():
+    """witness_generation (bintree.rs:467-529) in spirit: the layers really add curve points -- with on-curve inputs the
+    output columns are the projective sums of the two halves of the point list"""
+    from oracle.pyref import curves as CV
+    rng = random.Random(9)
+    log_n = 3
+    pts = [CV.te_random_point(rng) for _ in range(1 << log_n)]
+    layers = O.bintree_layers(log_n)
+    _, out = O.bintree_witness([[p[0] for p in pts], [p[1] for p in pts]], layers, log_n)
+    for k in range(2):  # even/odd splits: output k sums the points whose index has top... collect by construction below
+        got = CV.te_to_affine((out[0][k], out[1][k], out[2][k]))
+        # after log_n - 1 even/odd splits entry k of the output holds the points with index = k mod 2 ... in bit-reversed order:
+        # split i pairs (2j, 2j+1) of the CURRENT table, so the first addition joins neighbours; entry k sums indices [4k, 4k+4)
+        acc = (0, 1, 1)
+        for p in pts[4 * k:4 * k + 4]:
+            acc = CV.te_add_proj(acc, (p[0], p[1], 1))
+        assert got == CV.te_to_affine(acc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log_n", [4, 9])
+def test_device_old_bintree_equals_oracle(ctx, log_n):
+    """BASELINE config[4] flow on the device: witness tables, every round polynomial, the final claim and the transcript
+    state equal the restated old API"""
+    import gkr_msm_b200 as g
+    from gkr_msm_b200 import oldapi as DO
+
+    tables, layers, trace, output, point, evs = _bintree_instance(log_n, 700 + log_n)
+    dtabs = [ctx.upload(to_limbs(t)) for t in tables]
+    dlayers = DO.bintree_layers(log_n)
+    dtrace, dout = DO.bintree_witness(ctx, dtabs, dlayers, log_n)
+    assert [from_limbs(t.download()) for t in dout] == output
+    assert [[from_limbs(t.download()) for t in lay] for lay in dtrace[:5]] == trace[:5]
+    tp = O.OldTranscript(b"test")
+    (fpoint, fevs), proofs = O.bintree_prove(tp, point, evs, trace, layers, log_n)
+    tr = g.Transcript(b"test")
+    (dpoint, devs), dproofs = DO.bintree_prove(ctx, tr, to_limbs(point), to_limbs(evs), dtrace, dlayers, log_n)
+    assert (dpoint, devs) == (fpoint, fevs)
+    assert dproofs == proofs
+    assert from_limbs(tr.challenge_scalar_old(b"end").reshape(1, 4))[0] == tp.challenge_scalar(b"end")

@@ -3,7 +3,12 @@
 tree over bucketed points (VecVecBintreeAdd, src/cleanup/protocols/gkrs/bintree_add.rs) on one B200.
 Synthetic: M = y_size * 2^x point-digit incidences spread over y_size * 2^d bucket rows with uniform digits, random
 field elements as coordinates (the arithmetic cost does not depend on the points being on the curve).
-usage: python tools/bench_bintree.py --x 16 --d 8 --ysize 16 [--reps 3]"""
+usage: python tools/bench_bintree.py --x 16 --d 8 --ysize 16 [--reps 3]
+       python tools/bench_bintree.py --old-api --log-points 22 [--reps 3]
+--old-api: the reference's own config[4] program, benches/bintree.rs (old round-by-round API: BintreeProtocol::witness +
+BintreeProver::round with labelled 64-byte merlin challenges, src/protocol/bintree.rs:168-288) on 2^log-points affine points,
+`Shape::full` tables -- gkr-msm_b200/oldapi.py drives the device objects; "witness", "proof" and "witness+proof" are the three
+criterion groups of the bench (benches/bintree.rs:134-216)."""
 import argparse
 import json
 import os
@@ -20,13 +25,58 @@ from gkr_msm_b200 import protocols as DP  # noqa: E402
 from gkr_msm_b200.fieldutil import to_limb1  # noqa: E402
 
 
+def old_api(a):
+    from gkr_msm_b200 import oldapi as DO
+    from gkr_msm_b200.fieldutil import from_limbs, to_limbs
+
+    ctx = g.Context(0)
+    log_n = a.log_points
+    n = 1 << log_n
+    # synthetic coordinates straight from the device generator (the cost of the polynomial gates does not depend on the
+    # values being curve points); the claim is the TRUE evaluation of the outputs, computed from the downloaded 2-entry tables
+    tabs = [ctx.synth(300 + j, n) for j in range(2)]
+    layers = DO.bintree_layers(log_n)
+    rng = np.random.default_rng(5)
+    point = [int.from_bytes(rng.bytes(32), "little") % DO.R_MOD]
+    res = []
+    for rep in range(a.reps + 1):
+        ctx.sync()
+        l0 = ctx.launches
+        t0 = time.perf_counter()
+        trace, out = DO.bintree_witness(ctx, tabs, layers, log_n)
+        ctx.sync()
+        t1 = time.perf_counter()
+        evs = []
+        for t in out:  # FragmentedPoly::evaluate of a 1-variable table: p[0] + r (p[1] - p[0])
+            v = from_limbs(t.download())
+            evs.append((v[0] + point[0] * (v[1] - v[0])) % DO.R_MOD)
+        tr = g.Transcript(b"test")
+        ctx.sync()
+        t2 = time.perf_counter()
+        (fpoint, fevs), proofs = DO.bintree_prove(ctx, tr, to_limbs(point), to_limbs(evs), trace, layers, log_n)
+        ctx.sync()
+        t3 = time.perf_counter()
+        if rep:
+            res.append((t1 - t0, t3 - t2, ctx.launches - l0, sum(len(p[0]) for p in proofs if p is not None)))
+        del trace, out
+    w = min(r[0] for r in res) * 1e3
+    p = min(r[1] for r in res) * 1e3
+    print(json.dumps({"workload": f"old API bintree (benches/bintree.rs), 2^{log_n} points, Shape::full", "leaves": n, "witness_ms": w, "proof_ms": p,
+                      "witness_plus_proof_ms": w + p, "launches": res[-1][2], "sumcheck_rounds": res[-1][3],
+                      "leaves_per_s": n / ((w + p) * 1e-3), "host": "python (gkr-msm_b200/oldapi.py)", "final_point_len": len(fpoint)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--old-api", action="store_true")
+    ap.add_argument("--log-points", type=int, default=22)
     ap.add_argument("--x", type=int, default=16)
     ap.add_argument("--d", type=int, default=8)
     ap.add_argument("--ysize", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
+    if a.old_api:
+        return old_api(a)
     ylog = max(1, (a.ysize - 1).bit_length())
     ctx = g.Context(0)
     rng = np.random.default_rng(1)

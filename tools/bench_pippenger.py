@@ -89,6 +89,23 @@ def run(args, ctx=None, team_name=None):
                                                  "--team-worker", str(rk), "--team-name", name, "--team-tau", "%x" % tau]))
         team.wait_ready(timeout_s=300.0)
 
+    # peak device memory while proving (driver view, includes the stream-ordered pool): sampled every 5 ms
+    mem_peak = [0]
+    stop_sampling = [False]
+    sampler = None
+    if getattr(args, "mem", False):
+        import threading
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(0)
+
+        def sample():
+            while not stop_sampling[0]:
+                mem_peak[0] = max(mem_peak[0], pynvml.nvmlDeviceGetMemoryInfo(handle).used)
+                time.sleep(0.005)
+
+        sampler = threading.Thread(target=sample, daemon=True)
+        sampler.start()
     times, proof_len, launches = [], 0, 0
     for rep in range(args.reps):
         tr = g.Transcript(b"fgstglsp")
@@ -125,8 +142,12 @@ def run(args, ctx=None, team_name=None):
         for w in workers:
             w.wait(timeout=120)
         team.close()
+    if sampler is not None:
+        stop_sampling[0] = True
+        sampler.join()
     best = min(times)
     return ({
+        "peak_device_memory_gib": mem_peak[0] / 2**30 if mem_peak[0] else None,
         "bench": "run_pippenger (witness + commit + prove)", "host": "python" if args.python_host else "c++ (gkr_run_pippenger)", "x_logsize": xl, "d_logsize": dl, "nbits": nbits, "clm": clm,
         "y_size": cfg["y_size"], "incidences": cfg["y_size"] << xl, "prove_ms_best": best * 1e3, "prove_ms_all": [t * 1e3 for t in times],
         "proof_bytes": proof_len, "gpu_launches": launches, "input_generation_s": t_inputs, "srs_setup_s": t_setup,
@@ -146,6 +167,7 @@ def main():
     ap.add_argument("--profile", action="store_true", help="print a per-phase breakdown of the last repetition (python host)")
     ap.add_argument("--python-host", action="store_true", help="time the python orchestration instead of gkr_run_pippenger (C++)")
     ap.add_argument("--precompute-c", type=int, default=-1, help="window of the fixed-base SRS table (0: none; default: 20 from x + clm >= 19)")
+    ap.add_argument("--mem", action="store_true", help="sample the device memory in use while proving (pynvml) and report the peak")
     ap.add_argument("--gpus", type=int, default=1, help="N > 1: spawn N - 1 worker processes (cuda:1..N-1) that share the large commitment MSMs")
     ap.add_argument("--team-worker", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--team-name", default="", help=argparse.SUPPRESS)
