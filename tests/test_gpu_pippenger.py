@@ -88,7 +88,7 @@ def test_pippenger_device_vs_oracle(ctx, d, x, nbits, clm):
     assert np.array_equal(npair[0], dpair[0]) and np.array_equal(npair[1], dpair[1])
 
 
-@pytest.mark.parametrize("d,x,nbits,clm", [(6, 12, 128, 0), (5, 10, 64, 2), (8, 16, 128, 0), (10, 20, 128, 0)])
+@pytest.mark.parametrize("d,x,nbits,clm", [(6, 12, 128, 0), (5, 10, 64, 2), (8, 16, 128, 0), (10, 20, 128, 0), (8, 14, 253, 2)])
 def test_pippenger_full_size_properties(ctx, d, x, nbits, clm):
     """Sizes the python prover cannot reach (BASELINE config[0], x = 16, and the 2^20-point shape of config[2], x = 20): size-independent properties instead of a
     byte comparison -- (1) the ORACLE VERIFIER accepts the device-made proof (every sumcheck round, every claim reduction,

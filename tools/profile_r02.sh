@@ -30,5 +30,6 @@ $NCU --set full --clock-control none -k regex:msm_accumulate_light_kernel -c 1 -
 # 5. raw pages of the full captures as CSV (read on the CPU box)
 for r in r02_dense_eval r02_dense_fused r02_msm_light; do
   [ -f $OUT/$r.ncu-rep ] && $NCU -i $OUT/$r.ncu-rep --page raw --csv > $OUT/$r.raw.csv 2>/dev/null
+  rm -f $OUT/$r.ncu-rep   # 20-80 MB each: gpurun brings back at most 64 MiB of gpurun_out/
 done
 ls -la $OUT | grep r02_
