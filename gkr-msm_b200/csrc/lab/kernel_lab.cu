@@ -262,3 +262,78 @@ extern "C" int gkr_lab_imad_wide_peak(gkr_ctx* ctx, int ilp, int threads, int bl
     *mads_per_s = (double)grid * threads * (double)iters * 4.0 * eff / (best * 1e-3);
     return GKR_OK;
 }
+
+// ---- the same probe in the form the field routines use: mad.lo.cc / madc.hi.cc pairs chained through the carry flag (ptxas
+// fuses each pair into one IMAD.WIDE.U32.X).  ILP independent 8-pair chains per thread.  Answers whether the carry-chained form
+// retires at the rate of the plain IMAD.WIDE.U32 above.
+template <int ILP>
+__global__ void imad_wide_x_peak_kernel(unsigned int* out, int iters, uint32_t b0) {
+    uint32_t acc[ILP][17];
+    const uint32_t a = threadIdx.x * 2654435761u + 12345u, b = b0 + blockIdx.x * 40503u;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int i = 0; i < 17; i++) acc[k][i] = (k + 1) * 0x9e3779b9u + i + threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < ILP; k++) {
+            asm volatile(
+                "mad.lo.cc.u32 %0, %17, %18, %0;\n\t"
+                "madc.hi.cc.u32 %1, %17, %18, %1;\n\t"
+                "madc.lo.cc.u32 %2, %17, %18, %2;\n\t"
+                "madc.hi.cc.u32 %3, %17, %18, %3;\n\t"
+                "madc.lo.cc.u32 %4, %17, %18, %4;\n\t"
+                "madc.hi.cc.u32 %5, %17, %18, %5;\n\t"
+                "madc.lo.cc.u32 %6, %17, %18, %6;\n\t"
+                "madc.hi.cc.u32 %7, %17, %18, %7;\n\t"
+                "madc.lo.cc.u32 %8, %17, %18, %8;\n\t"
+                "madc.hi.cc.u32 %9, %17, %18, %9;\n\t"
+                "madc.lo.cc.u32 %10, %17, %18, %10;\n\t"
+                "madc.hi.cc.u32 %11, %17, %18, %11;\n\t"
+                "madc.lo.cc.u32 %12, %17, %18, %12;\n\t"
+                "madc.hi.cc.u32 %13, %17, %18, %13;\n\t"
+                "madc.lo.cc.u32 %14, %17, %18, %14;\n\t"
+                "madc.hi.cc.u32 %15, %17, %18, %15;\n\t"
+                "addc.u32 %16, %16, 0;\n\t"
+                : "+r"(acc[k][0]), "+r"(acc[k][1]), "+r"(acc[k][2]), "+r"(acc[k][3]), "+r"(acc[k][4]), "+r"(acc[k][5]), "+r"(acc[k][6]), "+r"(acc[k][7]),
+                  "+r"(acc[k][8]), "+r"(acc[k][9]), "+r"(acc[k][10]), "+r"(acc[k][11]), "+r"(acc[k][12]), "+r"(acc[k][13]), "+r"(acc[k][14]),
+                  "+r"(acc[k][15]), "+r"(acc[k][16])
+                : "r"(a), "r"(b));
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < ILP; k++)
+#pragma unroll
+        for (int i = 0; i < 17; i++) s ^= acc[k][i];
+    if (s == 0x12345678u) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int gkr_lab_imad_wide_x_peak(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* mads_per_s) {
+    if (!ctx || !mads_per_s) return GKR_ERR_ARG;
+    unsigned int* out = nullptr;
+    int grid = ctx->num_sms * blocks_per_sm;
+    GKR_CUDA_OK(ctx, cudaMalloc(&out, sizeof(unsigned int) * (size_t)grid * threads));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(a, ctx->stream);
+        if (ilp <= 1) imad_wide_x_peak_kernel<1><<<grid, threads, 0, ctx->stream>>>(out, iters, 77u);
+        else if (ilp <= 2) imad_wide_x_peak_kernel<2><<<grid, threads, 0, ctx->stream>>>(out, iters, 77u);
+        else imad_wide_x_peak_kernel<4><<<grid, threads, 0, ctx->stream>>>(out, iters, 77u);
+        cudaEventRecord(b, ctx->stream);
+        ctx->launches++;
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    const int eff = ilp <= 1 ? 1 : (ilp <= 2 ? 2 : 4);
+    *mads_per_s = (double)grid * threads * (double)iters * 8.0 * eff / (best * 1e-3);  // 8 wide multiply-adds per chain
+    return GKR_OK;
+}

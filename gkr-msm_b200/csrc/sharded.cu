@@ -17,6 +17,7 @@
 #include <atomic>
 #include <cstring>
 #include "common.cuh"
+#include "host_gates.hpp"
 #include "so.hpp"
 #include "transcript.hpp"
 
@@ -151,60 +152,58 @@ extern "C" int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exc
         for (uint32_t j = 0; j < P; j++) frh_to_limbs(fe[j], mine.data() + 4 * j);
         rc = gkr_exchange_allgather(ex, mine.data(), P, all.data());
         if (rc) return ctx->fail(rc, "final gather failed");
-        if (so_kind == GKR_SO_PLAIN && gate == GKR_GATE_PROD3 && P == 3) {
-            // the last log2(world) rounds over world x 3 values on the HOST: same arithmetic as the device object
-            // (sumcheck.rs:277-332, 160-163), without the uploads, the object and g more launches
-            std::vector<std::vector<gkr::FrH>> tb(3, std::vector<gkr::FrH>(world));
-            for (uint32_t j = 0; j < 3; j++)
-                for (int q = 0; q < world; q++) tb[j][q] = frh_from_limbs(all.data() + ((size_t)q * P + j) * 4);
-            for (int k = 0; k < g; k++) {
-                const size_t half = tb[0].size() / 2;
-                gkr::FrH sums[3] = {gkr::frh::ZERO, gkr::frh::ZERO, gkr::frh::ZERO};
-                for (size_t i = 0; i < half; i++) {
-                    gkr::FrH a[3], d[3];
-                    for (int j = 0; j < 3; j++) {
-                        a[j] = tb[j][2 * i + 1];
-                        d[j] = gkr::frh::sub(tb[j][2 * i + 1], tb[j][2 * i]);
-                    }
-                    for (int sidx = 0; sidx < 3; sidx++) {
-                        if (sidx)
-                            for (int j = 0; j < 3; j++) a[j] = gkr::frh::add(a[j], d[j]);
-                        sums[sidx] = gkr::frh::add(sums[sidx], gkr::frh::mul(gkr::frh::mul(a[0], a[1]), a[2]));
-                    }
+        // The last log2(world) rounds run over world x P gathered values on the HOST of every rank -- the same arithmetic as the
+        // device object (sumcheck.rs:277-332, 160-163) for whatever single-output gate the object wraps, without uploads, a
+        // second object and log2(world) more launches.
+        std::vector<gkr::FrH> consts(n_consts);
+        for (uint32_t i = 0; i < n_consts; i++) consts[i] = frh_from_limbs(gate_consts + 4 * i);
+        int gi = 0, go = 0;
+        const bool eq_gamma = so_kind == GKR_SO_EQ_GAMMA;
+        if (eq_gamma && (!gkr::base_gate_io(gate, &gi, &go) || (uint32_t)gi + 1 != P || (go > 1 && n_consts < (uint32_t)go)))
+            return ctx->fail(GKR_ERR_ARG, "sharded sumcheck: gate / constants do not match the object");
+        if (!eq_gamma && !(gate == GKR_GATE_PROD3 && P == 3) && !(gate == GKR_GATE_FOLDED_PROD && P == 2 * gate_param && n_consts >= gate_param))
+            return ctx->fail(GKR_ERR_UNSUPPORTED, "sharded sumcheck: unsupported single-output gate");
+        auto f = [&](const gkr::FrH* a) {  // the object's single-output function on one point
+            using namespace gkr::frh;
+            if (!eq_gamma) {
+                if (gate == GKR_GATE_PROD3) return mul(mul(a[0], a[1]), a[2]);
+                gkr::FrH s = ZERO;  // FoldedProdAlgFn, multiopen_reduction.rs:28-32
+                for (uint32_t k = 0; k < gate_param; k++) s = add(s, mul(mul(a[k], a[k + gate_param]), consts[k]));
+                return s;
+            }
+            gkr::FrH o[16];
+            gkr::base_gate_eval(gate, a, o);
+            gkr::FrH s = o[0];  // GammaWrapper: out_0 + sum_i gamma^i out_i, then EqWrapper: times the eq value
+            for (int k = 1; k < go; k++) s = add(s, mul(o[k], consts[k]));
+            return mul(s, a[gi]);
+        };
+        std::vector<std::vector<gkr::FrH>> tb(P, std::vector<gkr::FrH>(world));
+        for (uint32_t jj = 0; jj < P; jj++)
+            for (int q = 0; q < world; q++) tb[jj][q] = frh_from_limbs(all.data() + ((size_t)q * P + jj) * 4);
+        std::vector<gkr::FrH> a(P), d(P);
+        for (int k = 0; k < g; k++) {
+            const size_t half = tb[0].size() / 2;
+            gkr::FrH sums[GKR_MAX_DEG];
+            for (uint32_t sidx = 0; sidx < deg; sidx++) sums[sidx] = gkr::frh::ZERO;
+            for (size_t i = 0; i < half; i++) {
+                for (uint32_t jj = 0; jj < P; jj++) {
+                    a[jj] = tb[jj][2 * i + 1];
+                    d[jj] = gkr::frh::sub(tb[jj][2 * i + 1], tb[jj][2 * i]);
                 }
-                gkr::FrH x = round_io(sums);
-                for (int j = 0; j < 3; j++) {
-                    for (size_t i = 0; i < half; i++)
-                        tb[j][i] = gkr::frh::add(tb[j][2 * i], gkr::frh::mul(x, gkr::frh::sub(tb[j][2 * i + 1], tb[j][2 * i])));
-                    tb[j].resize(half);
+                for (uint32_t sidx = 0; sidx < deg; sidx++) {
+                    if (sidx)
+                        for (uint32_t jj = 0; jj < P; jj++) a[jj] = gkr::frh::add(a[jj], d[jj]);
+                    sums[sidx] = gkr::frh::add(sums[sidx], f(a.data()));
                 }
             }
-            for (int j = 0; j < 3; j++) fe[j] = tb[j][0];
-        } else {
-        std::vector<gkr_table*> tabs(P, nullptr);
-        std::vector<uint64_t> col((size_t)4 * world);
-        for (uint32_t j = 0; j < P && rc == GKR_OK; j++) {
-            for (int q = 0; q < world; q++) std::memcpy(col.data() + 4 * q, all.data() + ((size_t)q * P + j) * 4, 32);
-            rc = gkr_table_upload(ctx, col.data(), (uint64_t)world, &tabs[j]);
-            if (rc == GKR_OK) rc = gkr_ctx_sync(ctx);  // `col` is reused
+            gkr::FrH x = round_io(sums);
+            for (uint32_t jj = 0; jj < P; jj++) {
+                for (size_t i = 0; i < half; i++)
+                    tb[jj][i] = gkr::frh::add(tb[jj][2 * i], gkr::frh::mul(x, gkr::frh::sub(tb[jj][2 * i + 1], tb[jj][2 * i])));
+                tb[jj].resize(half);
+            }
         }
-        gkr_so* tail = nullptr;
-        uint64_t cl[4];
-        frh_to_limbs(claim, cl);
-        if (rc == GKR_OK) rc = gkr_so_create_dense(ctx, so_kind, gate, gate_param, gate_consts, n_consts, tabs.data(), P, (uint32_t)g, cl, &tail);
-        for (int k = 0; k < g && rc == GKR_OK; k++) {
-            gkr::FrH ev[GKR_MAX_DEG + 1];
-            uint32_t n = 0;
-            rc = tail->unipoly(ev, &n);
-            if (rc) break;
-            gkr::FrH x = round_io(ev + 1);
-            rc = tail->bind(x);
-        }
-        if (rc == GKR_OK) rc = tail->final_evals(fe.data());
-        delete tail;
-        for (auto* tb : tabs) gkr_table_free(tb);
-        if (rc) return rc;
-        }
+        for (uint32_t jj = 0; jj < P; jj++) fe[jj] = tb[jj][0];
     }
     if (out_claim) frh_to_limbs(claim, out_claim);
     if (out_point)

@@ -120,3 +120,75 @@ def test_msm_split_by_point_range_equals_single_gpu(ctx):
     srs = g.Srs.mock_setup(ctx, tau, H.g1_to_limbs(H.G1_GEN), n_local * world)
     whole = srs.msm(ctx.synth(5, n_local * world))
     assert whole.tolist() == res[0][1]
+
+
+def _eq_gamma_worker(rank, world, port, log_n_local, gate, n_in, point_limbs, gamma_limbs, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    import gkr_msm_b200 as g
+    from gkr_msm_b200.sharded import mont_add_many
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = g.Context(0)
+    name = f"/gkr_eqg_test_{port}"
+    ex = g.Exchange(name, rank, world, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        ex = g.Exchange(name, rank, world, create=False)
+    dist.barrier()
+    n = 1 << log_n_local
+    tabs = [ctx.synth(300 + j, n, first_index=rank * n) for j in range(n_in)]
+    # the eq table of the GLOBAL point, sliced by the top index bits like every other table
+    eq_full = ctx.eq_table(np.array(point_limbs, dtype=np.uint64)).download()
+    tabs.append(ctx.upload(eq_full[rank * n:(rank + 1) * n]))
+    consts = np.array(gamma_limbs, dtype=np.uint64)
+    local = ctx.gate_sum(g.SO_EQ_GAMMA, gate, tabs, consts=consts)
+    allc = ex.allgather(local.reshape(1, 4))
+    claim = mont_add_many([allc[r, 0] for r in range(world)])
+    so = ctx.dense_so(g.SO_EQ_GAMMA, gate, tabs, log_n_local, claim, consts=consts)
+    tr = g.Transcript(b"fgstglsp")
+    out = g.sumcheck_prove_sharded(tr, so, ex, log_n_local, g.SO_EQ_GAMMA, gate, claim, consts=consts)
+    q.put((rank, tr.proof(), claim.tolist(), out[1].tolist(), out[2].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gate_name", ["AFF_L1", "LOGUP_LAYER"])
+def test_sharded_eq_gamma_object_equals_single_rank(ctx, gate_name):
+    """the sharded driver is not Prod3-shaped: an EqWrapper(GammaWrapper(gate)) object -- eq table sliced like the other tables --
+    over 2 ranks gives the single-rank proof, incl. the last log2(world) rounds that run on the host"""
+    import torch.multiprocessing as mp
+
+    import gkr_msm_b200 as g
+    from oracle.pyref.field import P
+    from tests.util import to_limbs
+
+    gate, n_in, n_out = {"AFF_L1": (g.GATE_AFF_L1, 4, 3), "LOGUP_LAYER": (g.GATE_LOGUP_LAYER, 4, 2)}[gate_name]
+    world, log_n_local = 2, 9
+    n = log_n_local + 1
+    rng = random.Random(4242 + gate)
+    point = to_limbs([rng.randrange(P) for _ in range(n)])
+    gamma = rng.randrange(P)
+    consts = to_limbs([pow(gamma, i, P) for i in range(max(n_out, 2))])
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = 33500 + random.randrange(2000)
+    procs = [mpctx.Process(target=_eq_gamma_worker, args=(r, world, port, log_n_local, gate, n_in, point.tolist(), consts.tolist(), q))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    assert res[0][1:] == res[1][1:]
+    tabs = [ctx.synth(300 + j, 1 << n) for j in range(n_in)] + [ctx.eq_table(point)]
+    claim = ctx.gate_sum(g.SO_EQ_GAMMA, gate, tabs, consts=consts)
+    assert claim.tolist() == res[0][2]
+    so = ctx.dense_so(g.SO_EQ_GAMMA, gate, tabs, n, claim, consts=consts)
+    tr = g.Transcript(b"fgstglsp")
+    out = g.sumcheck_prove_sharded(tr, so, None, n, g.SO_EQ_GAMMA, gate, claim, consts=consts)
+    assert tr.proof() == res[0][1]
+    assert out[1].tolist() == res[0][3] and out[2].tolist() == res[0][4]

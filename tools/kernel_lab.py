@@ -27,6 +27,9 @@ names = {0: "regs, >=3 blocks/SM", 1: "regs, >=4 blocks/SM (spills)", 2: "smem a
          14: "node-split, >=8", 15: "node-split, >=10"}
 for ilp in (4, 8, 16):
     print(f"IMAD.WIDE peak, {ilp} independent chains/thread: {lablib.imad_wide_peak(ctx, ilp=ilp):.4g} wide multiply-adds/s", flush=True)
+for ilp in (1, 2, 4):
+    for bps in (2, 4, 8):
+        print(f"IMAD.WIDE.X (carry-chained) peak, {ilp} chains/thread, {bps} x 256 threads/SM: {lablib.imad_wide_x_peak(ctx, ilp=ilp, blocks_per_sm=bps):.4g} wide multiply-adds/s", flush=True)
 for mode in (0, 1):
     bytes_ = (32 * 3 * n) if mode == 0 else (48 * 3 * n)
     for variant in sorted(names):

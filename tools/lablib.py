@@ -20,6 +20,8 @@ def lab():
         _lab.gkr_lab_dense_prod3.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         _lab.gkr_lab_imad_wide_peak.restype = C.c_int
         _lab.gkr_lab_imad_wide_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        _lab.gkr_lab_imad_wide_x_peak.restype = C.c_int
+        _lab.gkr_lab_imad_wide_x_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lab.gkr_bench_modmul.restype = C.c_int
         _lab.gkr_bench_modmul.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     return _lab
@@ -31,6 +33,15 @@ def imad_wide_peak(ctx, ilp=8, threads=256, blocks_per_sm=8, iters=4000) -> floa
     rc = lab().gkr_lab_imad_wide_peak(ctx.h, ilp, threads, blocks_per_sm, iters, C.byref(out))
     if rc:
         raise RuntimeError(f"gkr_lab_imad_wide_peak failed: {rc}")
+    return out.value
+
+
+def imad_wide_x_peak(ctx, ilp=2, threads=256, blocks_per_sm=4, iters=4000) -> float:
+    """carry-chained wide multiply-adds per second (mad.lo.cc / madc.hi.cc pairs = IMAD.WIDE.U32.X), `ilp` independent 8-pair chains"""
+    out = C.c_double(0)
+    rc = lab().gkr_lab_imad_wide_x_peak(ctx.h, ilp, threads, blocks_per_sm, iters, C.byref(out))
+    if rc:
+        raise RuntimeError(f"gkr_lab_imad_wide_x_peak failed: {rc}")
     return out.value
 
 
