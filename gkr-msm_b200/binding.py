@@ -61,6 +61,7 @@ def _sig(lib):
     f("gkr_ctx_stream", _vp, _vp)
     f("gkr_ctx_timing_enable", C.c_int, _vp, C.c_int)
     f("gkr_ctx_set_fast_fold", C.c_int, _vp, C.c_int)
+    f("gkr_ctx_set_tuning", C.c_int, _vp, C.c_char_p, C.c_longlong)
     f("gkr_ctx_host_stats", C.c_int, _vp, _vp, C.c_int)
     f("gkr_ctx_timing_read", C.c_int, _vp, _vp, _vp, _vp, C.c_int)
     f("gkr_table_upload", C.c_int, _vp, _vp, C.c_uint64, C.POINTER(_vp))
@@ -171,6 +172,10 @@ class Context:
 
     def set_fast_fold(self, on: bool = True):
         self.check(self.lib.gkr_ctx_set_fast_fold(self.h, 1 if on else 0))
+
+    def set_tuning(self, key: str, value: int):
+        """kernel-selection knob by name (gkr_ctx_set_tuning): every setting is bit-exact"""
+        self.check(self.lib.gkr_ctx_set_tuning(self.h, key.encode(), int(value)))
 
     def timing_enable(self, on: bool = True):
         self.check(self.lib.gkr_ctx_timing_enable(self.h, 1 if on else 0))

@@ -7,6 +7,7 @@
 #include "../gates.cuh"
 #include "../dense_kernel.cuh"
 #include "../dense_split_kernel.cuh"
+#include "dense29_kernel.cuh"
 
 template <int MODE, bool FAST, int MINB, bool ACC_SMEM, int PF = 0>
 static int lab_run(gkr_ctx* ctx, DenseRoundArgs& a, int iters, float* ms, int* blocks_per_sm, int grid_mult) {
@@ -102,6 +103,36 @@ static int lab_run_split(gkr_ctx* ctx, DenseRoundArgs& a, int iters, float* ms, 
     return GKR_OK;
 }
 
+template <int MODE, int MINB>
+static int lab_run29(gkr_ctx* ctx, DenseRoundArgs& a, int iters, float* ms, int* blocks_per_sm, int grid_mult) {
+    auto kern = dense29_prod3_kernel<MODE, MINB>;
+    int b = 0;
+    GKR_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, GKR_REDUCE_THREADS, 0));
+    *blocks_per_sm = b;
+    unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)ctx->num_sms * b * grid_mult, GKR_MAX_BLOCKS);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int w = 0; w < 2; w++) {
+        a.o = ctx->round_out(0);
+        kern<<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(a);
+    }
+    cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; i < iters; i++) {
+        a.o = ctx->round_out(0);
+        kern<<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(a);
+        ctx->launches++;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    GKR_CUDA_OK(ctx, cudaGetLastError());
+    cudaEventElapsedTime(ms, e0, e1);
+    *ms /= iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return GKR_OK;
+}
+
 // mode 0: eval only over pairs; mode 1: FAST fold + eval (writes `out` tables of n/2).  n = table length.
 extern "C" int gkr_lab_dense_prod3(gkr_ctx* ctx, int variant, int mode, gkr_table* const* tables, gkr_table* const* out, uint64_t n,
                                    int iters, int grid_mult, float* ms, int* blocks_per_sm) {
@@ -135,6 +166,9 @@ extern "C" int gkr_lab_dense_prod3(gkr_ctx* ctx, int variant, int mode, gkr_tabl
             case 13: return lab_run_split<0, false, 7>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
             case 14: return lab_run_split<0, false, 8>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
             case 15: return lab_run_split<0, false, 10>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
+            case 20: return lab_run29<0, 3>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
+            case 21: return lab_run29<0, 2>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
+            case 22: return lab_run29<0, 4>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
         }
     } else {
         switch (variant) {
@@ -154,6 +188,9 @@ extern "C" int gkr_lab_dense_prod3(gkr_ctx* ctx, int variant, int mode, gkr_tabl
             case 13: return lab_run_split<1, true, 7>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
             case 14: return lab_run_split<1, true, 8>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
             case 15: return lab_run_split<1, true, 10>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
+            case 20: return lab_run29<1, 3>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
+            case 21: return lab_run29<1, 2>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
+            case 22: return lab_run29<1, 4>(ctx, a, iters, ms, blocks_per_sm, grid_mult);
         }
     }
 #undef LAB
@@ -232,6 +269,56 @@ __global__ void imad_wide_peak_kernel(unsigned long long* out, int iters, uint32
 #pragma unroll
     for (int k = 0; k < ILP; k++) s ^= acc[k];
     if (s == 0x123456789abcdef0ull) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keep the work alive
+}
+
+// The same probe with DISTINCT multiplier registers per instruction (8 a's x 8 b's, as a multi-precision product has): the
+// probe above re-reads the same two registers in every instruction, which the operand reuse cache serves without touching
+// the register file; a product of two 8..14-limb numbers cannot.  This is the rate a field multiplication can reach.
+__global__ void imad_wide_rot_kernel(unsigned long long* out, int iters, uint32_t b0) {
+    unsigned long long acc[16];
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        a[k] = threadIdx.x * 2654435761u + 12345u + 77u * k;
+        b[k] = b0 + blockIdx.x * 40503u + 1013u * k;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = 0x9e3779b97f4a7c15ull * (k + 1) + threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[i + j]) : "r"(a[i]), "r"(b[j]));
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s ^= acc[k];
+    if (s == 0x123456789abcdef0ull) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+extern "C" int gkr_lab_imad_wide_rot_peak(gkr_ctx* ctx, int threads, int blocks_per_sm, int iters, double* mads_per_s) {
+    if (!ctx || !mads_per_s) return GKR_ERR_ARG;
+    unsigned long long* out = nullptr;
+    int grid = ctx->num_sms * blocks_per_sm;
+    GKR_CUDA_OK(ctx, cudaMalloc(&out, sizeof(unsigned long long) * (size_t)grid * threads));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(a, ctx->stream);
+        imad_wide_rot_kernel<<<grid, threads, 0, ctx->stream>>>(out, iters, 77u);
+        cudaEventRecord(b, ctx->stream);
+        ctx->launches++;
+        GKR_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    *mads_per_s = (double)grid * threads * (double)iters * 64.0 / (best * 1e-3);
+    return GKR_OK;
 }
 
 extern "C" int gkr_lab_imad_wide_peak(gkr_ctx* ctx, int ilp, int threads, int blocks_per_sm, int iters, double* mads_per_s) {

@@ -141,20 +141,45 @@ __device__ Fq fq_inv(const Fq& a) {
 }
 
 // ---- kernels ------------------------------------------------------------------------------------------
-// scalars: Fr in Montgomery form -> plain integers; per (window, digit) histogram
-__global__ void msm_digits_kernel(const Fr* scalars, uint32_t n, int c, int n_windows, uint32_t* digits /* [W][n] */, uint32_t* counts /* [W][2^c] */) {
+// Window digits.  A digit entry is MSM_SKIP (nothing to add) or  bucket | sign << 31.
+//   unsigned (cb == c):   bucket = digit in [1, 2^c)
+//   signed   (cb == c-1): v = raw digit + carry; v > 2^cb is recoded as v - 2^c with a carry into the next window, so the
+//                         magnitudes are 0 .. 2^cb and a window needs HALF the buckets.  bucket = magnitude mod 2^cb: bucket
+//                         0 holds the magnitude 2^cb (the reduction gives it that weight, msm_window_sums `wrap`), and the
+//                         negative digits add the NEGATED base.  The window count covers 256 bits, so the last carry is zero.
+#define MSM_SKIP 0xffffffffu
+#define MSM_NEG 0x80000000u
+__device__ __forceinline__ uint32_t msm_raw_digit(const Fr& s, int w, int c) {
+    const int bit = w * c;
+    if (bit >= 256) return 0;
+    const int limb = bit >> 5, sh = bit & 31;
+    uint64_t v = s.l[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1);
+}
+__device__ __forceinline__ uint32_t msm_recode(uint32_t raw, int c, int cb, uint32_t& carry) {
+    if (cb == c) return raw ? raw : MSM_SKIP;
+    const uint32_t half = 1u << cb, v = raw + carry;
+    if (v > half) {
+        carry = 1;
+        const uint32_t m = (1u << c) - v;  // 0 .. half - 1
+        return m ? (m | MSM_NEG) : MSM_SKIP;
+    }
+    carry = 0;
+    return v ? (v & (half - 1)) : MSM_SKIP;  // v == half -> bucket 0
+}
+// scalars: Fr in Montgomery form -> plain integers; per (window, bucket) histogram
+__global__ void msm_digits_kernel(const Fr* scalars, uint32_t n, int c, int cb, int n_windows, uint32_t* digits /* [W][n] */,
+                                  uint32_t* counts /* [W][2^cb] */) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Fr one_raw = fr_zero();
         one_raw.l[0] = 1;
         Fr s = fr_mul(scalars[i], one_raw);  // s * R^-1: the canonical integer
+        uint32_t carry = 0;
         for (int w = 0; w < n_windows; w++) {
-            int bit = w * c;
-            int limb = bit >> 5, sh = bit & 31;
-            uint64_t v = s.l[limb];
-            if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
-            uint32_t d = (uint32_t)(v >> sh) & ((1u << c) - 1);
-            digits[(size_t)w * n + i] = d;
-            if (d) atomicAdd(&counts[((size_t)w << c) + d], 1u);
+            const uint32_t e = msm_recode(msm_raw_digit(s, w, c), c, cb, carry);
+            digits[(size_t)w * n + i] = e;
+            if (e != MSM_SKIP) atomicAdd(&counts[((size_t)w << cb) + (e & ~MSM_NEG)], 1u);
         }
     }
 }
@@ -166,25 +191,23 @@ struct MsmMultiScalars {
     uint32_t n[MSM_MULTI_MAX];
     uint32_t k;
 };
-__global__ void msm_digits_multi_kernel(const __grid_constant__ MsmMultiScalars S, uint32_t n_max, int c, int n_windows,
-                                        uint32_t* digits /* [k W][n_max] */, uint32_t* counts /* [k W][2^c] */) {
+__global__ void msm_digits_multi_kernel(const __grid_constant__ MsmMultiScalars S, uint32_t n_max, int c, int cb, int n_windows,
+                                        uint32_t* digits /* [k W][n_max] */, uint32_t* counts /* [k W][2^cb] */) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_max; i += gridDim.x * blockDim.x) {
         for (uint32_t j = 0; j < S.k; j++) {
             const size_t w0 = (size_t)j * n_windows;
-            if (i >= S.n[j]) {  // beyond this problem's length: digit zero (never accumulated)
-                for (int w = 0; w < n_windows; w++) digits[(w0 + w) * n_max + i] = 0;
+            if (i >= S.n[j]) {  // beyond this problem's length: never accumulated
+                for (int w = 0; w < n_windows; w++) digits[(w0 + w) * n_max + i] = MSM_SKIP;
                 continue;
             }
             Fr one_raw = fr_zero();
             one_raw.l[0] = 1;
             Fr s = fr_mul(S.s[j][i], one_raw);
+            uint32_t carry = 0;
             for (int w = 0; w < n_windows; w++) {
-                const int bit = w * c, limb = bit >> 5, sh = bit & 31;
-                uint64_t v = s.l[limb];
-                if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
-                const uint32_t d = (uint32_t)(v >> sh) & ((1u << c) - 1);
-                digits[(w0 + w) * n_max + i] = d;
-                if (d) atomicAdd(&counts[((w0 + w) << c) + d], 1u);
+                const uint32_t e = msm_recode(msm_raw_digit(s, w, c), c, cb, carry);
+                digits[(w0 + w) * n_max + i] = e;
+                if (e != MSM_SKIP) atomicAdd(&counts[((w0 + w) << cb) + (e & ~MSM_NEG)], 1u);
             }
         }
     }
@@ -237,14 +260,16 @@ __global__ void msm_scan_add_kernel(uint32_t* offsets, const uint32_t* tile_offs
     offsets[(size_t)blockIdx.x * 1024 + threadIdx.x] += tile_offs[blockIdx.x];
 }
 
-__global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int c, int n_windows, const uint32_t* offsets, uint32_t* cursor,
+// sorted entries: point index | sign << 31 (the accumulation negates the base of a negative digit)
+__global__ void msm_scatter_kernel(const uint32_t* digits, uint32_t n, int cb, int n_windows, const uint32_t* offsets, uint32_t* cursor,
                                    uint32_t* sorted /* [W][n] */) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         for (int w = 0; w < n_windows; w++) {
-            uint32_t d = digits[(size_t)w * n + i];
-            if (!d) continue;
-            uint32_t pos = atomicAdd(&cursor[((size_t)w << c) + d], 1u);
-            sorted[(size_t)w * n + offsets[((size_t)w << c) + d] + pos] = i;
+            const uint32_t e = digits[(size_t)w * n + i];
+            if (e == MSM_SKIP) continue;
+            const size_t b = ((size_t)w << cb) + (e & ~MSM_NEG);
+            const uint32_t pos = atomicAdd(&cursor[b], 1u);
+            sorted[(size_t)w * n + offsets[b] + pos] = i | (e & MSM_NEG);
         }
     }
 }
@@ -304,20 +329,27 @@ __global__ void __launch_bounds__(256) msm_bin_scatter_kernel(const uint32_t* co
 }
 
 // KIND 0: affine bases, 1: Jacobian (X, Y, Z), 2: extended Jacobian (X, Y, ZZ, ZZZ) as produced by gkr_g1_bucket_sums
+// `e` = base index | sign << 31 (sorted entries of the signed-digit MSM; the bucket-sum callers never set the sign);
+// shift: base offset of the problem (gkr_msm_g1_batch)
 template <int KIND>
-__device__ __forceinline__ void msm_add_base(G1X& acc, const void* bases, uint32_t i) {
+__device__ __forceinline__ void msm_add_base(G1X& acc, const void* bases, uint32_t e, uint32_t shift = 0) {
+    const uint32_t i = (e & ~MSM_NEG) + shift;
+    const bool neg = (e & MSM_NEG) != 0;
     if (KIND == 2) {
-        g1x_add_i(acc, ((const G1X*)bases)[i]);
+        G1X t = ((const G1X*)bases)[i];
+        if (neg) t.Y = fq_sub(fq_zero(), t.Y);
+        g1x_add_i(acc, t);
     } else if (KIND == 1) {
         // Jacobian (X, Y, Z) base: ZZ = Z^2, ZZZ = Z^3
         const Fq* p = (const Fq*)bases + (size_t)3 * i;
         Fq Z = p[2];
         if (fq_is_zero(Z)) return;
         G1X t;
-        t.X = p[0]; t.Y = p[1]; t.ZZ = fq_sqr(Z); t.ZZZ = fq_mul(t.ZZ, Z);
+        t.X = p[0]; t.Y = neg ? fq_sub(fq_zero(), p[1]) : p[1]; t.ZZ = fq_sqr(Z); t.ZZZ = fq_mul(t.ZZ, Z);
         g1x_add_i(acc, t);
     } else {
         G1Aff p = ((const G1Aff*)bases)[i];
+        if (neg) p.y = fq_sub(fq_zero(), p.y);  // (0, 0) = infinity stays (0, 0)
         g1x_madd_i(acc, p);
     }
 }
@@ -333,8 +365,9 @@ struct MsmAccArgs {
 };
 
 // light tier (< cap entries): one thread per bucket, in size order
-template <int KIND>
-__global__ void __launch_bounds__(128) msm_accumulate_light_kernel(const __grid_constant__ MsmAccArgs A) {
+// MINB: resident blocks per SM the register allocation is capped for (2: 176 registers; 3: 168, 12 warps per SM)
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_accumulate_light_kernel(const __grid_constant__ MsmAccArgs A) {
     const uint64_t n_heavy = (uint64_t)A.bins[A.cap] + A.bins[A.cap + 1];
     const uint64_t n_light = A.total - n_heavy;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_light * A.n_problems; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -344,7 +377,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_light_kernel(const __grid_
         const uint32_t shift = p * A.problem_stride;
         G1X acc = g1x_inf();
         const uint32_t* idx = A.sorted + (size_t)(b >> A.c) * A.n + A.offsets[b];
-        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, A.bases, idx[k] + shift);
+        for (uint32_t k = 0; k < cnt; k++) msm_add_base<KIND>(acc, A.bases, idx[k], shift);
         A.buckets[(size_t)p * A.total + b] = acc;
     }
 }
@@ -373,7 +406,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_medium_kernel(const __grid
         const uint32_t shift = p * A.problem_stride;
         const uint32_t* idx = A.sorted + (size_t)(b >> A.c) * A.n + A.offsets[b];
         G1X acc = g1x_inf();
-        for (uint32_t k = lane; k < cnt; k += 32) msm_add_base<KIND>(acc, A.bases, idx[k] + shift);
+        for (uint32_t k = lane; k < cnt; k += 32) msm_add_base<KIND>(acc, A.bases, idx[k], shift);
         sh[lane] = acc;
         __syncwarp();
         msm_group_tree(sh, lane, 32, false);
@@ -394,7 +427,7 @@ __global__ void __launch_bounds__(256) msm_accumulate_huge_kernel(const __grid_c
         const uint32_t shift = p * A.problem_stride;
         const uint32_t* idx = A.sorted + (size_t)(b >> A.c) * A.n + A.offsets[b];
         G1X acc = g1x_inf();
-        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, A.bases, idx[k] + shift);
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) msm_add_base<KIND>(acc, A.bases, idx[k], shift);
         sh[threadIdx.x] = acc;
         __syncthreads();
         msm_group_tree(sh, threadIdx.x, blockDim.x, true);
@@ -405,8 +438,14 @@ __global__ void __launch_bounds__(256) msm_accumulate_huge_kernel(const __grid_c
 
 // per window: sum_d d * B_d.  A thread owns the segment [lo, lo + L) of one window; descending running sums give
 // tot = sum (d - lo + 1) B_d and run = sum B_d, so the segment contributes tot + (lo - 1) * run.
+// 2^k * p by k doublings
+__device__ __forceinline__ G1X g1x_mul_pow2(G1X p, int k) {
+    for (int j = 0; j < k; j++) p = g1x_dbl(p);
+    return p;
+}
+// wrap: bucket 0 of every window weighs 2^c instead of 0 (the magnitude 2^c of the signed-digit recoding, msm_recode)
 __global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, int c, int seg_log, uint64_t n_threads, G1X* seg_out,
-                                                          uint32_t out_stride /* entries per window in seg_out */) {
+                                                          uint32_t out_stride /* entries per window in seg_out */, bool wrap) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     const uint32_t segs = 1u << (c - seg_log);
@@ -432,6 +471,7 @@ __global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, in
         G1X neg = run;
         neg.Y = fq_sub(fq_zero(), neg.Y);
         g1x_add(tot, neg);
+        if (wrap) g1x_add(tot, g1x_mul_pow2(B[0], c));
     }
     seg_out[(size_t)w * out_stride + sgm] = tot;
 }
@@ -441,7 +481,7 @@ __global__ void __launch_bounds__(128) msm_segment_kernel(const G1X* buckets, in
 // the second sum being the same weighted sum over an array 2^seg_log times shorter (msm_segment_kernel on it).
 // Per bucket: (2 L + seg_log) / L additions here + 5 / L above, instead of 5.
 __global__ void __launch_bounds__(128) msm_segment_level0_kernel(const G1X* buckets, int c, int seg_log, uint64_t n_threads, G1X* tot_out,
-                                                                 uint32_t tot_stride, G1X* run_out) {
+                                                                 uint32_t tot_stride, G1X* run_out, bool wrap) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_threads) return;
     const uint32_t segs = 1u << (c - seg_log);
@@ -455,6 +495,7 @@ __global__ void __launch_bounds__(128) msm_segment_level0_kernel(const G1X* buck
     }
     g1x_add(run, B[lo]);  // weight zero inside the segment
     for (int k = 0; k < seg_log; k++) run = g1x_dbl(run);
+    if (wrap && lo == 0) g1x_add(tot, g1x_mul_pow2(B[0], c));  // run_0 has weight zero in level 1, so B[0] counts only here
     tot_out[(size_t)w * tot_stride + sgm] = tot;
     run_out[t] = run;
 }
@@ -534,18 +575,17 @@ __global__ void __launch_bounds__(128) srs_precompute_kernel(const G1Aff* P, uin
 }
 
 // digits of all windows into one histogram; entry e = k * n + i
-__global__ void msm_digits_pre_kernel(const Fr* scalars, uint32_t n, int c, int n_windows, uint32_t* digits /* [W][n] */, uint32_t* counts /* [2^c] */) {
+__global__ void msm_digits_pre_kernel(const Fr* scalars, uint32_t n, int c, int cb, int n_windows, uint32_t* digits /* [W][n] */,
+                                      uint32_t* counts /* [2^cb] */) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         Fr one_raw = fr_zero();
         one_raw.l[0] = 1;
         Fr s = fr_mul(scalars[i], one_raw);  // the canonical integer
+        uint32_t carry = 0;
         for (int w = 0; w < n_windows; w++) {
-            const int bit = w * c, limb = bit >> 5, sh = bit & 31;
-            uint64_t v = s.l[limb];
-            if (limb + 1 < 8) v |= (uint64_t)s.l[limb + 1] << 32;
-            const uint32_t d = (uint32_t)(v >> sh) & ((1u << c) - 1);
-            digits[(size_t)w * n + i] = d;
-            if (d) atomicAdd(&counts[d], 1u);
+            const uint32_t e = msm_recode(msm_raw_digit(s, w, c), c, cb, carry);
+            digits[(size_t)w * n + i] = e;
+            if (e != MSM_SKIP) atomicAdd(&counts[e & ~MSM_NEG], 1u);
         }
     }
 }
@@ -554,10 +594,11 @@ __global__ void msm_scatter_pre_kernel(const uint32_t* digits, uint32_t n, int n
                                        uint32_t* cursor, uint32_t* sorted) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         for (int w = 0; w < n_windows; w++) {
-            const uint32_t d = digits[(size_t)w * n + i];
-            if (!d) continue;
+            const uint32_t e = digits[(size_t)w * n + i];
+            if (e == MSM_SKIP) continue;
+            const uint32_t d = e & ~MSM_NEG;
             const uint32_t pos = atomicAdd(&cursor[d], 1u);
-            sorted[offsets[d] + pos] = (uint32_t)w * srs_n + first + i;
+            sorted[offsets[d] + pos] = ((uint32_t)w * srs_n + first + i) | (e & MSM_NEG);
         }
     }
 }
@@ -629,20 +670,28 @@ extern "C" void gkr_srs_free(gkr_srs* s) {
 
 // window width: minimise W * (n + 3 * 2^c) bucket additions (accumulate + running-sum reduce) over c, and avoid a
 // degenerate top window (255 - (W - 1) c < 7 bits would put n / 2^bits points into each of a handful of buckets)
-static int pick_window(uint64_t n) {
+// Signed digits (msm_recode) halve the buckets of a window at the same number of additions; they are used from c = 8 up
+// (smaller MSMs are a handful of points) and need the windows to cover 256 bits (the last carry).
+struct MsmWindow {
+    int c, cb, W;  // window bits, bucket bits (c - 1 when signed), windows
+    bool is_signed() const { return cb != c; }
+};
+static MsmWindow pick_window(uint64_t n, bool allow_signed) {
     int lg = 0;
     while (((uint64_t)1 << lg) < n) lg++;
-    int best = 4;
+    MsmWindow best = {4, 4, 64};
     double best_cost = 1e300;
     for (int c = 4; c <= 18; c++) {
         if (c > lg + 1 && c > 4) break;
-        const int W = (255 + c - 1) / c;
-        const int top_bits = 255 - (W - 1) * c;
-        double cost = (double)W * ((double)n + 3.0 * (double)((uint64_t)1 << c));
+        const bool sg = allow_signed && c >= 8;
+        const int W = sg ? (256 + c - 1) / c : (255 + c - 1) / c;
+        const int cb = sg ? c - 1 : c;
+        const int top_bits = 255 - (W - 1) * c;  // scalar bits in the top window (a signed top window also takes a carry)
+        double cost = (double)W * ((double)n + 3.0 * (double)((uint64_t)1 << cb));
         if (top_bits < 7 && n > 4096) cost += 4.0 * (double)n;
         if (cost < best_cost) {
             best_cost = cost;
-            best = c;
+            best = {c, cb, W};
         }
     }
     return best;
@@ -680,7 +729,8 @@ static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint3
 #define GKR_MSM_ACC(K)                                                   \
     msm_accumulate_huge_kernel<K><<<gh, 256, sh_huge, st>>>(A);          \
     msm_accumulate_medium_kernel<K><<<gm, 128, sh_med, st>>>(A);         \
-    msm_accumulate_light_kernel<K><<<gl, 128, 0, st>>>(A);
+    if (ctx->msm_light_minb >= 3) msm_accumulate_light_kernel<K, 3><<<gl, 128, 0, st>>>(A);   \
+    else msm_accumulate_light_kernel<K, 2><<<gl, 128, 0, st>>>(A);
     if (kind == 2) { GKR_MSM_ACC(2) } else if (kind == 1) { GKR_MSM_ACC(1) } else { GKR_MSM_ACC(0) }
 #undef GKR_MSM_ACC
     ctx->launches += 6;
@@ -690,11 +740,12 @@ static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint3
 
 // window sums S_w = sum_d d * buckets[w][d] for W consecutive groups of 2^c buckets: segment running sums and the
 // per-group tree on the device, result (extended Jacobian) copied to the host.
-static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, std::vector<gkr::G1XH>& h) {
+// wrap: bucket 0 of every group weighs 2^c (signed-digit windows).
+static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, std::vector<gkr::G1XH>& h, bool wrap = false) {
     cudaStream_t st = ctx->stream;
     G1X* seg_out = nullptr;
     G1X* wsums = nullptr;
-    if (c == 4) {  // tiny windows: one warp per window
+    if (c == 4 && !wrap) {  // tiny windows: one warp per window
         GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * W, st));
         wsums = seg_out;
         msm_window_bits_kernel<<<(W + 3) / 4, 128, 0, st>>>(buckets, W, wsums);
@@ -712,8 +763,8 @@ static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, 
             G1X* runs = seg_out + (uint64_t)W * stride;
             wsums = runs + n_threads;
             G1X* parts = wsums + W;
-            msm_segment_level0_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, stride, runs);
-            msm_segment_kernel<<<(unsigned)((n_threads1 + 127) / 128), 128, 0, st>>>(runs, c1, seg_log1, n_threads1, seg_out + segs, stride);
+            msm_segment_level0_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, stride, runs, wrap);
+            msm_segment_kernel<<<(unsigned)((n_threads1 + 127) / 128), 128, 0, st>>>(runs, c1, seg_log1, n_threads1, seg_out + segs, stride, false);
             // stride = 9 * segs1 entries per window: nine blocks per window sum segs1 entries each, then one block the nine partials
             msm_window_tree_kernel<<<9 * W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs1, parts);
             msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(parts, 9, wsums);
@@ -721,7 +772,7 @@ static int msm_window_sums(gkr_ctx* ctx, const G1X* buckets, int c, uint32_t W, 
         } else {
             GKR_CUDA_OK(ctx, gkr_malloc_async(&seg_out, sizeof(G1X) * (n_threads + W), st));
             wsums = seg_out + n_threads;
-            msm_segment_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, segs);
+            msm_segment_kernel<<<(unsigned)((n_threads + 127) / 128), 128, 0, st>>>(buckets, c, seg_log, n_threads, seg_out, segs, wrap);
             msm_window_tree_kernel<<<W, 256, sizeof(G1X) * 256, st>>>(seg_out, segs, wsums);
             ctx->launches += 2;
         }
@@ -758,7 +809,7 @@ extern "C" int gkr_srs_precompute(gkr_ctx* ctx, gkr_srs* srs, int c) {
     if (!ctx) return GKR_ERR_ARG;
     if (!srs || srs->kind != 0 || c < 12 || c > 22 || srs->n == 0) return ctx->fail(GKR_ERR_ARG, "gkr_srs_precompute: affine SRS and 12 <= c <= 22");
     const int W = (255 + c - 1) / c;
-    if ((uint64_t)W * srs->n >= ((uint64_t)1 << 32)) return ctx->fail(GKR_ERR_UNSUPPORTED, "gkr_srs_precompute: table index does not fit 32 bits");
+    if ((uint64_t)W * srs->n >= ((uint64_t)1 << 31)) return ctx->fail(GKR_ERR_UNSUPPORTED, "gkr_srs_precompute: table index does not fit 31 bits");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     if (srs->pre) gkr_free_async(srs->pre, ctx->stream);
     srs->pre = nullptr;
@@ -778,9 +829,12 @@ extern "C" int gkr_srs_precompute(gkr_ctx* ctx, gkr_srs* srs, int c) {
 // R_j = sum_{d in chunk} B_d; the V pairs go to the host, which finishes with a running sum over the R_j.
 static int msm_g1_pre(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr* d_scalars, uint64_t n, uint64_t* out_xy) {
     cudaStream_t st = ctx->stream;
-    const int c = srs->pre_c, W = srs->pre_w, cc = c < 14 ? c : 14;
-    const size_t nbk = (size_t)1 << c;
-    const uint32_t V = 1u << (c - cc);
+    // signed digits (msm_recode) when the windows cover 256 bits: half the buckets to reduce
+    const int c = srs->pre_c, W = srs->pre_w;
+    const bool sg = ctx->msm_signed != 0 && W * c >= 256;
+    const int cb = sg ? c - 1 : c, cc = cb < 14 ? cb : 14;
+    const size_t nbk = (size_t)1 << cb;
+    const uint32_t V = 1u << (cb - cc);
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr;
     G1X* buckets = nullptr;
     GKR_CUDA_OK(ctx, gkr_malloc_async(&digits, sizeof(uint32_t) * W * n, st));
@@ -793,22 +847,23 @@ static int msm_g1_pre(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr
     G1X* part_sums = chunk_sums + V;
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
-    msm_digits_pre_kernel<<<g1, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, counts);
-    if (c >= 12) {  // tiled scan: `cursor` (still zero) doubles as scratch for the tile totals / bases and is cleared again
-        const uint32_t tiles = 1u << (c - 10);
+    msm_digits_pre_kernel<<<g1, 256, 0, st>>>(d_scalars, (uint32_t)n, c, cb, W, digits, counts);
+    if (cb >= 12) {  // tiled scan: `cursor` (still zero) doubles as scratch for the tile totals / bases and is cleared again
+        const uint32_t tiles = 1u << (cb - 10);
         uint32_t *tile_sums = cursor, *tile_offs = cursor + tiles;
         msm_scan_tiles_kernel<<<tiles, 1024, 0, st>>>(counts, offsets, tile_sums);
-        msm_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tile_offs, c - 10);
+        msm_scan_kernel<<<1, 1024, 0, st>>>(tile_sums, tile_offs, cb - 10);
         msm_scan_add_kernel<<<tiles, 1024, 0, st>>>(offsets, tile_offs);
         GKR_CUDA_OK(ctx, cudaMemsetAsync(cursor, 0, sizeof(uint32_t) * 2 * tiles, st));
         ctx->launches += 2;
     } else {
-        msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, c);
+        msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cb);
     }
     msm_scatter_pre_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, W, (uint32_t)first, (uint32_t)srs->n, offsets, cursor, sorted);
     ctx->launches += 3;
     std::vector<gkr::G1XH> hs, hr(V);
-    int rc = msm_accumulate(ctx, srs->pre, 0, sorted, counts, offsets, (uint32_t)((uint64_t)W * n), c, nbk, (uint64_t)W * n, work, buckets);
+    gkr::G1XH b0;  // bucket 0 = the magnitude 2^cb of the signed recoding
+    int rc = msm_accumulate(ctx, srs->pre, 0, sorted, counts, offsets, (uint32_t)((uint64_t)W * n), cb, nbk, (uint64_t)W * n, work, buckets);
     if (rc == GKR_OK) {
         if (nbk >= 1024 && parts >= V) {  // plain chunk sums R_j in two stages, so that the first one fills the machine
             msm_window_tree_kernel<<<parts, 256, sizeof(G1X) * 256, st>>>(buckets, 1024, part_sums);
@@ -822,6 +877,7 @@ static int msm_g1_pre(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr
     }
     if (rc == GKR_OK) {
         cudaError_t e = cudaMemcpyAsync(hr.data(), chunk_sums, sizeof(G1X) * V, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&b0, buckets, sizeof(G1X), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) rc = ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
     }
@@ -839,6 +895,10 @@ static int msm_g1_pre(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, const Fr
     for (int k = 0; k < cc; k++) wsum = dbl(wsum);
     for (uint32_t j = 0; j < V; j++) total = add(total, hs[j]);
     total = add(total, wsum);
+    if (sg) {
+        for (int k = 0; k < cb; k++) b0 = dbl(b0);
+        total = add(total, b0);
+    }
     to_affine(total, out_xy);
     return GKR_OK;
 }
@@ -862,9 +922,9 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
         std::memset(out_xy, 0, 96 * (size_t)n_problems);
         return GKR_OK;
     }
-    const int c = pick_window(n);
-    const int W = (255 + c - 1) / c;
-    const size_t nbk = (size_t)W << c;
+    const MsmWindow mw = pick_window(n, ctx->msm_signed != 0);
+    const int c = mw.c, cb = mw.cb, W = mw.W;
+    const size_t nbk = (size_t)W << cb;
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *work = nullptr;
     G1X* buckets = nullptr;
     GKR_CUDA_OK(ctx, gkr_malloc_async(&digits, sizeof(uint32_t) * W * n, st));
@@ -876,15 +936,15 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
     GKR_CUDA_OK(ctx, gkr_malloc_async(&buckets, sizeof(G1X) * nbk * n_problems, st));
     GKR_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, sizeof(uint32_t) * nbk * 3, st));
     unsigned g1 = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->num_sms * 8);
-    msm_digits_kernel<<<g1, 256, 0, st>>>(d_scalars, (uint32_t)n, c, W, digits, counts);
-    msm_scan_kernel<<<W, 1024, 0, st>>>(counts, offsets, c);
-    msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, c, W, offsets, cursor, sorted);
+    msm_digits_kernel<<<g1, 256, 0, st>>>(d_scalars, (uint32_t)n, c, cb, W, digits, counts);
+    msm_scan_kernel<<<W, 1024, 0, st>>>(counts, offsets, cb);
+    msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n, cb, W, offsets, cursor, sorted);
     ctx->launches += 3;
     const void* bases = (const unsigned char*)srs->d + first * srs->stride();
     std::vector<gkr::G1XH> h;
-    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, c, nbk, (uint64_t)W * n, work, buckets, n_problems,
+    int rc = msm_accumulate(ctx, bases, srs->kind, sorted, counts, offsets, (uint32_t)n, cb, nbk, (uint64_t)W * n, work, buckets, n_problems,
                             (uint32_t)problem_stride);
-    if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, c, (uint32_t)W * n_problems, h);
+    if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, cb, (uint32_t)W * n_problems, h, mw.is_signed());
     gkr_free_async(digits, st);
     gkr_free_async(sorted, st);
     gkr_free_async(counts, st);
@@ -941,10 +1001,10 @@ extern "C" int gkr_msm_g1_multi(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first
     }
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const int c = pick_window(n_max);
-    const int W = (255 + c - 1) / c;
+    const MsmWindow mw = pick_window(n_max, ctx->msm_signed != 0);
+    const int c = mw.c, cb = mw.cb, W = mw.W;
     const uint32_t KW = k * (uint32_t)W;
-    const size_t nbk = (size_t)KW << c;
+    const size_t nbk = (size_t)KW << cb;
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr;
     G1X* buckets = nullptr;
     GKR_CUDA_OK(ctx, gkr_malloc_async(&digits, sizeof(uint32_t) * KW * n_max, st));
@@ -962,14 +1022,14 @@ extern "C" int gkr_msm_g1_multi(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first
         if (j < k) entries += (uint64_t)W * n[j];
     }
     unsigned g1 = (unsigned)std::min<uint64_t>((n_max + 255) / 256, (uint64_t)ctx->num_sms * 8);
-    msm_digits_multi_kernel<<<g1, 256, 0, st>>>(S, (uint32_t)n_max, c, W, digits, counts);
-    msm_scan_kernel<<<KW, 1024, 0, st>>>(counts, offsets, c);
-    msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n_max, c, (int)KW, offsets, cursor, sorted);
+    msm_digits_multi_kernel<<<g1, 256, 0, st>>>(S, (uint32_t)n_max, c, cb, W, digits, counts);
+    msm_scan_kernel<<<KW, 1024, 0, st>>>(counts, offsets, cb);
+    msm_scatter_kernel<<<g1, 256, 0, st>>>(digits, (uint32_t)n_max, cb, (int)KW, offsets, cursor, sorted);
     ctx->launches += 3;
     const void* bases = (const unsigned char*)srs->d + first * srs->stride();
     std::vector<gkr::G1XH> h;
-    int rc = msm_accumulate(ctx, bases, 0, sorted, counts, offsets, (uint32_t)n_max, c, nbk, entries, work, buckets);
-    if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, c, KW, h);
+    int rc = msm_accumulate(ctx, bases, 0, sorted, counts, offsets, (uint32_t)n_max, cb, nbk, entries, work, buckets);
+    if (rc == GKR_OK) rc = msm_window_sums(ctx, buckets, cb, KW, h, mw.is_signed());
     gkr_free_async(digits, st);
     gkr_free_async(sorted, st);
     gkr_free_async(counts, st);

@@ -178,6 +178,8 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     ctx->num_sms = prop.multiProcessorCount;
     { const char* nf = getenv("GKR_NO_FAST_FOLD"); ctx->no_fast_fold = nf && nf[0] == '1'; }
     { const char* v = getenv("GKR_DENSE_FLAVOR"); if (v) ctx->dense_flavor = atoi(v); }
+    { const char* v = getenv("GKR_MSM_SIGNED"); if (v) ctx->msm_signed = atoi(v); }
+    { const char* v = getenv("GKR_MSM_LIGHT_MINB"); if (v) ctx->msm_light_minb = atoi(v); }
     { const char* v = getenv("GKR_DENSE_STAGED_MIN"); if (v && atoll(v) >= 0) ctx->dense_staged_min = (uint64_t)atoll(v); }
     { const char* v = getenv("GKR_DENSE_SMALL_MAX"); if (v && atoll(v) >= 0) ctx->dense_small_max = (uint64_t)atoll(v); }
     { const char* v = getenv("GKR_DEG2_COMPACT_MAX"); if (v && atoll(v) >= 0) ctx->deg2_compact_max = (uint64_t)atoll(v); }
@@ -494,6 +496,18 @@ extern "C" int gkr_ctx_host_stats(gkr_ctx* ctx, uint64_t out[4], int reset) {
 extern "C" int gkr_ctx_set_fast_fold(gkr_ctx* ctx, int on) {
     if (!ctx) return GKR_ERR_ARG;
     ctx->no_fast_fold = on == 0;
+    return GKR_OK;
+}
+
+extern "C" int gkr_ctx_set_tuning(gkr_ctx* ctx, const char* key, long long value) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!key || value < 0) return ctx->fail(GKR_ERR_ARG, "gkr_ctx_set_tuning: null key / negative value");
+    const std::string k(key);
+    if (k == "dense_small_max") ctx->dense_small_max = (uint64_t)value;
+    else if (k == "deg2_compact_max") ctx->deg2_compact_max = (uint64_t)value;
+    else if (k == "msm_signed") ctx->msm_signed = (int)value;
+    else if (k == "msm_light_minb") ctx->msm_light_minb = (int)value;
+    else return ctx->fail(GKR_ERR_ARG, "gkr_ctx_set_tuning: unknown key");
     return GKR_OK;
 }
 

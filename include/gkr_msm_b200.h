@@ -76,6 +76,10 @@ int gkr_ctx_timing_enable(gkr_ctx* ctx, int on);
 /* test hook: on = 0 makes DenseSumcheckObjectSO::bind always use the full Montgomery product instead of the
  * 128-bit-challenge fold (both are bit-exact; tests compare them at sizes the oracle cannot reach). Default on. */
 int gkr_ctx_set_fast_fold(gkr_ctx* ctx, int on);
+/* test / experiment hook: the kernel-selection knobs that the environment sets at context creation (GKR_DENSE_SMALL_MAX,
+ * GKR_DEG2_COMPACT_MAX, GKR_MSM_SIGNED), by name ("dense_small_max", "deg2_compact_max", "msm_signed").  Every setting is
+ * bit-exact; the tests run parity cases under each of them.  Unknown key: GKR_ERR_ARG. */
+int gkr_ctx_set_tuning(gkr_ctx* ctx, const char* key, long long value);
 /* host-side latency accounting: out = {ns spent inside kernel-launch calls of the round kernels, ns spent waiting for
  * round results, number of waits, kernels launched}; reset != 0 clears the first three. */
 int gkr_ctx_host_stats(gkr_ctx* ctx, uint64_t out[4], int reset);

@@ -255,3 +255,4 @@ def test_c_oracle_parity_across_kernel_switch(ctx, so_kind, gate, ntab):
     for r in range(nv):
         assert np.array_equal(evs[r], oev[r]), f"round {r}"
     assert np.array_equal(so.final_evals(), ofe)
+

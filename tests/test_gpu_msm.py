@@ -206,3 +206,81 @@ def test_msm_multi_equals_single_calls(ctx):
     out = np.zeros((4, 12), np.uint64)
     ctx.check(lib.gkr_msm_g1_multi(ctx.h, srs.h, 0, arr, ln.ctypes.data_as(C.c_void_p), 4, out.ctypes.data_as(C.c_void_p)))
     assert np.array_equal(out, want)
+
+
+@pytest.fixture(params=[1, 0], ids=["signed", "unsigned"])
+def recoding(ctx, request):
+    """both window recodings of the bucket MSM (msm_recode, msm.cu): signed digits (the default) and unsigned"""
+    ctx.set_tuning("msm_signed", request.param)
+    yield request.param
+    ctx.set_tuning("msm_signed", 1)
+
+
+@pytest.mark.parametrize("n", [300, 3000])
+def test_msm_signed_digit_boundaries(ctx, recoding, n):
+    """scalars built from the boundary digits of the signed recoding -- windows equal to 2^(c-1) (stay positive, bucket 0 =
+    the magnitude 2^(c-1)), 2^(c-1) + 1 (first negative), 2^c - 1 (carry chains through every window), r - 1 and values whose
+    top window takes a carry -- for every window width the size picks (c = 8 .. 12 here), against the textbook oracle"""
+    rng = random.Random(1000 + n)
+    base = [rand_g1(rng) for _ in range(16)]
+    pts = [base[i % 16] for i in range(n)]
+    sc = []
+    for c in (8, 9, 10, 11, 12, 13):
+        half = 1 << (c - 1)
+        for digit in (half, half + 1, half - 1, (1 << c) - 1, 1):
+            v = 0
+            for w in range(0, 255, c):
+                v |= digit << w
+            sc.append(v % P)
+        sc.append(sum((half if (w // c) % 2 == 0 else (1 << c) - 1) << w for w in range(0, 255, c)) % P)
+    sc += [P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, (1 << 254) - 1, (1 << 254), (1 << 254) + (1 << 253), 0, 1]
+    sc += [rng.randrange(P) for _ in range(n - len(sc))]
+    srs = g.Srs(ctx, aff_to_limbs(pts))
+    got = res_to_point(srs.msm(ctx.upload(to_limbs(sc))))
+    assert got == CV.g1_msm(pts, sc)
+
+
+def test_msm_signed_equals_unsigned_at_scale(ctx):
+    """2^17 and 2^19 points over the mock SRS (windows of 14 / 15 bits, one- and two-level bucket reduction): both recodings
+    return the same affine point, which is the closed form sum_i s_i tau^i G; same for the fixed-base table path"""
+    from gkr_msm_b200 import hostmath as H
+    from gkr_msm_b200.fieldutil import to_limb1
+
+    tau = 0x1234567890ABCDEF1234567
+    for log_n in (17, 19):
+        n = 1 << log_n
+        srs = g.Srs.mock_setup(ctx, to_limb1(tau), H.g1_to_limbs(H.G1_GEN), n)
+        sc = ctx.synth(4000 + log_n, n)
+        res = []
+        for sg in (1, 0):
+            ctx.set_tuning("msm_signed", sg)
+            res.append(srs.msm(sc).tolist())
+        ctx.set_tuning("msm_signed", 1)
+        assert res[0] == res[1]
+        if log_n == 17:
+            srs.precompute(16)  # 16 x 16 = 256 bits: the signed fixed-base path
+            assert srs.msm(sc).tolist() == res[0]
+            vals = from_limbs_fast(sc.download())
+            acc, t = 0, 1
+            for v in vals:
+                acc = (acc + v * t) % P
+                t = t * tau % P
+            assert res_to_point(np.array(res[0], dtype=np.uint64)) == CV.g1_mul(acc, CV.G1_GEN)
+        srs.free()
+
+
+def test_msm_signed_projective_and_batch(ctx, recoding):
+    """negative digits negate Jacobian and XYZZ bases too (msm_nonaff over bucket sums, gkr_msm_g1_batch)"""
+    rng = random.Random(77)
+    n = 600
+    base = [rand_g1(rng) for _ in range(12)]
+    pts = [base[i % 12] for i in range(n)]
+    sc = [rng.randrange(P) for _ in range(n)]
+    sc[:4] = [P - 1, (1 << 7) | (1 << 15), (P + 1) // 2, 255]
+    zs = [rng.randrange(1, FQ_MODULUS) for _ in range(n)]
+    proj = np.zeros((n, 18), np.uint64)
+    for i, (p, z) in enumerate(zip(pts, zs)):
+        z2 = z * z % FQ_MODULUS
+        proj[i] = fq_vec_to_mont_u64([p[0] * z2 % FQ_MODULUS, p[1] * z2 * z % FQ_MODULUS, z]).reshape(18)
+    srs = g.Srs(ctx, proj, projective=True)
+    assert res_to_point(srs.msm(ctx.upload(to_limbs(sc)))) == CV.g1_msm(pts, sc)

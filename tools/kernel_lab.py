@@ -24,12 +24,16 @@ names = {0: "regs, >=3 blocks/SM", 1: "regs, >=4 blocks/SM (spills)", 2: "smem a
          4: "regs, >=2 blocks/SM", 5: "regs, 3 blocks, L2 prefetch +1", 6: "regs, 3 blocks, L2 prefetch +2", 7: "regs, 3 blocks, L2 prefetch +4",
          8: "cp.async staged, >=3 blocks/SM", 9: "cp.async staged, >=4 blocks/SM (spills)",
          10: "node-split, >=4 blocks of 96", 11: "node-split, >=5", 12: "node-split, >=6", 13: "node-split, >=7",
-         14: "node-split, >=8", 15: "node-split, >=10"}
-for ilp in (4, 8, 16):
-    print(f"IMAD.WIDE peak, {ilp} independent chains/thread: {lablib.imad_wide_peak(ctx, ilp=ilp):.4g} wide multiply-adds/s", flush=True)
-for ilp in (1, 2, 4):
+         14: "node-split, >=8", 15: "node-split, >=10",
+         20: "reduced radix 9x29, >=3 blocks/SM", 21: "reduced radix 9x29, >=2 blocks/SM", 22: "reduced radix 9x29, >=4 blocks/SM (spills)"}
+if not os.environ.get("LAB_SKIP_PEAKS"):
+    for ilp in (4, 8, 16):
+        print(f"IMAD.WIDE peak, {ilp} independent chains/thread: {lablib.imad_wide_peak(ctx, ilp=ilp):.4g} wide multiply-adds/s", flush=True)
     for bps in (2, 4, 8):
-        print(f"IMAD.WIDE.X (carry-chained) peak, {ilp} chains/thread, {bps} x 256 threads/SM: {lablib.imad_wide_x_peak(ctx, ilp=ilp, blocks_per_sm=bps):.4g} wide multiply-adds/s", flush=True)
+        print(f"IMAD.WIDE peak, 8 x 8 product pattern (distinct operand registers), {bps} x 256 threads/SM: {lablib.imad_wide_rot_peak(ctx, blocks_per_sm=bps):.4g} wide multiply-adds/s", flush=True)
+    for ilp in (1, 2, 4):
+        for bps in (2, 4, 8):
+            print(f"IMAD.WIDE.X (carry-chained) peak, {ilp} chains/thread, {bps} x 256 threads/SM: {lablib.imad_wide_x_peak(ctx, ilp=ilp, blocks_per_sm=bps):.4g} wide multiply-adds/s", flush=True)
 for mode in (0, 1):
     bytes_ = (32 * 3 * n) if mode == 0 else (48 * 3 * n)
     for variant in sorted(names):

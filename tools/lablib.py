@@ -20,6 +20,8 @@ def lab():
         _lab.gkr_lab_dense_prod3.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
         _lab.gkr_lab_imad_wide_peak.restype = C.c_int
         _lab.gkr_lab_imad_wide_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        _lab.gkr_lab_imad_wide_rot_peak.restype = C.c_int
+        _lab.gkr_lab_imad_wide_rot_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lab.gkr_lab_imad_wide_x_peak.restype = C.c_int
         _lab.gkr_lab_imad_wide_x_peak.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
         _lab.gkr_bench_modmul.restype = C.c_int
@@ -33,6 +35,16 @@ def imad_wide_peak(ctx, ilp=8, threads=256, blocks_per_sm=8, iters=4000) -> floa
     rc = lab().gkr_lab_imad_wide_peak(ctx.h, ilp, threads, blocks_per_sm, iters, C.byref(out))
     if rc:
         raise RuntimeError(f"gkr_lab_imad_wide_peak failed: {rc}")
+    return out.value
+
+
+def imad_wide_rot_peak(ctx, threads=256, blocks_per_sm=4, iters=500) -> float:
+    """wide multiply-adds per second of an 8 x 8 limb product pattern (64 instructions over 8 + 8 distinct multiplier registers and
+    15 accumulator columns): no operand-reuse-cache help, the rate a multi-precision product can reach"""
+    out = C.c_double(0)
+    rc = lab().gkr_lab_imad_wide_rot_peak(ctx.h, threads, blocks_per_sm, iters, C.byref(out))
+    if rc:
+        raise RuntimeError(f"gkr_lab_imad_wide_rot_peak failed: {rc}")
     return out.value
 
 
