@@ -271,9 +271,25 @@ def _ctx_deg2_vecvec_so(self, gate, polys, gamma_pows, claim, point, col_logsize
     return SumcheckObject(self, h, list(polys))
 
 
+def _ctx_deg2_vecvec_shard_so(self, gate, polys, gamma_pows, point, col_logsize, shard, n_shards) -> "SumcheckObject":
+    """row shard `shard` of `n_shards` of a VecVecDeg2SumcheckObjectSO (gkr_so_create_deg2_vecvec_shard): polys hold this shard's
+    rows (col_logsize - log2(n_shards) column variables); point / col_logsize describe the whole object"""
+    lib = self.lib
+    lib.gkr_so_create_deg2_vecvec_shard.restype = C.c_int
+    lib.gkr_so_create_deg2_vecvec_shard.argtypes = [_vp, C.c_int, C.POINTER(_vp), C.c_uint32, _vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                    C.c_uint32, C.POINTER(_vp)]
+    arr = (_vp * len(polys))(*[p.h for p in polys])
+    gp, pt = _limbs(gamma_pows).reshape(-1, 4), _limbs(point).reshape(-1, 4)
+    h = _vp()
+    self.check(lib.gkr_so_create_deg2_vecvec_shard(self.h, gate, arr, len(polys), _ptr(gp), _ptr(pt), pt.shape[0], col_logsize, shard, n_shards,
+                                                   C.byref(h)))
+    return SumcheckObject(self, h, list(polys))
+
+
 Context.upload_vecvec = _ctx_upload_vecvec
 Context.deg2_dense_so = _ctx_deg2_dense_so
 Context.deg2_vecvec_so = _ctx_deg2_vecvec_so
+Context.deg2_vecvec_shard_so = _ctx_deg2_vecvec_shard_so
 
 
 class VecVec:
@@ -534,6 +550,21 @@ def sumcheck_prove_sharded(transcript: Transcript, so: SumcheckObject, exchange,
                                                so_kind, gate, gate_param, _ptr(c), c.shape[0], _ptr(gc), _ptr(claim), _ptr(point), _ptr(fe))
     so.ctx.check(rc)
     return claim, point[: local_rounds + g_], fe
+
+
+def sumcheck_prove_sharded_vecvec(transcript: Transcript, so: SumcheckObject, exchange, num_vars: int, global_claim):
+    """VecVecDeg2Sumcheck::prove with one row shard per rank (gkr_sumcheck_prove_sharded_vecvec; exchange=None: one shard).
+    num_vars: variables of the WHOLE object.  Returns (claim, point, final_evals) -- identical on every rank."""
+    lib = so.ctx.lib
+    lib.gkr_sumcheck_prove_sharded_vecvec.restype = C.c_int
+    lib.gkr_sumcheck_prove_sharded_vecvec.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    claim = np.zeros(4, np.uint64)
+    point = np.zeros((max(num_vars, 1), 4), np.uint64)
+    fe = np.zeros((so.num_polys, 4), np.uint64)
+    gc = _limbs(global_claim).reshape(4)
+    so.ctx.check(lib.gkr_sumcheck_prove_sharded_vecvec(transcript.h, so.h, exchange.h if exchange is not None else None, _ptr(gc), _ptr(claim),
+                                                       _ptr(point), _ptr(fe)))
+    return claim, point[:num_vars], fe
 
 
 # ---- witness maps (trait MapSplit) -------------------------------------------------------------------------

@@ -21,6 +21,7 @@
 #include "host_gates.hpp"
 #include "deg2_kernel.cuh"
 #include "so.hpp"
+#include "transcript.hpp"
 
 #define GKR_DEG2_COMPACT_MAX_PAIRS 32768  // pairs x gate blocks up to which a round runs the compact kernel
 
@@ -418,8 +419,9 @@ class Deg2SO : public gkr_so {
         return GKR_OK;
     }
 
-    int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
-        if (dense) return dense->unipoly(out, n_evals);
+    // the two eq-weighted totals of this round (vecvec_eq.rs:302-388 up to the call of from12): linear in the rows, so the row
+    // shards of one object (gkr_so_create_deg2_vecvec_shard) add theirs up
+    int round_totals(gkr::FrH* total1, gkr::FrH* total2) {
         if (round_idx >= n_sparse) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly: the protocol has already ended");
         if (cached) return ctx->fail(GKR_ERR_PROTOCOL, "unipoly called twice in a round");  // dense_eq.rs:109-111
         using namespace gkr::frh;
@@ -439,13 +441,32 @@ class Deg2SO : public gkr_so {
             padterm = mul(padG, r[2]);
             if (has_col_tail) padterm = add(padterm, mul(colpadG, col_tail));
         }  // dense object: tables are full, trailing_sum (dense_eq.rs:141) is zero
-        gkr::FrH total1 = mul(add(r[0], padterm), multiplier);
-        gkr::FrH total2 = mul(add(r[1], padterm), multiplier);
+        *total1 = mul(add(r[0], padterm), multiplier);
+        *total2 = mul(add(r[1], padterm), multiplier);
+        return GKR_OK;
+    }
+
+    int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
+        if (dense) return dense->unipoly(out, n_evals);
+        gkr::FrH total1, total2;
+        int rc = round_totals(&total1, &total2);
+        if (rc) return rc;
         const uint32_t b = binding_idx();
         from12(total1, total2, point[b], eq0_inv[b], claim_, evals);
         cached = true;
         for (int i = 0; i < 4; i++) out[i] = evals[i];
         if (n_evals) *n_evals = 4;
+        return GKR_OK;
+    }
+
+    int partial_sums(gkr::FrH* out, uint32_t* n) override {
+        if (dense) return dense->partial_sums(out, n);
+        int rc = round_totals(&out[0], &out[1]);
+        if (rc) return rc;
+        // the round polynomial belongs to the driver that adds the shards up: this object's own claim is not tracked from here on
+        for (int i = 0; i < 4; i++) evals[i] = gkr::frh::ZERO;
+        cached = true;
+        *n = 2;
         return GKR_OK;
     }
 
@@ -792,9 +813,10 @@ extern "C" int gkr_so_create_deg2_dense(gkr_ctx* ctx, const int* part_gate, cons
 }
 
 // VecVecDeg2SumcheckObjectSO::new   vecvec_eq.rs:94-118
-extern "C" int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
-                                         const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, uint32_t col_logsize,
-                                         gkr_so** out) {
+// weight: multiplier the object starts from (ONE; a row shard starts from eq(top column coordinates, shard index))
+static int make_vecvec_so(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
+                          const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, uint32_t col_logsize, const gkr::FrH& weight,
+                          gkr_so** out) {
     if (!ctx) return GKR_ERR_ARG;
     if (!polys || !gamma_pows || !claim || !point || !out) return ctx->fail(GKR_ERR_ARG, "null argument");
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -840,7 +862,105 @@ extern "C" int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* con
     so->lens0 = p0->row_len;
     rc = so->setup(in);
     if (rc) { delete so; return rc; }
+    so->multiplier = weight;
     *out = so;
+    return GKR_OK;
+}
+
+extern "C" int gkr_so_create_deg2_vecvec(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
+                                         const uint64_t claim[4], const uint64_t* point, uint32_t num_vars, uint32_t col_logsize,
+                                         gkr_so** out) {
+    return make_vecvec_so(ctx, gate, polys, n_polys, gamma_pows, claim, point, num_vars, col_logsize, gkr::frh::ONE, out);
+}
+
+// ---- VecVec sumcheck sharded by bucket rows ---------------------------------------------------------------------
+// The column (bucket-index) variables are the MOST significant ones and are only bound in the dense tail (vecvec.rs:156-159), so
+// the rows split by the top log2(G) bits of the row index: shard g holds the rows [g R / G, (g + 1) R / G) as a VecVec bundle
+// with col_logsize - log2(G) column variables.  Its row multipliers are eq(point_col_low, local row); the missing factor
+// e_g = eq(point[0 .. log2 G), g) is what the shard's multiplier starts from, so everything it reports -- the two totals of a
+// sparse round, the eq table of its slice of bind_into_dense -- is its exact share of the whole object's value.
+//   point: the WHOLE object's point (num_vars = row_logsize + col_logsize coordinates); polys: this shard's rows.
+extern "C" int gkr_so_create_deg2_vecvec_shard(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
+                                               const uint64_t* point, uint32_t num_vars, uint32_t col_logsize, uint32_t shard, uint32_t n_shards,
+                                               gkr_so** out) {
+    if (!ctx) return GKR_ERR_ARG;
+    if (!point || !out) return ctx->fail(GKR_ERR_ARG, "null argument");
+    uint32_t g = 0;
+    while ((1u << g) < n_shards) g++;
+    if (n_shards == 0 || (1u << g) != n_shards || shard >= n_shards || g > col_logsize)
+        return ctx->fail(GKR_ERR_ARG, "the number of shards must be a power of two, at most the number of rows");
+    using namespace gkr::frh;
+    gkr::FrH weight = ONE;  // eq(point[0 .. g), shard): point[0] pairs with the top bit of the row index
+    for (uint32_t i = 0; i < g; i++) {
+        const gkr::FrH p = frh_from_limbs(point + 4 * i);
+        weight = mul(weight, ((shard >> (g - 1 - i)) & 1) ? p : sub(ONE, p));
+    }
+    const uint64_t zero[4] = {0, 0, 0, 0};  // a shard does not track the claim: the driver owns it
+    return make_vecvec_so(ctx, gate, polys, n_polys, gamma_pows, zero, point + 4 * g, num_vars - g, col_logsize - g, weight, out);
+}
+
+extern "C" int gkr_exchange_world(const gkr_exchange* ex);  // sharded.cu
+
+// VecVecDeg2Sumcheck::prove over the row shards: every rank calls this with its shard, the shared transcript state and the WHOLE
+// object's claim.  Sparse rounds: the shards' totals are added (one all-gather of two field elements per round through the
+// exchange), from12 + Fiat-Shamir run replicated on every rank; then the dense tail over the column variables is the dense
+// sharded sumcheck (sharded.cu: local rounds, final gather, last log2(G) rounds on the host).  ex == NULL: one shard.
+// out_point: all num_vars challenges reversed (sumcheck.rs:120); out_final_evals: n_polys + 1 values (the eq table last).
+extern "C" int gkr_sumcheck_prove_sharded_vecvec(gkr_transcript* t, gkr_so* so, gkr_exchange* ex, const uint64_t global_claim[4],
+                                                 uint64_t out_claim[4], uint64_t* out_point, uint64_t* out_final_evals) {
+    if (!t || !so || !global_claim) return GKR_ERR_ARG;
+    gkr_ctx* ctx = so->ctx;
+    Deg2SO* d = dynamic_cast<Deg2SO*>(so);
+    if (!d || !d->is_vecvec || d->round_idx != 0 || d->dense) return ctx->fail(GKR_ERR_ARG, "expects a fresh VecVec Deg2 object");
+    using namespace gkr::frh;
+    const uint32_t world = ex ? (uint32_t)gkr_exchange_world(ex) : 1;
+    gkr::FrH claim = frh_from_limbs(global_claim);
+    std::vector<gkr::FrH> r;
+    std::vector<uint64_t> mine(8), all((size_t)8 * world);
+    const uint32_t n_sparse = d->n_sparse;
+    for (uint32_t k = 0; k < n_sparse; k++) {
+        gkr::FrH tot[2];
+        uint32_t n = 0;
+        const uint32_t b = d->binding_idx();
+        int rc = d->partial_sums(tot, &n);
+        if (rc) return rc;
+        if (world > 1) {
+            frh_to_limbs(tot[0], mine.data());
+            frh_to_limbs(tot[1], mine.data() + 4);
+            rc = gkr_exchange_allgather(ex, mine.data(), 2, all.data());
+            if (rc) return ctx->fail(rc, "partial-sum exchange failed");
+            tot[0] = tot[1] = ZERO;
+            for (uint32_t q = 0; q < world; q++) {
+                tot[0] = add(tot[0], frh_from_limbs(all.data() + (size_t)q * 8));
+                tot[1] = add(tot[1], frh_from_limbs(all.data() + (size_t)q * 8 + 4));
+            }
+        }
+        gkr::FrH ev[4];
+        from12(tot[0], tot[1], d->point[b], d->eq0_inv[b], claim, ev);
+        std::vector<gkr::FrH> poly = interpolate_coeffs(ev, 4);
+        gkr::FrH msg[3] = {poly[0], poly[2], poly[3]};  // compress_coefficients: the linear term is dropped
+        t->t.write_scalars(msg, 3);
+        const gkr::FrH x = t->t.challenge(128);
+        r.push_back(x);
+        claim = evaluate_univar(poly, x);
+        rc = d->bind(x);
+        if (rc) return rc;
+    }
+    // dense tail: EqWrapper(GammaWrapper(func, gamma)) over this shard's rows, eq slice already scaled by the shard weight
+    std::vector<uint64_t> consts(4 * d->gamma_pows.size()), tail_point((size_t)4 * (d->col + 8));
+    for (size_t i = 0; i < d->gamma_pows.size(); i++) frh_to_limbs(d->gamma_pows[i], consts.data() + 4 * i);
+    uint64_t cl[4];
+    frh_to_limbs(claim, cl);
+    uint32_t g = 0;
+    while ((1u << g) < world) g++;
+    int rc = gkr_sumcheck_prove_sharded(t, so, ex, d->col, GKR_SO_EQ_GAMMA, d->tail_gate, 0, consts.data(), (uint32_t)d->gamma_pows.size(), cl, out_claim,
+                                        tail_point.data(), out_final_evals);
+    if (rc) return rc;
+    if (out_point) {
+        const uint32_t n_tail = d->col + g;
+        std::memcpy(out_point, tail_point.data(), (size_t)32 * n_tail);  // the last challenges come first
+        for (uint32_t k = 0; k < n_sparse; k++) frh_to_limbs(r[n_sparse - 1 - k], out_point + 4 * ((size_t)n_tail + k));
+    }
     return GKR_OK;
 }
 

@@ -67,6 +67,8 @@ extern "C" int gkr_exchange_open(const char* name, int rank, int world, int crea
     return GKR_OK;
 }
 
+extern "C" int gkr_exchange_world(const gkr_exchange* ex) { return ex ? ex->world : 1; }
+
 extern "C" void gkr_exchange_close(gkr_exchange* ex) {
     if (!ex) return;
     munmap(ex->sh, sizeof(ExShared));

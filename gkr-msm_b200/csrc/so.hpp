@@ -10,6 +10,18 @@ struct gkr_so {
     virtual int unipoly(gkr::FrH* evals, uint32_t* n_evals) = 0;
     virtual int bind(const gkr::FrH& t) = 0;
     virtual int final_evals(gkr::FrH* out) = 0;
+    // Multi-GPU drivers (sharded.cu, deg2.cu): the LINEAR part of this round's message, i.e. what the shards of one object add up
+    // before the host derives the round polynomial.  Default: the sums at the nodes 1..deg (dense objects); the Deg2 objects
+    // return their two eq-weighted totals (the inputs of from12).  Counts as this round's unipoly() for the call protocol.
+    virtual int partial_sums(gkr::FrH* out, uint32_t* n) {
+        gkr::FrH ev[GKR_MAX_DEG + 1];
+        uint32_t ne = 0;
+        int rc = unipoly(ev, &ne);
+        if (rc) return rc;
+        for (uint32_t s = 1; s < ne; s++) out[s - 1] = ev[s];
+        *n = ne - 1;
+        return GKR_OK;
+    }
     virtual gkr::FrH claim() const = 0;
     virtual uint32_t degree() const = 0;
     virtual uint32_t num_polys() const = 0;

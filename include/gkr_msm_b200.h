@@ -356,6 +356,21 @@ int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exchange* ex, 
                                uint32_t gate_param, const uint64_t* gate_consts, uint32_t n_consts,
                                const uint64_t global_claim[4], uint64_t out_claim[4], uint64_t* out_point,
                                uint64_t* out_final_evals);
+int gkr_exchange_world(const gkr_exchange* ex);
+/* VecVecDeg2SumcheckObjectSO sharded by bucket ROWS (the column variables are the most significant ones and are
+ * bound last, src/cleanup/polys/vecvec.rs:150-160): shard g of n_shards (a power of two) holds the rows
+ * [g R / n_shards, (g + 1) R / n_shards) of every polynomial, uploaded / gathered / mapped as VecVec handles with
+ * col_logsize - log2(n_shards) column variables -- the witness maps (gkr_map_vecvec) are row-local, so each shard builds its
+ * layers from its own rows.  point / num_vars / col_logsize describe the WHOLE object. */
+int gkr_so_create_deg2_vecvec_shard(gkr_ctx* ctx, int gate, gkr_vecvec* const* polys, uint32_t n_polys, const uint64_t* gamma_pows,
+                                    const uint64_t* point, uint32_t num_vars, uint32_t col_logsize, uint32_t shard, uint32_t n_shards,
+                                    gkr_so** out);
+/* VecVecDeg2Sumcheck::prove (vecvec_eq.rs:447-500 over GenericSumcheckProtocol::prove) with one shard per rank: per sparse
+ * round the two eq-weighted totals of every shard are added through the exchange, from12 and Fiat-Shamir run replicated on
+ * every rank; the dense tail is gkr_sumcheck_prove_sharded.  ex == NULL: one shard.  The proof bytes, the point
+ * (num_vars challenges, reversed) and the n_polys + 1 final evaluations equal the single-GPU object's. */
+int gkr_sumcheck_prove_sharded_vecvec(gkr_transcript* t, gkr_so* so, gkr_exchange* ex, const uint64_t global_claim[4],
+                                      uint64_t out_claim[4], uint64_t* out_point, uint64_t* out_final_evals);
 
 #ifdef __cplusplus
 }

@@ -192,3 +192,115 @@ def test_sharded_eq_gamma_object_equals_single_rank(ctx, gate_name):
     out = g.sumcheck_prove_sharded(tr, so, None, n, g.SO_EQ_GAMMA, gate, claim, consts=consts)
     assert tr.proof() == res[0][1]
     assert out[1].tolist() == res[0][3] and out[2].tolist() == res[0][4]
+
+
+def _vv_problem(seed, rowv, colv, nrows):
+    """deterministic ragged PRJ_L1 bundle (6 polynomials, the reference's point padding), point, gamma powers"""
+    from oracle.pyref.field import P
+
+    rng = random.Random(seed)
+    lens = [rng.randrange(0, (1 << rowv) + 1) for _ in range(nrows)]
+    lens[0] = 1 << rowv
+    lens[nrows - 1] = max(lens[nrows - 1], 3)
+    pads = [(0, 0), (1, 1), (1, 1)] * 2
+    data = [[[rng.randrange(P) for _ in range(l)] for l in lens] for _ in range(6)]
+    point = [rng.randrange(P) for _ in range(rowv + colv)]
+    gamma = rng.randrange(P)
+    gp = [pow(gamma, i, P) for i in range(4)]
+    return lens, pads, data, point, gp
+
+
+def _vv_upload(ctx, data, pads, rowv, colv, r0, r1):
+    from tests.util import to_limb1, to_limbs
+
+    return [ctx.upload_vecvec([to_limbs(r) if len(r) else np.zeros((0, 4), np.uint64) for r in data[j][r0:r1]], to_limb1(pads[j][0]),
+                              to_limb1(pads[j][1]), rowv, colv) for j in range(6)]
+
+
+def _vv_worker(rank, world, port, seed, rowv, colv, nrows, claim_limbs, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+
+    import gkr_msm_b200 as g
+    from tests.util import to_limbs
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ctx = g.Context(0)
+    name = f"/gkr_vv_test_{port}"
+    ex = g.Exchange(name, rank, world, create=True) if rank == 0 else None
+    dist.barrier()
+    if rank != 0:
+        ex = g.Exchange(name, rank, world, create=False)
+    dist.barrier()
+    lens, pads, data, point, gp = _vv_problem(seed, rowv, colv, nrows)
+    gl = world.bit_length() - 1
+    per = 1 << (colv - gl)
+    r0, r1 = rank * per, min((rank + 1) * per, nrows)
+    polys = _vv_upload(ctx, data, pads, rowv, colv - gl, r0, r1)
+    so = ctx.deg2_vecvec_shard_so(g.GATE_PRJ_L1, polys, to_limbs(gp), to_limbs(point), colv, rank, world)
+    tr = g.Transcript(b"fgstglsp")
+    claim, pt, fe = g.sumcheck_prove_sharded_vecvec(tr, so, ex, rowv + colv, np.array(claim_limbs, dtype=np.uint64))
+    # the witness maps are row-local: this shard's L1 layer from its own rows
+    l1 = ctx.map_vecvec([(g.GATE_PRJ_L1, 1)], polys, mode=0)
+    rows = [[r.tolist() for r in p.download()[0]] for p in l1]
+    q.put((rank, tr.proof(), claim.tolist(), pt.tolist(), fe.tolist(), rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,colv,nrows", [(2, 3, 7), (4, 3, 8), (2, 1, 2)])
+def test_vecvec_sumcheck_sharded_by_rows_equals_single_gpu(ctx, world, colv, nrows):
+    """SURVEY 8e, VecVec by bucket rows: the ragged Deg2 sumcheck with its rows split by the top bits of the row index over
+    `world` ranks -- sparse rounds (totals added through the exchange), bind_into_dense, sharded dense tail with the last
+    log2(world) rounds on the host -- writes the single-GPU proof bytes and returns its point and final evaluations; the
+    single-GPU proof is the oracle's (tests/test_gpu_deg2.py).  The shards' witness maps are the rows of the whole map."""
+    import torch.multiprocessing as mp
+
+    import gkr_msm_b200 as g
+    from oracle.pyref import gates as G
+    from oracle.pyref import sumcheck as S
+    from oracle.pyref.field import P
+    from tests.util import to_limb1, to_limbs
+
+    rowv, seed = 4, 5150 + 10 * world + colv
+    lens, pads, data, point, gp = _vv_problem(seed, rowv, colv, nrows)
+    nv = rowv + colv
+    gate = G.PrjL1()
+    opolys = [S.VecVecPolynomial(data[j], pads[j][0], pads[j][1], rowv, colv) for j in range(6)]
+    eqp = S.eq_poly_sequence_last(point)
+    dense = [p.vec() for p in opolys]
+    evs = [0] * gate.n_outs
+    for i in range(len(eqp)):
+        o = gate.exec([d[i] for d in dense])
+        for k in range(gate.n_outs):
+            evs[k] = (evs[k] + o[k] * eqp[i]) % P
+    claim = sum(gp[i] * evs[i] for i in range(gate.n_outs)) % P
+
+    polys = _vv_upload(ctx, data, pads, rowv, colv, 0, nrows)
+    so = ctx.deg2_vecvec_so(g.GATE_PRJ_L1, polys, to_limbs(gp), to_limb1(claim), to_limbs(point), colv)
+    tr = g.Transcript(b"fgstglsp")
+    c1, p1, f1 = g.sumcheck_prove(tr, so, nv)
+    want = (tr.proof(), c1.tolist(), p1.tolist(), f1.tolist())
+    # one shard through the sharded driver
+    so1 = ctx.deg2_vecvec_shard_so(g.GATE_PRJ_L1, polys, to_limbs(gp), to_limbs(point), colv, 0, 1)
+    tr1 = g.Transcript(b"fgstglsp")
+    c2, p2, f2 = g.sumcheck_prove_sharded_vecvec(tr1, so1, None, nv, to_limb1(claim))
+    assert (tr1.proof(), c2.tolist(), p2.tolist(), f2.tolist()) == want
+    full_l1 = [[r.tolist() for r in p.download()[0]] for p in ctx.map_vecvec([(g.GATE_PRJ_L1, 1)], polys, mode=0)]
+
+    mpctx = mp.get_context("spawn")
+    q = mpctx.Queue()
+    port = 35500 + random.randrange(2000)
+    procs = [mpctx.Process(target=_vv_worker, args=(r, world, port, seed, rowv, colv, nrows, to_limb1(claim).tolist(), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+    per = 1 << (colv - (world.bit_length() - 1))
+    for rk, proof, c, pt, fe, rows in res:
+        assert (proof, c, pt, fe) == want, f"rank {rk}"
+        for j in range(len(full_l1)):
+            assert rows[j] == full_l1[j][rk * per:(rk + 1) * per]
