@@ -329,16 +329,21 @@ def run_ours(args, rank, world, local_rank):
         # multiplier-pipe roofline: achieved wide multiply-adds per second over the measured peak of the same instruction
         try:
             from tools import lablib
-            pk = max(lablib.imad_wide_peak(ctx, ilp=ilp) for ilp in (8, 16))
+            # the field routines are chains of mad.lo.cc / madc.hi.cc pairs = IMAD.WIDE.U32.X, which retires at HALF the rate of the
+            # carry-less IMAD.WIDE.U32 on this part (both probes in csrc/lab/kernel_lab.cu): the chained rate is the peak that applies
+            pk_x = max(lablib.imad_wide_x_peak(ctx, ilp=ilp, blocks_per_sm=8) for ilp in (2, 4))
+            pk_plain = max(lablib.imad_wide_peak(ctx, ilp=ilp) for ilp in (8, 16))
             for e in roofline_all:
-                e["frac_int_pipe"] = e["achieved_wide_mads_per_s"] / pk
-            roofline["int_pipe"] = {"achieved_wide_mads_per_s": dom["achieved_wide_mads_per_s"], "peak_wide_mads_per_s": pk,
-                                    "frac": dom["achieved_wide_mads_per_s"] / pk,
-                                    "how": "peak = IMAD.WIDE.U32 probe, 8-16 independent accumulators per thread, 8 x 256 threads per SM "
-                                           "(csrc/lab/kernel_lab.cu); achieved = static multiply-add count of the field routines x items / "
-                                           "measured launch time.  The kernels issue carry-chained IMAD.WIDE.U32.X plus ~1.3 non-multiply "
-                                           "integer instructions per multiply-add, so the fraction understates how busy the pipe is "
-                                           "(ncu: sm__inst_executed_pipe_fmaheavy, profiles/)"}
+                e["frac_int_pipe"] = e["achieved_wide_mads_per_s"] / pk_x
+            roofline["int_pipe"] = {"achieved_wide_mads_per_s": dom["achieved_wide_mads_per_s"], "peak_wide_mads_per_s": pk_x,
+                                    "frac": dom["achieved_wide_mads_per_s"] / pk_x,
+                                    "peak_carryless_wide_mads_per_s": pk_plain, "frac_of_carryless_peak": dom["achieved_wide_mads_per_s"] / pk_plain,
+                                    "how": "peak = carry-chained multiply-add probe (mad.lo.cc / madc.hi.cc pairs = IMAD.WIDE.U32.X, the form the field "
+                                           "routines use), 2-4 independent chains per thread, 8 x 256 threads per SM (csrc/lab/kernel_lab.cu); it is half "
+                                           "the carry-less IMAD.WIDE.U32 rate (peak_carryless).  achieved = static multiply-add count of the field routines "
+                                           "x items / measured launch time.  A carry-free 9 x 29-bit rewrite of the round kernel (full-rate IMAD.WIDE.U32, "
+                                           "lab variant 20) was measured 2x slower: it needs 1.7x the multiply-adds and its 64-bit column carries load the "
+                                           "ALU pipe (DESIGN.md 3.1)"}
         except Exception as e:  # pragma: no cover
             roofline["int_pipe"] = {"error": str(e)}
         roofline["roofline_all"] = roofline_all
@@ -387,6 +392,37 @@ def run_ours(args, rank, world, local_rank):
                   "what": f"strong scaling: ONE 2^{log_n} x 3 sumcheck split by top index bits over {world} GPUs; compare with the 1-GPU ms_per_step of the "
                           "weak line (same total work).  Limiter: the ~20 small rounds and the per-round host exchange are latency, not bandwidth"}
         del sjob
+
+    # ---- the ragged Deg2 sumcheck of one addition layer with the bucket rows split over the ranks (VecVec by rows) ----
+    vecvec_rows = None
+    if not args.no_vecvec:
+        from gkr_msm_b200.sharded import ShardedVecVecSumcheck
+        try:
+            vjob = ShardedVecVecSumcheck(ctx, row_log=args.vecvec_row_log, col_local_log=args.vecvec_col_log, rank=rank, world=world,
+                                         exchange=job.exchange if world > 1 else None)
+            for _ in range(3):
+                vjob.prove()
+            barrier()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record(stream)
+            for _ in range(args.steps):
+                vjob.prove()
+            v1.record(stream)
+            barrier()
+            v_ms = v0.elapsed_time(v1)
+            if dist is not None:
+                t = torch.tensor([v_ms], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                v_ms = float(t.item())
+            v_ms /= args.steps
+            vecvec_rows = {"ms_per_step": v_ms, "table_elements_per_gpu": vjob.elements, "table_elements_per_s": vjob.elements * world / (v_ms * 1e-3),
+                           "scaling": "weak", "num_vars": vjob.num_vars,
+                           "what": f"VecVecDeg2Sumcheck::prove, gate twisted_edwards_add_l1 (6 polynomials), 2^{args.vecvec_col_log} rows of "
+                                   f"2^{args.vecvec_row_log} elements per GPU, rows split by the top bits of the row index over {world} GPU(s); "
+                                   "per sparse round two field elements per rank through the exchange, dense tail sharded like the headline"}
+            del vjob
+        except Exception as e:  # pragma: no cover
+            vecvec_rows = {"error": repr(e)}
 
     # ---- N > 1: the whole prover with the commitment MSMs split by point range over the ranks (csrc/msm_team.cu) -----------
     pip20_multi = None
@@ -475,7 +511,7 @@ def run_ours(args, rank, world, local_rank):
                                   "the max-over-ranks timing all-reduce; no device collective on the data path"),
                    "l2": "inputs (1.5 GiB per GPU) larger than the 126 MB L2", "transcript": "merlin on host, one challenge per round"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "pippenger_prove": pip, "pippenger_prove_2e20": pip20, "strong_scaling": strong,
+        "pippenger_prove": pip, "pippenger_prove_2e20": pip20, "strong_scaling": strong, "vecvec_rows": vecvec_rows,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -494,6 +530,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pippenger", action="store_true")
+    ap.add_argument("--no-vecvec", action="store_true", help="skip the row-sharded ragged sumcheck leg")
+    ap.add_argument("--vecvec-row-log", type=int, default=11)
+    ap.add_argument("--vecvec-col-log", type=int, default=12, help="log2 of the rows per GPU of the row-sharded ragged sumcheck leg")
     ap.add_argument("--no-pippenger-2e20", action="store_true", help="skip the x=20 whole-prover leg (about 15 s of input generation)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -99,6 +99,50 @@ class ShardedProd3Sumcheck:
         return out
 
 
+class ShardedVecVecSumcheck:
+    """VecVecDeg2Sumcheck::prove (src/cleanup/protocols/sumchecks/vecvec_eq.rs:447-500) with the bucket rows split over the ranks by the
+    top bits of the row index: every rank holds 2^col_local_log full rows of 2^row_log elements of the 6 coordinate
+    polynomials of a projective addition layer (gate twisted_edwards_add_l1, the reference's point padding), built on its GPU.
+    Weak scaling: the rows per GPU are fixed.  The claim is synthetic (this is a timing job; parity of the sharded path with the
+    single-GPU object and the oracle is in tests/test_gpu_sharded.py)."""
+    P = 6
+
+    def __init__(self, ctx: g.Context, row_log: int, col_local_log: int, rank: int = 0, world: int = 1, exchange=None, seed: int = 11):
+        assert world & (world - 1) == 0, "world size must be a power of two"
+        from .fieldutil import to_limb1, to_limbs
+
+        self.ctx, self.rank, self.world, self.exchange = ctx, rank, world, exchange
+        self.row_log, self.col_log = row_log, col_local_log + (world.bit_length() - 1)
+        nrows, rlen = 1 << col_local_log, 1 << row_log
+        n = nrows * rlen
+        idx = np.arange(n, dtype=np.uint32)
+        lens = np.full(nrows, rlen, dtype=np.uint32)
+        pads = [(0, 0), (1, 1), (1, 1)] * 2
+        self.polys = []
+        for j in range(self.P):
+            src = ctx.synth(seed + j, n, first_index=rank * n)
+            self.polys.append(ctx.vecvec_gather(src, idx, lens, to_limb1(pads[j][0]), to_limb1(pads[j][1]), row_log, col_local_log))
+            src.free()
+        rng = np.random.default_rng(seed)
+        from .fieldutil import R_MOD
+        nv = self.row_log + self.col_log
+        self.num_vars = nv
+        self.point = to_limbs([int.from_bytes(rng.bytes(32), "little") % R_MOD for _ in range(nv)])
+        gamma = int.from_bytes(rng.bytes(16), "little")
+        self.gp = to_limbs([pow(gamma, i, R_MOD) for i in range(4)])
+        self.claim = to_limb1(12345)
+        self.elements = self.P * n  # table elements per GPU
+        self.last = None
+
+    def prove(self):
+        so = self.ctx.deg2_vecvec_shard_so(g.GATE_PRJ_L1, self.polys, self.gp, self.point, self.col_log, self.rank, self.world)
+        tr = g.Transcript(b"fgstglsp")
+        out = g.sumcheck_prove_sharded_vecvec(tr, so, self.exchange, self.num_vars, self.claim)
+        self.last = (out, tr.proof())
+        so.destroy()
+        return out
+
+
 def sharded_commit(srs_slice: "g.Srs", scalars_slice: "g.Table", exchange) -> np.ndarray:
     """KzgProvingKey::commit (src/commitments/kzg.rs:123-126) split by POINT RANGE over the ranks of one box (SURVEY 8e):
     every rank commits its own slice of the SRS / coefficient vector on its GPU, the G affine partial results (96 bytes
