@@ -30,6 +30,8 @@
 #include "so.hpp"
 #include "transcript.hpp"
 
+void gkr_big_mem_stats(uint64_t out[2], bool reset_peak);  // tables.cu
+
 namespace {
 
 using gkr::FrH;
@@ -64,7 +66,10 @@ struct Span {
     ~Span() {
         if (on) {
             if (sync) cudaStreamSynchronize(ctx->stream);
-            fprintf(stderr, "  [gkr_run_pippenger] %9.2f ms  %s\n", (gkr_now_ns() - t0) / 1e6, name);
+            uint64_t m[2];
+            gkr_big_mem_stats(m, true);  // table memory now / its peak since the previous span line
+            fprintf(stderr, "  [gkr_run_pippenger] %9.2f ms  %-44s  tables %7.2f GiB live, peak %7.2f GiB\n", (gkr_now_ns() - t0) / 1e6, name,
+                    m[0] / 1073741824.0, m[1] / 1073741824.0);
         }
     }
 };
@@ -147,10 +152,15 @@ typedef std::shared_ptr<U32H> U32;
 struct Claims {
     std::vector<FrH> point, evs;
 };
+struct Gate;
 struct Advice {
     int kind = 0;  // 0 empty, 1 VecVec polys, 2 dense tables  (SplitVecVecMapGKRAdvice, split_map_gkr.rs:65-71)
     std::vector<Vv> vv;
     std::vector<Tab> dense;
+    // kind 3: not stored -- recomputed as chain.back()(.. chain[0](*base)) when the prover reaches it (bintree_witness, memory plan
+    // of large instances: only the INPUT of every addition layer stays resident, its L1 / L2 images are two maps away)
+    std::shared_ptr<Advice> base;
+    std::vector<const Gate*> chain;
 };
 struct Gate {
     int gid;  // public gate id for single-gate objects (-1: stack only)
@@ -477,10 +487,38 @@ struct ZeroCheck : Layer {  // zero_check.rs:17-33
     }
 };
 
+Advice advice_map(Dev& d, const Advice& a, const Gate& gate);
 Claims simple_gkr_prove(Dev& d, Layers& layers, Claims claims, std::vector<Advice>& advices) {  // gkr.rs:45-50
     if (advices.size() != layers.size()) fail(d.ctx, "SimpleGKR: advice / layer count mismatch");
+    // recomputed advices (kind 3): the layers of one addition are visited L3, L2, L1 -- the L1 image computed on the way to the
+    // L2 image is kept for the next visit and dropped after it
+    const Advice* stash_base = nullptr;
+    Advice stash;
     for (size_t i = layers.size(); i-- > 0;) {
-        claims = layers[i]->prove(d, claims, advices.back());
+        if (advices.back().kind == 3) {
+            const Advice lazy = advices.back();
+            Advice cur;
+            size_t from = 0;
+            if (stash_base == lazy.base.get() && lazy.chain.size() == 1) {
+                cur = stash;
+                from = 1;
+            } else {
+                cur = *lazy.base;
+            }
+            stash_base = nullptr;
+            stash = Advice();
+            for (size_t k = from; k < lazy.chain.size(); k++) {
+                Span sp(d.ctx, "    bintree map (recomputed)");
+                cur = advice_map(d, cur, *lazy.chain[k]);
+                if (k == 0 && lazy.chain.size() > 1) {
+                    stash_base = lazy.base.get();
+                    stash = cur;
+                }
+            }
+            claims = layers[i]->prove(d, claims, cur);
+        } else {
+            claims = layers[i]->prove(d, claims, advices.back());
+        }
         advices.pop_back();
     }
     return claims;
@@ -514,17 +552,33 @@ Advice advice_map_split(Dev& d, const Advice& a, const Gate& gate, uint32_t laye
     }
     return out;
 }
-std::vector<Advice> bintree_witness(Dev& d, Advice advice, uint32_t row_logsize, uint32_t num_adds, bool do_bitcheck) {  // bintree_add.rs:173-202
+// recompute: keep only the input of every addition layer resident and leave its L1 / L2 images as recipes (Advice kind 3) that
+// simple_gkr_prove replays when it reaches them -- the reference keeps all three per layer (bintree_add.rs:149-170), which is
+// 70 % of the prover's memory; the images are the same tables either way, so the proof does not change.
+std::vector<Advice> bintree_witness(Dev& d, Advice advice, uint32_t row_logsize, uint32_t num_adds, bool do_bitcheck, bool recompute) {  // bintree_add.rs:173-202
     std::vector<Advice> advices;
     for (uint32_t add_idx = 0; add_idx < num_adds; add_idx++) {
+        const Gate& g1 = add_idx == 0 ? AFF_L1 : PRJ_L1;
+        const Gate& g2 = add_idx == 0 ? AFF_L2 : PRJ_L2;
+        std::shared_ptr<Advice> base;
         for (int step = 0; step < 3; step++) {
             const bool last = add_idx + 1 == num_adds;
             Advice nxt;
             Span sp(d.ctx, step == 0 ? "    bintree L1 map" : (step == 1 ? "    bintree L2 map" : "    bintree L3 map+split"));
-            if (step == 0) nxt = advice_map(d, advice, add_idx == 0 ? AFF_L1 : PRJ_L1);
-            else if (step == 1) nxt = advice_map(d, advice, add_idx == 0 ? AFF_L2 : PRJ_L2);
+            if (step == 0) nxt = advice_map(d, advice, g1);
+            else if (step == 1) nxt = advice_map(d, advice, g2);
             else if (!last) nxt = advice_map_split(d, advice, add_idx == 0 ? AFF_L3 : PRJ_L3, add_idx, row_logsize, 3);
-            advices.push_back(advice);
+            if (recompute && step == 0) base = std::make_shared<Advice>(advice);
+            if (recompute && step > 0) {
+                Advice lazy;
+                lazy.kind = 3;
+                lazy.base = base;
+                lazy.chain.push_back(&g1);
+                if (step == 2) lazy.chain.push_back(&g2);
+                advices.push_back(lazy);
+            } else {
+                advices.push_back(advice);
+            }
             if (add_idx == 0 && step == 0 && do_bitcheck) advices.push_back(Advice());
             if (!(step == 2 && last)) advice = nxt;
         }
@@ -589,12 +643,20 @@ Layers triangle_protocol(uint32_t num_vars, uint32_t hi) {  // triangle_add.rs:1
 
 struct PippengerEndingWG {  // pippenger_ending.rs:32-95 (the reference builds the bintree witness twice; once suffices)
     std::vector<Advice> bintree_advices, triangle_advices;
-    PippengerEndingWG(Dev& d, uint32_t multirow_vars, uint32_t bucket_vars, uint32_t horizontal_vars, const std::vector<Vv>& inputs) {
+    PippengerEndingWG(Dev& d, uint32_t multirow_vars, uint32_t bucket_vars, uint32_t horizontal_vars, const std::vector<Vv>& inputs, bool recompute) {
         Advice in;
         in.kind = 1;
         in.vv = inputs;
-        bintree_advices = bintree_witness(d, in, horizontal_vars, horizontal_vars, true);
-        Advice last = advice_map(d, bintree_advices.back(), horizontal_vars - 1 == 0 ? AFF_L3 : PRJ_L3);
+        Advice l2_last;  // input of the last L3 step (the last stored advice unless it is a recipe)
+        bintree_advices = bintree_witness(d, in, horizontal_vars, horizontal_vars, true, recompute);
+        if (bintree_advices.back().kind == 3) {
+            l2_last = *bintree_advices.back().base;
+            for (const Gate* g : bintree_advices.back().chain) l2_last = advice_map(d, l2_last, *g);
+        } else {
+            l2_last = bintree_advices.back();
+        }
+        Advice last = advice_map(d, l2_last, horizontal_vars - 1 == 0 ? AFF_L3 : PRJ_L3);
+        l2_last = Advice();
         std::vector<Tab> split_l1 = d.map_dense(ID(3), last.dense, 1, multirow_vars, 3);
         std::vector<Tab> split_l2 = d.map_dense(ID(6), split_l1, 1, multirow_vars, 3);
         triangle_advices = triangle_witness(d, split_l2, multirow_vars + bucket_vars - 2, multirow_vars);
@@ -1119,7 +1181,18 @@ extern "C" int gkr_run_pippenger(gkr_ctx* ctx, gkr_transcript* transcript, const
         std::vector<Vv> glue;  // GlueSplit::witness: split (x, y) as a bundle of 2 and the domain polynomial alone
         d.map_vecvec(ID(2), {st.image[0], st.image[1]}, 1, 2, &glue, nullptr);
         d.map_vecvec(ID(1), {st.image[2]}, 1, 1, &glue, nullptr);
-        PippengerEndingWG ending(d, yl, dl, xl, glue);
+        // memory plan: with more than ~35 % of the device memory in bintree witness (about 640 bytes per point-digit incidence when
+        // every layer keeps its L1 / L2 images, as the reference does) only the layer inputs stay resident (GKR_WITNESS_RECOMPUTE=0/1 forces)
+        bool recompute = false;
+        {
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            const double witness_bytes = 640.0 * (double)y_size * (double)((uint64_t)1 << xl);
+            recompute = witness_bytes > 0.35 * (double)total_b;
+            const char* v = getenv("GKR_WITNESS_RECOMPUTE");
+            if (v) recompute = v[0] == '1';
+        }
+        PippengerEndingWG ending(d, yl, dl, xl, glue, recompute);
         sp.reset(new Span(ctx, "output claims"));
         // claims on the output of the triangle (pippenger.rs:528-539)
         std::vector<Tab> dense_out = d.map_dense(repeated(PRJ_L3, (dl - 2) + 3), ending.last());

@@ -45,7 +45,22 @@ struct BigCache {
 };
 std::mutex g_big_mutex;
 std::map<cudaStream_t, BigCache> g_big;
+// bytes of large blocks handed out (live) and their high-water mark: the footprint of the tables of a proof without the
+// idle blocks the cache keeps for reuse (GKR_TRACE prints both per span, protocol.cu)
+uint64_t g_big_live = 0, g_big_peak = 0;
+inline void big_account(int64_t delta) {
+    g_big_live = (uint64_t)((int64_t)g_big_live + delta);
+    if (g_big_live > g_big_peak) g_big_peak = g_big_live;
+}
 }  // namespace
+
+// out[0] = live bytes in large blocks, out[1] = their peak since the last reset
+void gkr_big_mem_stats(uint64_t out[2], bool reset_peak) {
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    out[0] = g_big_live;
+    out[1] = g_big_peak;
+    if (reset_peak) g_big_peak = g_big_live;
+}
 
 cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
     if (n < GKR_BIG_BLOCK) return cudaMallocAsync(p, n, s);
@@ -55,6 +70,7 @@ cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
     if (it != c.free_blocks.end() && it->first <= 2 * n) {
         *p = it->second;
         c.live[*p] = it->first;
+        big_account((int64_t)it->first);
         c.free_blocks.erase(it);
         return cudaSuccess;
     }
@@ -65,7 +81,10 @@ cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
         (void)cudaGetLastError();
         e = cudaMallocAsync(p, n, s);
     }
-    if (e == cudaSuccess) c.live[*p] = n;
+    if (e == cudaSuccess) {
+        c.live[*p] = n;
+        big_account((int64_t)n);
+    }
     return e;
 }
 
@@ -78,6 +97,7 @@ cudaError_t gkr_free_async(void* p, cudaStream_t s) {
             auto it = ci->second.live.find(p);
             if (it != ci->second.live.end()) {
                 ci->second.free_blocks.emplace(it->second, p);
+                big_account(-(int64_t)it->second);
                 ci->second.live.erase(it);
                 return cudaSuccess;
             }

@@ -222,3 +222,73 @@ def test_pippenger_device_vs_cpp_oracle_live(ctx, d, x, nbits, clm):
     assert np.array_equal(ndense, want["dense_output"])
     assert np.array_equal(nevs, want["claim_evs"])
     assert np.array_equal(npair, want["pair"])
+
+
+@pytest.mark.parametrize("d,x,nbits,clm", [(6, 12, 128, 0), (5, 10, 64, 2), (8, 14, 253, 2)])
+def test_pippenger_witness_recompute_plan_same_proof(ctx, d, x, nbits, clm, monkeypatch):
+    """memory plan of large instances (protocol.cu, bintree_witness): only the input of every addition layer stays resident,
+    the L1 / L2 images are recomputed when the prover reaches the layer -- same tables, so the proof, the outputs and the
+    pairing pair are the golden ones of the independent CPU prover"""
+    monkeypatch.setenv("GKR_WITNESS_RECOMPUTE", "1")
+    rng = np.random.default_rng(1000 * d + x)
+    n = 1 << x
+    k0, step = 0x1234567 + x, 0x9E3779B97F4A7C15
+    pts = H.te_points_arithmetic_progression(k0, step, n)
+    points_xy = np.stack([to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])])
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, nbits // 8:] = 0
+    coefs_u64 = raw.view(np.uint64).reshape(n, 4)
+    cfg = DPP.pippenger_config(d, x, nbits, clm)
+    r = [int.from_bytes(rng.bytes(32), "little") % P for _ in range(cfg["y_logsize"])]
+    tau = int.from_bytes(rng.bytes(32), "little") % P
+    nv = x + clm
+    key = DPP.KnucklesKey(ctx, DPP.KzgKey.mock_setup(ctx, tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    tr = g.Transcript(b"fgstglsp")
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr, key.kzg.srs, key.kzg.g0, key.dev, points_xy, coefs_u64, d, x, nbits, clm, to_limbs(r))
+    gold = LARGE_GOLDEN[f"pippenger_d{d}_x{x}_n{nbits}_c{clm}"]
+    assert hashlib.sha256(tr.proof()).hexdigest() == gold["proof_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(ndense).tobytes()).hexdigest() == gold["dense_output_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(nevs).tobytes()).hexdigest() == gold["claim_evs_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(npair).tobytes()).hexdigest() == gold["pair_sha256"]
+
+
+@pytest.mark.skipif(not os.environ.get("GKR_TEST_LARGE_X"), reason="minutes of host-side input generation: set GKR_TEST_LARGE_X=<x_logsize> (profiles/ keeps the log)")
+def test_pippenger_config3_shape_largest_single_gpu(ctx):
+    """BASELINE config[3] shape (full-width 253-bit scalars, d = 8, commitment-log-multiplicity 2) at the largest x one B200 holds:
+    the oracle verifier accepts the device proof and recovers the true MSM (closed form over the arithmetic-progression points)"""
+    x, d, nbits, clm = int(os.environ["GKR_TEST_LARGE_X"]), 8, 253, 2
+    rng = np.random.default_rng(1000 * d + x)
+    cfg = DPP.pippenger_config(d, x, nbits, clm)
+    n = 1 << x
+    k0, step = 0x1234567 + x, 0x9E3779B97F4A7C15
+    pts = H.te_points_arithmetic_progression(k0, step, n)
+    points_xy = np.stack([to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])])
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, nbits // 8:] = 0
+    coefs_u64 = raw.view(np.uint64).reshape(n, 4)
+    r = [int.from_bytes(rng.bytes(32), "little") % P for _ in range(cfg["y_logsize"])]
+    tau = int.from_bytes(rng.bytes(32), "little") % P
+    nv = x + clm
+    key = DPP.KnucklesKey(ctx, DPP.KzgKey.mock_setup(ctx, tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    tr = g.Transcript(b"fgstglsp")
+    import time
+    t0 = time.perf_counter()
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr, key.kzg.srs, key.kzg.g0, key.dev, points_xy, coefs_u64, d, x, nbits, clm, to_limbs(r))
+    print(f"x = {x}: run_pippenger {time.perf_counter() - t0:.2f} s (first call), proof {len(tr.proof())} bytes")
+    proof = tr.proof()
+    okey = PP.KnucklesKey(PP.KzgKey(tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    dense_output = [from_limbs(t) for t in ndense]
+    words = coefs_u64.astype(object)
+    total = 0
+    for i in range(n):
+        c = int(words[i, 0]) | (int(words[i, 1]) << 64) | (int(words[i, 2]) << 128) | (int(words[i, 3]) << 192)
+        total += c * (k0 + i * step)
+    expected = CV.te_to_affine(H.te_mul(total % CV.TE_SUBGROUP_ORDER, CV.TE_GEN))
+    tv = ProofTranscript2.start_verifier(b"fgstglsp", proof)
+    got = PP.verify_pippenger(tv, cfg, dense_output, (list(r), from_limbs(nevs)), okey, expected)
+    assert tv.ctr == len(proof) and got == expected
+    okey.kzg.verify_pair((res_to_point(npair[0]), res_to_point(npair[1])))
+    bad = bytearray(proof)
+    bad[len(bad) // 2] ^= 1
+    with pytest.raises(AssertionError):
+        PP.verify_pippenger(ProofTranscript2.start_verifier(b"fgstglsp", bytes(bad)), cfg, dense_output, (list(r), from_limbs(nevs)), okey, expected)
