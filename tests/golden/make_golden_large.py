@@ -35,7 +35,8 @@ from oracle import pippenger_oracle as PO  # noqa: E402
 from oracle.pyref import curves as CV  # noqa: E402
 from oracle.pyref.field import P, fq_vec_to_mont_u64, fr_vec_to_mont_u64  # noqa: E402
 
-CONFIGS = [(6, 12, 128, 0), (5, 10, 64, 2), (8, 16, 128, 0), (10, 20, 128, 0), (8, 14, 253, 2)]  # last: the shape of BASELINE config[3]
+CONFIGS = [(6, 12, 128, 0), (5, 10, 64, 2), (8, 16, 128, 0), (10, 20, 128, 0), (8, 14, 253, 2),  # (8, 14, 253, 2): the shape of BASELINE config[3]
+           (8, 18, 253, 2), (10, 22, 128, 0)]  # the two largest: minutes of CPU time each, compared on the device under GKR_TEST_LARGE_GOLDEN=1
 STEP = 0x9E3779B97F4A7C15
 
 

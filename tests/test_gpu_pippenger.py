@@ -292,3 +292,37 @@ def test_pippenger_config3_shape_largest_single_gpu(ctx):
     bad[len(bad) // 2] ^= 1
     with pytest.raises(AssertionError):
         PP.verify_pippenger(ProofTranscript2.start_verifier(b"fgstglsp", bytes(bad)), cfg, dense_output, (list(r), from_limbs(nevs)), okey, expected)
+
+
+@pytest.mark.parametrize("d,x,nbits,clm", [(8, 18, 253, 2), (10, 22, 128, 0)])
+def test_pippenger_large_golden_digests(ctx, d, x, nbits, clm):
+    """byte parity beyond the BASELINE sizes: the config[3] shape at x = 18 (2^23 point-digit incidences, 253-bit scalars, clm 2)
+    and 2^22 points at 128 bit -- proof, output tables, claims and pairing pair of the device prover hash to the digests the
+    independent CPU prover minted (tests/golden/make_golden_large.py; minutes of CPU time each).  The 2^22-point case needs
+    ~45 s of host-side input generation and runs under GKR_TEST_LARGE_GOLDEN=1 only."""
+    name = f"pippenger_d{d}_x{x}_n{nbits}_c{clm}"
+    if name not in LARGE_GOLDEN:
+        pytest.skip("digest not minted")
+    if x >= 20 and not os.environ.get("GKR_TEST_LARGE_GOLDEN"):
+        pytest.skip("set GKR_TEST_LARGE_GOLDEN=1")
+    rng = np.random.default_rng(1000 * d + x)
+    n = 1 << x
+    k0, step = 0x1234567 + x, 0x9E3779B97F4A7C15
+    pts = H.te_points_arithmetic_progression(k0, step, n)
+    points_xy = np.stack([to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])])
+    raw = np.frombuffer(rng.bytes(32 * n), dtype=np.uint8).reshape(n, 32).copy()
+    raw[:, nbits // 8:] = 0
+    coefs_u64 = raw.view(np.uint64).reshape(n, 4)
+    cfg = DPP.pippenger_config(d, x, nbits, clm)
+    r = [int.from_bytes(rng.bytes(32), "little") % P for _ in range(cfg["y_logsize"])]
+    tau = int.from_bytes(rng.bytes(32), "little") % P
+    nv = x + clm
+    key = DPP.KnucklesKey(ctx, DPP.KzgKey.mock_setup(ctx, tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    tr = g.Transcript(b"fgstglsp")
+    ndense, nevs, npair = g.run_pippenger_native(ctx, tr, key.kzg.srs, key.kzg.g0, key.dev, points_xy, coefs_u64, d, x, nbits, clm, to_limbs(r))
+    gold = LARGE_GOLDEN[name]
+    assert len(tr.proof()) == gold["proof_len"]
+    assert hashlib.sha256(tr.proof()).hexdigest() == gold["proof_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(ndense).tobytes()).hexdigest() == gold["dense_output_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(nevs).tobytes()).hexdigest() == gold["claim_evs_sha256"]
+    assert hashlib.sha256(np.ascontiguousarray(npair).tobytes()).hexdigest() == gold["pair_sha256"]
