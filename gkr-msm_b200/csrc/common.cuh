@@ -96,7 +96,7 @@ struct gkr_ctx {
     // large dense rounds (GKR_DENSE_FLAVOR): 2 (default) cp.async-staged kernel for fused rounds of <= 4 tables, register kernel otherwise;
     // 0 register kernel only; 1 node-split kernel (dense_split_kernel.cuh, measured slower: kept for the lab)
     int dense_flavor = 2;
-    // MSM window recoding (GKR_MSM_SIGNED): 1 = signed digits (half the buckets per window), 0 = unsigned (A/B experiments)
+    // MSM window recoding (GKR_MSM_SIGNED): 1 = signed digits from 2^15 points (half the buckets per window), 2 = always, 0 = unsigned
     int msm_signed = 1;
     int msm_light_minb = 3;  // GKR_MSM_LIGHT_MINB: register cap of the one-thread-per-bucket accumulation kernel (blocks per SM)
     uint64_t dense_staged_min = (uint64_t)1 << 13;  // items (quads) from which the staged kernel is used (GKR_DENSE_STAGED_MIN)

@@ -670,13 +670,16 @@ extern "C" void gkr_srs_free(gkr_srs* s) {
 
 // window width: minimise W * (n + 3 * 2^c) bucket additions (accumulate + running-sum reduce) over c, and avoid a
 // degenerate top window (255 - (W - 1) c < 7 bits would put n / 2^bits points into each of a handful of buckets)
-// Signed digits (msm_recode) halve the buckets of a window at the same number of additions; they are used from c = 8 up
-// (smaller MSMs are a handful of points) and need the windows to cover 256 bits (the last carry).
+// Signed digits (msm_recode) halve the buckets of a window at the same number of additions; they need c >= 8 and the windows
+// to cover 256 bits (the last carry).
 struct MsmWindow {
     int c, cb, W;  // window bits, bucket bits (c - 1 when signed), windows
     bool is_signed() const { return cb != c; }
 };
-static MsmWindow pick_window(uint64_t n, bool allow_signed) {
+// mode (gkr_ctx::msm_signed): 0 never, 1 from 2^15 points (below that an MSM is bound by the latency of its passes and the
+// signed recoding measured slower: the batched 2^10-point commitments of second_phase 7.9 -> 13 ms), 2 whenever c >= 8 (tests)
+static MsmWindow pick_window(uint64_t n, int mode) {
+    const bool allow_signed = mode >= 2 || (mode == 1 && n >= ((uint64_t)1 << 15));
     int lg = 0;
     while (((uint64_t)1 << lg) < n) lg++;
     MsmWindow best = {4, 4, 64};
@@ -729,8 +732,8 @@ static int msm_accumulate(gkr_ctx* ctx, const void* bases, int kind, const uint3
 #define GKR_MSM_ACC(K)                                                   \
     msm_accumulate_huge_kernel<K><<<gh, 256, sh_huge, st>>>(A);          \
     msm_accumulate_medium_kernel<K><<<gm, 128, sh_med, st>>>(A);         \
-    if (ctx->msm_light_minb >= 3) msm_accumulate_light_kernel<K, 3><<<gl, 128, 0, st>>>(A);   \
-    else msm_accumulate_light_kernel<K, 2><<<gl, 128, 0, st>>>(A);
+    if (K == 0 && ctx->msm_light_minb >= 3) msm_accumulate_light_kernel<K, 3><<<gl, 128, 0, st>>>(A);   \
+    else msm_accumulate_light_kernel<K, 2><<<gl, 128, 0, st>>>(A);  /* projective bases need 222 registers: no cap */
     if (kind == 2) { GKR_MSM_ACC(2) } else if (kind == 1) { GKR_MSM_ACC(1) } else { GKR_MSM_ACC(0) }
 #undef GKR_MSM_ACC
     ctx->launches += 6;
@@ -922,7 +925,7 @@ static int msm_g1_impl(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first, uint64_
         std::memset(out_xy, 0, 96 * (size_t)n_problems);
         return GKR_OK;
     }
-    const MsmWindow mw = pick_window(n, ctx->msm_signed != 0);
+    const MsmWindow mw = pick_window(n, ctx->msm_signed);
     const int c = mw.c, cb = mw.cb, W = mw.W;
     const size_t nbk = (size_t)W << cb;
     uint32_t *digits = nullptr, *sorted = nullptr, *counts = nullptr, *offsets = nullptr, *cursor = nullptr, *work = nullptr;
@@ -1001,7 +1004,7 @@ extern "C" int gkr_msm_g1_multi(gkr_ctx* ctx, const gkr_srs* srs, uint64_t first
     }
     GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    const MsmWindow mw = pick_window(n_max, ctx->msm_signed != 0);
+    const MsmWindow mw = pick_window(n_max, ctx->msm_signed);
     const int c = mw.c, cb = mw.cb, W = mw.W;
     const uint32_t KW = k * (uint32_t)W;
     const size_t nbk = (size_t)KW << cb;

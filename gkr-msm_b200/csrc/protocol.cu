@@ -1185,12 +1185,15 @@ extern "C" int gkr_run_pippenger(gkr_ctx* ctx, gkr_transcript* transcript, const
         // every layer keeps its L1 / L2 images, as the reference does) only the layer inputs stay resident (GKR_WITNESS_RECOMPUTE=0/1 forces)
         bool recompute = false;
         {
-            size_t free_b = 0, total_b = 0;
-            cudaMemGetInfo(&free_b, &total_b);
             const double witness_bytes = 640.0 * (double)y_size * (double)((uint64_t)1 << xl);
-            recompute = witness_bytes > 0.35 * (double)total_b;
             const char* v = getenv("GKR_WITNESS_RECOMPUTE");
-            if (v) recompute = v[0] == '1';
+            if (v) {
+                recompute = v[0] == '1';
+            } else if (witness_bytes > 16e9) {  // cudaMemGetInfo costs milliseconds: only asked when the answer can be yes
+                size_t free_b = 0, total_b = 0;
+                cudaMemGetInfo(&free_b, &total_b);
+                recompute = witness_bytes > 0.35 * (double)total_b;
+            }
         }
         PippengerEndingWG ending(d, yl, dl, xl, glue, recompute);
         sp.reset(new Span(ctx, "output claims"));

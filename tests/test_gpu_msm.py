@@ -208,9 +208,10 @@ def test_msm_multi_equals_single_calls(ctx):
     assert np.array_equal(out, want)
 
 
-@pytest.fixture(params=[1, 0], ids=["signed", "unsigned"])
+@pytest.fixture(params=[2, 0], ids=["signed", "unsigned"])
 def recoding(ctx, request):
-    """both window recodings of the bucket MSM (msm_recode, msm.cu): signed digits (the default) and unsigned"""
+    """both window recodings of the bucket MSM (msm_recode, msm.cu): signed digits (forced: the default uses them from 2^15
+    points) and unsigned"""
     ctx.set_tuning("msm_signed", request.param)
     yield request.param
     ctx.set_tuning("msm_signed", 1)
