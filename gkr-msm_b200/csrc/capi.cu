@@ -143,6 +143,12 @@ extern "C" int gkr_transcript_proof(const gkr_transcript* t, uint8_t* out) {
 }
 
 // GenericSumcheckProtocol::prove  (src/cleanup/protocols/sumcheck.rs:101-123)
+extern "C" int gkr_so_set_prelaunch(gkr_so* so, int on) {
+    if (!so) return GKR_ERR_ARG;
+    so->set_prelaunch(on != 0);
+    return GKR_OK;
+}
+
 // GKR_TRACE: where the host time of the round loop goes (printed by gkr_sumcheck_prove_stats_dump)
 static std::atomic<uint64_t> g_sc_ns[4];  // unipoly (launch-to-result wait included), interpolation + transcript, bind, final_evals
 static std::atomic<uint64_t> g_sc_rounds{0};
@@ -161,6 +167,12 @@ extern "C" int gkr_sumcheck_prove(gkr_transcript* t, gkr_so* so, uint32_t num_ro
     gkr::FrH claim = so->claim();
     std::vector<gkr::FrH> r;
     r.reserve(num_rounds);
+    // this loop is the strict unipoly -> bind alternation with nothing else on the stream: the object may pre-launch its small rounds
+    struct Prelaunch {
+        gkr_so* so;
+        explicit Prelaunch(gkr_so* s) : so(s) { so->set_prelaunch(true); }
+        ~Prelaunch() { so->set_prelaunch(false); }
+    } prelaunch_guard(so);
     uint64_t t0 = trace ? gkr_now_ns() : 0;
     for (uint32_t k = 0; k < num_rounds; k++) {
         gkr::FrH ev[GKR_MAX_DEG + 1];

@@ -39,6 +39,29 @@ struct RoundOut {  // kernel-side view of a slot
     uint32_t seq;
 };
 
+// Challenge mailbox of one sumcheck object, in pinned host memory mapped into the device address space (one per result slot).
+// The round kernel of round k + 1 is ENQUEUED while round k still runs -- before its challenge exists -- and waits for the host,
+// which hashes round k's message and writes the challenge here: the launch latency leaves the critical path.  One 32-byte
+// sector {seq, cmd, t[0..4), 0, 0} that the device fetches with ONE 256-bit system-scope load per poll (a PCIe read is ~2 us:
+// everything must arrive in one); only thread 0 of block 0 polls the host, the other blocks wait on a copy in device memory.
+// Host writes cmd / t first and seq last.  A launch that waits longer than GKR_MAILBOX_TIMEOUT_NS gives up without
+// publishing a result and says so in `timed_out` (the host relaunches the round the ordinary way): a pre-launched kernel can
+// never hang the device.  The challenge travels as the plain 128-bit integer of transcript.challenge(128).
+struct __attribute__((aligned(64))) GkrMailbox {
+    volatile uint32_t seq;        // host -> device, written last
+    volatile uint32_t cmd;        // 1: go, the challenge is in t; 2: cancelled
+    volatile uint32_t t[4];       // the 128-bit challenge as a plain integer
+    uint32_t pad_[2];
+    uint32_t pad2_[7];
+    volatile uint32_t timed_out;  // device -> host: seq of a launch that gave up
+};
+#define GKR_MAILBOX_TIMEOUT_NS 2000000000ull
+struct MailboxRef {  // kernel-side view; box == nullptr: the challenge travels in the kernel arguments
+    GkrMailbox* box = nullptr;
+    uint32_t* bcast = nullptr;  // device memory, 8 words per slot: {seq, cmd, t[0..4)} re-published by the polling thread
+    uint32_t seq = 0;
+};
+
 struct Deg2Layout;  // deg2.cu: row layout of the most recent ragged sumcheck bundle
 struct gkr_msm_team;  // msm_team.cu: commitment MSMs split by point range over the GPUs of one box
 
@@ -61,6 +84,26 @@ struct gkr_ctx {
     GkrSlot* slots_dev = nullptr;
     unsigned int* slot_tickets = nullptr;  // [GKR_RESULT_SLOTS] device
     uint32_t slot_seq[GKR_RESULT_SLOTS] = {0};
+    GkrMailbox* mbox_host = nullptr;  // [GKR_RESULT_SLOTS] pinned + mapped challenge mailboxes (pre-launched rounds)
+    GkrMailbox* mbox_dev = nullptr;
+    uint32_t* mbox_bcast = nullptr;   // [GKR_RESULT_SLOTS][8] device memory
+    uint32_t mbox_seq[GKR_RESULT_SLOTS] = {0};
+    bool prelaunch = true;            // GKR_PRELAUNCH=0: never enqueue a round before its challenge is known
+    MailboxRef next_mailbox(int slot) {
+        MailboxRef m;
+        m.box = mbox_dev + slot;
+        m.bcast = mbox_bcast + 8 * slot;
+        m.seq = ++mbox_seq[slot];
+        return m;
+    }
+    // host side of the mailbox: cmd 1 releases the pre-launched kernel with the challenge words, cmd 2 cancels it
+    void post_mailbox(int slot, uint32_t seq, uint32_t cmd, const uint32_t* t4) {
+        GkrMailbox* m = mbox_host + slot;
+        for (int k = 0; k < 4; k++) m->t[k] = t4 ? t4[k] : 0u;
+        m->cmd = cmd;
+        __atomic_store_n((uint32_t*)&m->seq, seq, __ATOMIC_RELEASE);
+    }
+    bool mailbox_timed_out(int slot, uint32_t seq) const { return mbox_host[slot].timed_out == seq; }
     RoundOut round_out(int slot) {  // next launch on this slot
         RoundOut o;
         o.part = slots_dev[slot].part;
@@ -149,7 +192,8 @@ struct GkrLaunchTimer {
     bool on;
     uint64_t t0;
     gkr_ctx::TimedLaunch t;
-    GkrLaunchTimer(gkr_ctx* c, int kernel_id, uint64_t n_items) : ctx(c), on(c->timing), t0(gkr_now_ns()) {
+    // events = false: host-side accounting only (a pre-launched kernel spins on its mailbox: its event time is not kernel time)
+    GkrLaunchTimer(gkr_ctx* c, int kernel_id, uint64_t n_items, bool events = true) : ctx(c), on(c->timing && events), t0(gkr_now_ns()) {
         if (!on) return;
         t.kernel_id = kernel_id;
         t.n_items = n_items;
@@ -226,9 +270,61 @@ int gkr_fetch_firsts(gkr_ctx* ctx, int slot, const GkrFirsts& f, gkr::FrH* out);
 int gkr_fetch_firsts_dev(gkr_ctx* ctx, int slot, const Fr* const* d_ptrs, int n, gkr::FrH* out);
 
 // host side: wait for the launch `seq` on `slot` and fold its per-block partials (n_acc accumulators per block)
-int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out);
+int gkr_slot_wait_seq(gkr_ctx* ctx, int slot, uint32_t seq, uint32_t n_blocks, int n_acc, gkr::FrH* out);
+static inline int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out) {  // the latest launch on the slot
+    return gkr_slot_wait_seq(ctx, slot, ctx->slot_seq[slot], n_blocks, n_acc, out);
+}
 
 #ifdef __CUDACC__
+// Device side of the mailbox.  Returns false when the launch is cancelled or gave up (all threads of the grid agree; nothing
+// may be published then).  t_out: the 4 challenge words, for every thread.
+__device__ __forceinline__ bool gkr_mailbox_wait(const MailboxRef& m, uint32_t* t_out) {
+    __shared__ uint32_t mb_sh[5];
+    if (threadIdx.x == 0) {
+        uint32_t w[8];
+        w[1] = 0;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {  // the one thread of the grid that talks to the host
+            unsigned long long t0, t1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            uint32_t polls = 0;
+            for (;;) {
+                asm volatile("ld.volatile.global.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                             : "l"(m.box)
+                             : "memory");
+                if (w[0] == m.seq) break;
+                if ((++polls & 15u) == 0) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                    if (t1 - t0 > GKR_MAILBOX_TIMEOUT_NS) {
+                        w[1] = 3;
+                        m.box->timed_out = m.seq;
+                        __threadfence_system();
+                        break;
+                    }
+                }
+            }
+            if (gridDim.x * gridDim.y > 1) {  // re-publish in device memory for the other blocks: payload, fence, seq
+#pragma unroll
+                for (int k = 1; k < 6; k++) ((volatile uint32_t*)m.bcast)[k] = w[k];
+                __threadfence();
+                ((volatile uint32_t*)m.bcast)[0] = m.seq;
+            }
+        } else {
+            while (((volatile uint32_t*)m.bcast)[0] != m.seq) {}
+            __threadfence();
+#pragma unroll
+            for (int k = 1; k < 6; k++) w[k] = ((volatile uint32_t*)m.bcast)[k];
+        }
+        mb_sh[4] = w[1];
+#pragma unroll
+        for (int k = 0; k < 4; k++) mb_sh[k] = w[2 + k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) t_out[k] = mb_sh[k];
+    return mb_sh[4] == 1;
+}
+
 // Sum `acc[0..N)` over all threads of the grid.  Field addition is associative and commutative and every
 // partial is canonical, so the result is bit-identical to the reference's sequential / rayon sum whatever
 // the order.  Block: shuffle tree inside each warp, one shared-memory hop, warp 0 finishes.  Grid: every

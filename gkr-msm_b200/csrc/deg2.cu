@@ -349,6 +349,7 @@ class Deg2SO : public gkr_so {
     std::vector<gkr_table*> dense_tables;
 
     ~Deg2SO() override {
+        if (pre_active) ctx->post_mailbox(slot, pre_mbox_seq, 2, nullptr);  // a spinning pre-launched kernel exits without publishing
         delete dense;
         for (auto* t : dense_tables) gkr_table_free(t);
         cudaStream_t s = ctx->stream;
@@ -360,20 +361,31 @@ class Deg2SO : public gkr_so {
     }
 
     uint32_t binding_idx() const { return n_vars - 1 - round_idx; }
-    uint32_t pending_blocks = 0;
+    uint32_t pending_blocks = 0, pending_seq = 0;
+    // pre-launched next round (set_prelaunch; common.cuh, GkrMailbox): enqueued while the current round runs, released by bind(t)
+    bool allow_prelaunch = false, pre_active = false;
+    uint32_t pre_mbox_seq = 0, pre_blocks = 0, pre_slot_seq = 0;
+    int pre_dst_set = 0;
+    void set_prelaunch(bool on) override {
+        allow_prelaunch = on;
+        if (dense) dense->set_prelaunch(on);
+    }
+    bool round_is_compact(uint32_t b) const { return (totals[b] / 2) * (uint64_t)n_blocks <= ctx->deg2_compact_max; }
 
-    // launches the round kernel for round `b` (= round_idx at call time); with fold_t != nullptr it first folds round b-1
-    int launch_round(uint32_t b, const gkr::FrH* fold_t) {
+    // launches the round kernel for round `b` (= round_idx at call time); with fold_t != nullptr it first folds round b-1.
+    // prelaunch: the fused kernel is enqueued BEFORE the challenge exists and takes it from the mailbox (fold_t is ignored).
+    int launch_round(uint32_t b, const gkr::FrH* fold_t, bool prelaunch = false) {
         const uint64_t n_pairs = totals[b] / 2;
         Deg2RoundArgs a;
         int dst_set = cur_set;
-        if (fold_t) {
+        if (fold_t || prelaunch) {
             dst_set = (cur_set == 1) ? 2 : 1;
             a.in = d_tabs[cur_set];
             a.out = (Fr* const*)d_tabs[dst_set];
             a.off_old = d_off + (size_t)(b - 1) * (nrows + 1);
             a.fold = 1;
-            a.t = fr_from_host(*fold_t);
+            a.t = fr_from_host(prelaunch ? gkr::frh::ZERO : *fold_t);
+            if (prelaunch) a.mbox = ctx->next_mailbox(slot);
         } else {
             a.in = d_tabs[cur_set];
             a.out = nullptr;
@@ -407,7 +419,6 @@ class Deg2SO : public gkr_so {
         dim3 grid((unsigned)(work_blocks + pad_blocks), (unsigned)n_blocks);
         unsigned threads = GKR_REDUCE_THREADS;
         if (grid.x == 1) threads = (unsigned)std::max<uint64_t>(32, std::min<uint64_t>(GKR_REDUCE_THREADS, (2 * n_pairs + 31) / 32 * 32));
-        pending_blocks = grid.x * grid.y;
         if (compact) {
             gkr_launch_deg2_round_compact(uniform_gate, a, grid, threads, ctx->stream);
         } else {
@@ -415,7 +426,17 @@ class Deg2SO : public gkr_so {
         }
         ctx->launches++;
         GKR_CUDA_OK(ctx, cudaGetLastError());
-        cur_set = dst_set;
+        if (prelaunch) {  // takes effect when bind() releases it
+            pre_active = true;
+            pre_mbox_seq = a.mbox.seq;
+            pre_slot_seq = a.o.seq;
+            pre_blocks = grid.x * grid.y;
+            pre_dst_set = dst_set;
+        } else {
+            pending_blocks = grid.x * grid.y;
+            pending_seq = a.o.seq;
+            cur_set = dst_set;
+        }
         return GKR_OK;
     }
 
@@ -429,11 +450,16 @@ class Deg2SO : public gkr_so {
             int rc = launch_round(round_idx, nullptr);
             if (rc) return rc;
         }
+        // the next fused round (small rounds only: the latency-bound ones) queues up behind the kernel we are about to wait for
+        if (allow_prelaunch && ctx->prelaunch && !pre_active && round_idx + 1 < n_sparse && round_is_compact(round_idx + 1)) {
+            int rc = launch_round(round_idx + 1, nullptr, true);
+            if (rc) return rc;
+        }
         gkr::FrH r[3];
         ctx->wait_kind = is_vecvec ? 2 : 1;
         ctx->wait_log = 0;
         while (((uint64_t)2 << ctx->wait_log) <= totals[round_idx]) ctx->wait_log++;
-        int rcw = gkr_slot_wait(ctx, slot, pending_blocks, 3, r);
+        int rcw = gkr_slot_wait_seq(ctx, slot, pending_seq, pending_blocks, 3, r);
         if (rcw) return rcw;
         sums_pending = false;
         gkr::FrH padterm = ZERO;
@@ -503,8 +529,23 @@ class Deg2SO : public gkr_so {
         gkr::FrH new_claim = interpolate_eval(evals, 4, t);
         gkr::FrH new_mult = mul(multiplier, eq1(point[b], t));
         if (is_vecvec && round_idx + 1 == n_sparse) return bind_into_dense(t, new_claim, new_mult);
-        int rc;
-        if (round_idx + 1 < n_sparse) {
+        int rc = GKR_OK;
+        if (pre_active) {
+            pre_active = false;
+            const gkr::FrH t_plain = mul(t, gkr::FrH{{1, 0, 0, 0}});
+            if (t_plain.v[2] == 0 && t_plain.v[3] == 0 && !ctx->mailbox_timed_out(slot, pre_mbox_seq)) {  // release the queued kernel
+                const uint32_t tw[4] = {(uint32_t)t_plain.v[0], (uint32_t)(t_plain.v[0] >> 32), (uint32_t)t_plain.v[1], (uint32_t)(t_plain.v[1] >> 32)};
+                ctx->post_mailbox(slot, pre_mbox_seq, 1, tw);
+                pending_blocks = pre_blocks;
+                pending_seq = pre_slot_seq;
+                cur_set = pre_dst_set;
+                sums_pending = true;
+            } else {  // a full-width challenge, or the launch gave up (the host was held up for seconds): cancel, ordinary launch
+                ctx->post_mailbox(slot, pre_mbox_seq, 2, nullptr);
+                rc = launch_round(round_idx + 1, &t);
+                sums_pending = true;
+            }
+        } else if (round_idx + 1 < n_sparse) {
             rc = launch_round(round_idx + 1, &t);  // fused: fold round b, evaluate round b+1
             sums_pending = true;
         } else {
@@ -756,6 +797,7 @@ int Deg2SO::bind_into_dense(const gkr::FrH& t, const gkr::FrH& new_claim, const 
     rc = gkr_make_dense_so(ctx, GKR_SO_EQ_GAMMA, tail_gate, 0, consts.data(), (uint32_t)std::min<size_t>(consts.size(), GKR_MAX_GATE_CONSTS),
                            dense_tables.data(), (uint32_t)P + 1, col, new_claim, &dense);
     if (rc) return rc;
+    dense->set_prelaunch(allow_prelaunch);
     multiplier = new_mult;
     claim_ = new_claim;
     cached = false;
@@ -914,6 +956,7 @@ extern "C" int gkr_sumcheck_prove_sharded_vecvec(gkr_transcript* t, gkr_so* so, 
     if (!d || !d->is_vecvec || d->round_idx != 0 || d->dense) return ctx->fail(GKR_ERR_ARG, "expects a fresh VecVec Deg2 object");
     using namespace gkr::frh;
     const uint32_t world = ex ? (uint32_t)gkr_exchange_world(ex) : 1;
+    so->set_prelaunch(true);  // strict partial_sums -> bind alternation below; the dense driver switches it off at the end
     gkr::FrH claim = frh_from_limbs(global_claim);
     std::vector<gkr::FrH> r;
     std::vector<uint64_t> mine(8), all((size_t)8 * world);

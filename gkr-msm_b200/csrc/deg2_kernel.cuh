@@ -42,6 +42,7 @@ struct Deg2RoundArgs {
     uint32_t work_blocks_x;    // blocks per gate slice that evaluate pairs
     int one_pair_rows;         // every row of this round holds exactly one pair: row == pair index, no search
     RoundOut o;                // 3 accumulators: S1, S2, T
+    MailboxRef mbox;           // pre-launched fused round: the challenge (plain 128-bit integer) comes through the mailbox
 };
 
 // Two lanes per pair.  Lane role r = lane & 1 owns element 2 idx + r of the (new) row: it folds (or loads) that element of
@@ -52,8 +53,8 @@ struct Deg2RoundArgs {
 namespace GKR_DEG2_NS {
 
 template <int G>
-__device__ __forceinline__ Fr deg2_block_round(const Deg2RoundArgs& A, const Deg2Block& blk, bool active, uint64_t q, uint32_t role, uint32_t row,
-                                               uint64_t idx, const Fr& w) {
+__device__ __forceinline__ Fr deg2_block_round(const Deg2RoundArgs& A, const Fr& t_fold, const Deg2Block& blk, bool active, uint64_t q, uint32_t role,
+                                               uint32_t row, uint64_t idx, const Fr& w) {
     constexpr int NI = MoGate<G>::N_INS, NO = MoGate<G>::N_OUTS;
     Fr a[NI];
     uint64_t old_base = 0, half_old = 0;
@@ -75,7 +76,7 @@ __device__ __forceinline__ Fr deg2_block_round(const Deg2RoundArgs& A, const Deg
                 if (i_self < half_old) {
                     const Fr* src = A.in[tj] + old_base + 2 * i_self;
                     Fr e0 = src[0], e1 = src[1];
-                    self = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
+                    self = fr_add(e0, fr_mul(t_fold, fr_sub(e1, e0)));
                 } else {
                     self = A.row_pads[tj];  // odd half re-padded with row_pad (vecvec.rs:432-436)
                 }
@@ -112,6 +113,18 @@ template <int GSEL>
 __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __grid_constant__ Deg2RoundArgs A) {
     __shared__ Fr smem[3 * (GKR_REDUCE_THREADS / 32)];
     Fr mine = fr_zero();
+    Fr t_fold = A.t;
+    if (A.mbox.box) {  // pre-launched: wait for the challenge (a cancelled launch publishes nothing)
+        uint32_t tw[4];
+        if (!gkr_mailbox_wait(A.mbox, tw)) return;
+        // the plain 128-bit integer -> Montgomery form: one product with R^2 mod r
+        Fr tp = fr_zero(), r2;
+#pragma unroll
+        for (int k = 0; k < 4; k++) tp.l[k] = tw[k];
+        r2.l[0] = 0xf3f29c6du; r2.l[1] = 0xc999e990u; r2.l[2] = 0x87925c23u; r2.l[3] = 0x2b6cedcbu;
+        r2.l[4] = 0x7254398fu; r2.l[5] = 0x05d31496u; r2.l[6] = 0x9f59ff11u; r2.l[7] = 0x0748d9d9u;
+        t_fold = fr_mul(tp, r2);
+    }
     const Deg2Block blk = A.blocks[blockIdx.y];
 #ifdef GKR_COMPACT_FIELD
     // latency flavour: the tail of the grid (blockIdx.x >= work_blocks_x) only computes T, overlapping the gate evaluations
@@ -148,18 +161,18 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) deg2_round_kernel(const __
         }
         Fr v = fr_zero();
         if constexpr (GSEL >= 0) {
-            v = deg2_block_round<GSEL>(A, blk, active, q, role, row, idx, w);
+            v = deg2_block_round<GSEL>(A, t_fold, blk, active, q, role, row, idx, w);
         } else
         switch (blk.gate) {
-            case GATE_AFF_L1: v = deg2_block_round<GATE_AFF_L1>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_AFF_L2: v = deg2_block_round<GATE_AFF_L2>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_AFF_L3: v = deg2_block_round<GATE_AFF_L3>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_PRJ_L1: v = deg2_block_round<GATE_PRJ_L1>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_PRJ_L2: v = deg2_block_round<GATE_PRJ_L2>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_PRJ_L3: v = deg2_block_round<GATE_PRJ_L3>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_BITCHECK: v = deg2_block_round<GATE_BITCHECK>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_LOGUP_LAYER: v = deg2_block_round<GATE_LOGUP_LAYER>(A, blk, active, q, role, row, idx, w); break;
-            case GATE_ADD_INVERSES: v = deg2_block_round<GATE_ADD_INVERSES>(A, blk, active, q, role, row, idx, w); break;
+            case GATE_AFF_L1: v = deg2_block_round<GATE_AFF_L1>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_AFF_L2: v = deg2_block_round<GATE_AFF_L2>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_AFF_L3: v = deg2_block_round<GATE_AFF_L3>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_PRJ_L1: v = deg2_block_round<GATE_PRJ_L1>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_PRJ_L2: v = deg2_block_round<GATE_PRJ_L2>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_PRJ_L3: v = deg2_block_round<GATE_PRJ_L3>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_BITCHECK: v = deg2_block_round<GATE_BITCHECK>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_LOGUP_LAYER: v = deg2_block_round<GATE_LOGUP_LAYER>(A, t_fold, blk, active, q, role, row, idx, w); break;
+            case GATE_ADD_INVERSES: v = deg2_block_round<GATE_ADD_INVERSES>(A, t_fold, blk, active, q, role, row, idx, w); break;
             default: break;
         }
         mine = fr_add(mine, v);  // inactive lanes carry w == 0

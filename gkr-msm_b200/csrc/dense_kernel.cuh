@@ -11,6 +11,7 @@ struct DenseRoundArgs {
     uint32_t t128[4];  // challenge as a plain 128-bit integer (FAST fold)
     GateConsts consts;
     RoundOut o;
+    MailboxRef mbox;   // pre-launched small round (dense_small_kernel, FAST fold): t128 comes through the mailbox
 };
 
 // MODE 0: evaluate pairs (2i, 2i+1) of `in`                      (first round: nothing to fold yet)
@@ -155,6 +156,11 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_small_kernel(const _
     __shared__ Fr sv[2 * P][QB];  // [2 * table + half][item]
     Fr mine = fr_zero();
     const uint32_t node = threadIdx.x >> 5, quad = threadIdx.x & 31;
+    // pre-launched round: the challenge of the fold arrives through the mailbox (a cancelled launch publishes nothing)
+    uint32_t t128[4] = {A.t128[0], A.t128[1], A.t128[2], A.t128[3]};
+    if (MODE == 1 && FAST && A.mbox.box) {
+        if (!gkr_mailbox_wait(A.mbox, t128)) return;
+    }
     for (uint64_t base = (uint64_t)blockIdx.x * QB; base < A.n_items; base += (uint64_t)gridDim.x * QB) {
         for (uint32_t task = threadIdx.x; task < 2 * P * QB; task += GKR_REDUCE_THREADS) {
             const uint32_t k = task / QB, j = k >> 1, half = k & 1;
@@ -164,7 +170,7 @@ __global__ void __launch_bounds__(GKR_REDUCE_THREADS) dense_small_kernel(const _
                 if (MODE == 1) {
                     const Fr* src = A.in[j] + 4 * i + 2 * half;
                     const Fr e0 = src[0], e1 = src[1];
-                    if (FAST) v = fr_fold128(e0, fr_sub(e1, e0), A.t128);
+                    if (FAST) v = fr_fold128(e0, fr_sub(e1, e0), t128);
                     else v = fr_add(e0, fr_mul(A.t, fr_sub(e1, e0)));
                     A.out[j][2 * i + half] = v;
                 } else {

@@ -74,7 +74,7 @@ static int launch_dense_round(gkr_ctx* ctx, const DenseRoundArgs& args, uint32_t
             unsigned grid = (unsigned)std::max<uint64_t>(1, (args.n_items + GKR_DENSE_SMALL_QB - 1) / GKR_DENSE_SMALL_QB);
             *n_blocks_out = grid;
             {
-                GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : GKR_K_DENSE_FOLD_EVAL, args.n_items);
+                GkrLaunchTimer timer(ctx, MODE == 0 ? GKR_K_DENSE_EVAL : GKR_K_DENSE_FOLD_EVAL, args.n_items, args.mbox.box == nullptr);
                 dense_small_kernel<SO, MODE, FAST><<<grid, GKR_REDUCE_THREADS, 0, ctx->stream>>>(args);
             }
             ctx->launches++;
@@ -195,11 +195,17 @@ class DenseSO : public gkr_so {
     int next_buf = 0;
     bool sums_pending = false;  // a launched kernel will deliver the sums of the current round
     uint32_t pending_blocks = 0;
+    uint32_t pending_seq = 0;   // result-slot sequence number of that kernel
+    // pre-launched next round (set_prelaunch): enqueued by unipoly() of round k before the challenge exists, released by bind(t_k)
+    bool allow_prelaunch = false, pre_active = false;
+    uint32_t pre_mbox_seq = 0, pre_blocks = 0, pre_slot_seq = 0;
+    void set_prelaunch(bool on) override { allow_prelaunch = on; }
     bool cached = false;
     gkr::FrH evals[GKR_MAX_DEG + 1];
     int slot = -1;
 
     ~DenseSO() override {
+        if (pre_active) ctx->post_mailbox(slot, pre_mbox_seq, 2, nullptr);  // a spinning pre-launched kernel exits without publishing
         if (slab) gkr_free_async(slab, ctx->stream);
         if (slot >= 0) gkr_result_slot_release(ctx, slot);
     }
@@ -210,15 +216,59 @@ class DenseSO : public gkr_so {
     }
 
     // gate constants for tables scaled by sigma: gamma^i * sigma^gamma_shift(i)   (gates.cuh, gamma_eval_scaled)
-    void rescale_consts() {
+    void consts_for(const gkr::FrH& sg, GateConsts* out) const {
         for (int i = 0; i < GKR_MAX_GATE_CONSTS; i++) {
             gkr::FrH g = base_consts[i];
             if (i < info.N_OUTS && info.gamma_shift[i] > 0) {
                 if (i == 0) g = gkr::frh::ONE;  // output 0 has coefficient one in the reference (sumcheck.rs:724-731)
-                for (int k = 0; k < info.gamma_shift[i]; k++) g = gkr::frh::mul(g, sigma);
+                for (int k = 0; k < info.gamma_shift[i]; k++) g = gkr::frh::mul(g, sg);
             }
-            consts.g[i] = fr_from_host(g);
+            out->g[i] = fr_from_host(g);
         }
+    }
+    void rescale_consts() { consts_for(sigma, &consts); }
+
+    int ensure_slab(uint64_t new_len) {
+        if (slab) return GKR_OK;
+        uint64_t per = new_len + (new_len >> 1);
+        GKR_CUDA_OK(ctx, gkr_malloc_async(&slab, sizeof(Fr) * per * P, ctx->stream));
+        for (int j = 0; j < P; j++) {
+            buf[0][j] = slab + (size_t)j * per;
+            buf[1][j] = slab + (size_t)j * per + new_len;
+        }
+        return GKR_OK;
+    }
+
+    // Enqueue the fused kernel of the NEXT round (fold by the challenge of this round, evaluate the round after) before that
+    // challenge exists: small rounds only (the block-cooperative kernel carries the mailbox prologue), 128-bit-challenge folds
+    // only (what transcript.challenge(128) produces; anything else cancels the launch in bind()).
+    int maybe_prelaunch() {
+        if (!allow_prelaunch || !ctx->prelaunch || pre_active || info.HDEG == 0 || ctx->no_fast_fold) return GKR_OK;
+        if (round_idx + 1 >= num_vars) return GKR_OK;
+        const uint64_t new_len = (uint64_t)1 << (num_vars - round_idx - 1);
+        if (new_len < 2 || (new_len >> 1) > ctx->dense_small_max) return GKR_OK;
+        int rc = ensure_slab(new_len);
+        if (rc) return rc;
+        DenseRoundArgs a;
+        for (int j = 0; j < P; j++) { a.in[j] = cur[j]; a.out[j] = buf[next_buf][j]; }
+        a.t = fr_from_host(gkr::frh::ZERO);
+        a.t128[0] = a.t128[1] = a.t128[2] = a.t128[3] = 0;
+        consts_for(gkr::frh::mul(sigma, inv128_m()), &a.consts);  // the tables after one more fast fold
+        a.o = ctx->round_out(slot);
+        a.mbox = ctx->next_mailbox(slot);
+        a.n_items = new_len >> 1;
+        uint32_t nb = 0;
+        rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
+            using SO = decltype(so);
+            if constexpr (SO::HDEG > 0) return launch_dense_round<SO, 1, true>(ctx, a, &nb);
+            return (int)GKR_ERR_UNSUPPORTED;
+        });
+        if (rc) return rc;
+        pre_active = true;
+        pre_mbox_seq = a.mbox.seq;
+        pre_slot_seq = a.o.seq;
+        pre_blocks = nb;
+        return GKR_OK;
     }
 
     int unipoly(gkr::FrH* out, uint32_t* n_evals) override {
@@ -233,10 +283,15 @@ class DenseSO : public gkr_so {
                     return launch_dense_round<decltype(so), 0>(ctx, a, &pending_blocks);
                 });
                 if (rc) return rc;
+                pending_seq = a.o.seq;
+            }
+            {
+                int rcp = maybe_prelaunch();  // the next round's kernel queues up behind the one we are about to wait for
+                if (rcp) return rcp;
             }
             ctx->wait_kind = 0;
             ctx->wait_log = (int)(num_vars - round_idx - 1);
-            int rcw = gkr_slot_wait(ctx, slot, pending_blocks, DEG, evals + 1);
+            int rcw = gkr_slot_wait_seq(ctx, slot, pending_seq, pending_blocks, DEG, evals + 1);
             if (rcw) return rcw;
             if (fast_folds)
                 for (int s = 1; s <= DEG; s++) evals[s] = gkr::frh::mul(evals[s], unscale_sum);
@@ -255,13 +310,9 @@ class DenseSO : public gkr_so {
         if (!frh_canonical(t)) return ctx->fail(GKR_ERR_ARG, "bind: challenge is not a canonical field element");
         const uint64_t cur_len = (uint64_t)1 << (num_vars - round_idx);
         const uint64_t new_len = cur_len >> 1;
-        if (!slab) {
-            uint64_t per = new_len + (new_len >> 1);
-            GKR_CUDA_OK(ctx, gkr_malloc_async(&slab, sizeof(Fr) * per * P, ctx->stream));
-            for (int j = 0; j < P; j++) {
-                buf[0][j] = slab + (size_t)j * per;
-                buf[1][j] = slab + (size_t)j * per + new_len;
-            }
+        {
+            int rcs = ensure_slab(new_len);
+            if (rcs) return rcs;
         }
         DenseRoundArgs a;
         for (int j = 0; j < P; j++) { a.in[j] = cur[j]; a.out[j] = buf[next_buf][j]; }
@@ -269,6 +320,17 @@ class DenseSO : public gkr_so {
         // transcript.challenge(128) is a 128-bit integer: fold with fr_fold128 when the gate is homogeneous
         const gkr::FrH t_plain = gkr::frh::mul(t, gkr::FrH{{1, 0, 0, 0}});
         const bool fast = info.HDEG > 0 && new_len >= 2 && t_plain.v[2] == 0 && t_plain.v[3] == 0 && !ctx->no_fast_fold;
+        bool released = false;
+        if (pre_active) {
+            pre_active = false;
+            if (fast && !ctx->mailbox_timed_out(slot, pre_mbox_seq)) {
+                const uint32_t tw[4] = {(uint32_t)t_plain.v[0], (uint32_t)(t_plain.v[0] >> 32), (uint32_t)t_plain.v[1], (uint32_t)(t_plain.v[1] >> 32)};
+                ctx->post_mailbox(slot, pre_mbox_seq, 1, tw);  // the kernel is already resident (or next in the stream): go
+                released = true;
+            } else {
+                ctx->post_mailbox(slot, pre_mbox_seq, 2, nullptr);  // full-width challenge (or the launch gave up): the ordinary launch below
+            }
+        }
         if (fast) {
             a.t128[0] = (uint32_t)t_plain.v[0]; a.t128[1] = (uint32_t)(t_plain.v[0] >> 32);
             a.t128[2] = (uint32_t)t_plain.v[1]; a.t128[3] = (uint32_t)(t_plain.v[1] >> 32);
@@ -278,8 +340,12 @@ class DenseSO : public gkr_so {
             for (int k = 0; k < info.HDEG; k++) unscale_sum = gkr::frh::mul(unscale_sum, pow128_m());
             rescale_consts();
         }
-        fill_common(a);
-        if (new_len >= 2) {
+        if (released) {
+            sums_pending = true;
+            pending_blocks = pre_blocks;
+            pending_seq = pre_slot_seq;
+        } else if (new_len >= 2) {
+            fill_common(a);
             a.n_items = new_len >> 1;
             int rc = dispatch_dense_so(ctx, so_kind, gate, gate_param, [&](auto so) {
                 using SO = decltype(so);
@@ -290,7 +356,9 @@ class DenseSO : public gkr_so {
             });
             if (rc) return rc;
             sums_pending = true;
+            pending_seq = a.o.seq;
         } else {
+            fill_common(a);
             a.n_items = new_len;
             dense_fold_kernel<<<1, 32, 0, ctx->stream>>>(a, P);
             ctx->launches++;

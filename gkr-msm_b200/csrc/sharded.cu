@@ -110,6 +110,11 @@ extern "C" int gkr_sumcheck_prove_sharded(gkr_transcript* t, gkr_so* so, gkr_exc
     const uint32_t deg = so->degree(), P = so->num_polys();
     gkr::FrH claim = frh_from_limbs(global_claim);
     std::vector<gkr::FrH> r;
+    so->set_prelaunch(true);  // strict partial_sums -> bind alternation below (so.hpp)
+    struct PrelaunchOff {
+        gkr_so* so;
+        ~PrelaunchOff() { so->set_prelaunch(false); }
+    } prelaunch_guard{so};
     auto round_io = [&](const gkr::FrH* sums_total) {  // sums at nodes 1..deg of the WHOLE hypercube
         gkr::FrH ev[GKR_MAX_DEG + 1];
         for (uint32_t s = 0; s < deg; s++) ev[s + 1] = sums_total[s];

@@ -22,6 +22,10 @@ struct gkr_so {
         *n = ne - 1;
         return GKR_OK;
     }
+    // The caller promises the strict unipoly() -> bind() alternation of GenericSumcheckProtocol::prove with NO other work on the
+    // context's stream in between (gkr_sumcheck_prove and the sharded drivers do): the object may then enqueue the kernel of the
+    // next small round while the current one runs and hand it the challenge through its mailbox (common.cuh, GkrMailbox).
+    virtual void set_prelaunch(bool) {}
     virtual gkr::FrH claim() const = 0;
     virtual uint32_t degree() const = 0;
     virtual uint32_t num_polys() const = 0;

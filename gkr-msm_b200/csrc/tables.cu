@@ -114,10 +114,9 @@ void gkr_big_cache_release(cudaStream_t s) {
     g_big.erase(ci);
 }
 
-int gkr_slot_wait(gkr_ctx* ctx, int slot, uint32_t n_blocks, int n_acc, gkr::FrH* out) {
+int gkr_slot_wait_seq(gkr_ctx* ctx, int slot, uint32_t seq, uint32_t n_blocks, int n_acc, gkr::FrH* out) {
     if (n_blocks > GKR_HOST_FOLD_MAX_BLOCKS) n_blocks = 1;  // large launches fold their partials on the device (grid_reduce_to_host)
     GkrSlot* s = &ctx->slots_host[slot];
-    const uint32_t seq = ctx->slot_seq[slot];
     uint64_t spins = 0;
     const uint64_t t0 = gkr_now_ns();
     while (s->flag != seq) {
@@ -220,6 +219,12 @@ extern "C" int gkr_ctx_create(int device, gkr_ctx** out) {
     if ((e = cudaHostAlloc(&ctx->slots_host, sizeof(GkrSlot) * GKR_RESULT_SLOTS, cudaHostAllocMapped)) != cudaSuccess) return bail(e);
     if ((e = cudaHostGetDevicePointer(&ctx->slots_dev, ctx->slots_host, 0)) != cudaSuccess) return bail(e);
     for (int i = 0; i < GKR_RESULT_SLOTS; i++) ctx->slots_host[i].flag = 0;
+    if ((e = cudaHostAlloc(&ctx->mbox_host, sizeof(GkrMailbox) * GKR_RESULT_SLOTS, cudaHostAllocMapped)) != cudaSuccess) return bail(e);
+    if ((e = cudaHostGetDevicePointer(&ctx->mbox_dev, ctx->mbox_host, 0)) != cudaSuccess) return bail(e);
+    std::memset((void*)ctx->mbox_host, 0, sizeof(GkrMailbox) * GKR_RESULT_SLOTS);
+    if ((e = cudaMalloc(&ctx->mbox_bcast, sizeof(uint32_t) * 8 * GKR_RESULT_SLOTS)) != cudaSuccess) return bail(e);
+    if ((e = cudaMemset(ctx->mbox_bcast, 0, sizeof(uint32_t) * 8 * GKR_RESULT_SLOTS)) != cudaSuccess) return bail(e);
+    { const char* v = getenv("GKR_PRELAUNCH"); if (v) ctx->prelaunch = v[0] != '0'; }
     if ((e = cudaMalloc(&ctx->slot_tickets, sizeof(unsigned int) * GKR_RESULT_SLOTS)) != cudaSuccess) return bail(e);
     if ((e = cudaMemset(ctx->slot_tickets, 0, sizeof(unsigned int) * GKR_RESULT_SLOTS)) != cudaSuccess) return bail(e);
     {
@@ -266,6 +271,8 @@ extern "C" void gkr_ctx_destroy(gkr_ctx* ctx) {
     if (ctx->ticket) cudaFree(ctx->ticket);
     if (ctx->result_host) cudaFreeHost(ctx->result_host);
     if (ctx->slots_host) cudaFreeHost(ctx->slots_host);
+    if (ctx->mbox_host) cudaFreeHost((void*)ctx->mbox_host);
+    if (ctx->mbox_bcast) cudaFree(ctx->mbox_bcast);
     if (ctx->slot_tickets) cudaFree(ctx->slot_tickets);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -526,6 +533,7 @@ extern "C" int gkr_ctx_set_tuning(gkr_ctx* ctx, const char* key, long long value
     if (k == "dense_small_max") ctx->dense_small_max = (uint64_t)value;
     else if (k == "deg2_compact_max") ctx->deg2_compact_max = (uint64_t)value;
     else if (k == "msm_signed") ctx->msm_signed = (int)value;
+    else if (k == "prelaunch") ctx->prelaunch = value != 0;
     else if (k == "msm_light_minb") ctx->msm_light_minb = (int)value;
     else return ctx->fail(GKR_ERR_ARG, "gkr_ctx_set_tuning: unknown key");
     return GKR_OK;
