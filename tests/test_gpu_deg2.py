@@ -75,6 +75,7 @@ def test_dense_deg2_rounds(ctx, parts, nv):
     assert from_limbs(dso.final_evals()) == oso.final_evals()
     # inputs untouched
     assert from_limbs(tabs[0].download()) == data[0]
+    dso.destroy()  # result slots are a bounded resource: do not wait for the collector
 
 
 def make_vecvec(rng, dens, rowv, colv, n_polys, pads):
@@ -122,6 +123,7 @@ def test_vecvec_deg2_rounds(ctx, dens, colv, gid):
         dso.bind(to_limb1(t))
         assert from_limbs(dso.claim.reshape(1, 4))[0] == oso.claim
     assert from_limbs(dso.final_evals()) == oso.final_evals()
+    dso.destroy()
 
 
 def test_vecvec_sumcheck_prover_verifier(ctx):
