@@ -51,6 +51,7 @@ extern "C" {
     pub fn gkr_so_claim(so: *const gkr_so, out: *mut u64) -> c_int;
     pub fn gkr_so_num_polys(so: *const gkr_so) -> u32;
     pub fn gkr_so_destroy(so: *mut gkr_so);
+    pub fn gkr_so_set_prelaunch(so: *mut gkr_so, on: c_int) -> c_int;
 
     pub fn gkr_vecvec_upload(ctx: *mut gkr_ctx, flat: *const u64, row_len: *const u32, n_rows: u32, row_pad: *const u64, col_pad: *const u64,
                              row_logsize: u32, col_logsize: u32, out: *mut *mut gkr_vecvec) -> c_int;

@@ -47,6 +47,15 @@ impl<F: PrimeField> GpuSo<F> {
         Self { ctx: ctx.clone(), raw, challenges: vec![], _tables: tables, _vecvecs: vecvecs, _pd: PhantomData }
     }
 
+    /// Latency of small rounds (`gkr_so_set_prelaunch`): only for an object that ONE loop drives alone as unipoly, transcript,
+    /// bind, ... with no other device work in between -- GenericSumcheckProtocol::prove (sumcheck.rs:101-123), which
+    /// `dispatch.rs` wraps.  NOT for the combined loop of pushforward.rs:781-806: there the first kernel of the second object
+    /// would queue up behind the pre-launched kernel of the first one and the device-side watchdog (2 s) would have to
+    /// break the wait.
+    pub fn set_prelaunch(&mut self, on: bool) {
+        unsafe { gkr_so_set_prelaunch(self.raw, on as i32) };
+    }
+
     /// DenseSumcheckObjectSO::new(polys, f, num_vars, claim_hint) with a single-output gate (PROD3; FOLDED_PROD with
     /// `gate_consts = make_gamma_pows(gamma, nargs)`)
     pub fn dense_plain(ctx: &Rc<GpuCtx>, gate: i32, gate_param: u32, gate_consts: &[F], polys: Vec<DeviceTable>, num_vars: usize, claim: F) -> Self {
