@@ -541,6 +541,7 @@ class Deg2SO : public gkr_so {
                 cur_set = pre_dst_set;
                 sums_pending = true;
             } else {  // a full-width challenge, or the launch gave up (the host was held up for seconds): cancel, ordinary launch
+                if (ctx->mailbox_timed_out(slot, pre_mbox_seq)) ctx->prelaunch = false;  // see DenseSO::bind
                 ctx->post_mailbox(slot, pre_mbox_seq, 2, nullptr);
                 rc = launch_round(round_idx + 1, &t);
                 sums_pending = true;

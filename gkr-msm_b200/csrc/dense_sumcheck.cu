@@ -328,6 +328,9 @@ class DenseSO : public gkr_so {
                 ctx->post_mailbox(slot, pre_mbox_seq, 1, tw);  // the kernel is already resident (or next in the stream): go
                 released = true;
             } else {
+                // a launch that gave up means something serialises launches behind our back (a profiler replaying kernels, a
+                // debugger): stop pre-launching on this context instead of paying the watchdog again
+                if (ctx->mailbox_timed_out(slot, pre_mbox_seq)) ctx->prelaunch = false;
                 ctx->post_mailbox(slot, pre_mbox_seq, 2, nullptr);  // full-width challenge (or the launch gave up): the ordinary launch below
             }
         }

@@ -141,7 +141,8 @@ uint32_t gkr_so_num_polys(const gkr_so* so);
 uint32_t gkr_so_round(const gkr_so* so);
 void gkr_so_destroy(gkr_so* so);
 /* Latency of small rounds.  on != 0 is the caller's promise that the object is driven like GenericSumcheckProtocol::prove
- * (sumcheck.rs:101-123): unipoly, bind, unipoly, bind ... with NO other work on the context between a unipoly and its bind.  The
+ * (sumcheck.rs:101-123): unipoly, bind, unipoly, bind ... with NO other work on the context -- no table operation and no round of
+ * ANOTHER sumcheck object, so not the two-object loop of pushforward.rs:781-806 -- between a unipoly and its bind.  The
  * object may then enqueue the kernel of the next small round while the current one runs and pass it the challenge through a
  * mailbox in mapped host memory, which takes the launch (~5 us of a 12-20 us round) off the critical path; a challenge that does
  * not fit the pre-launched kernel, a destroyed object or a host that stalls for seconds cancel the launch.  Results are the same

@@ -4,6 +4,10 @@
 # benchmark values.   usage: bash tools/profile_r02.sh
 OUT=gpurun_out
 mkdir -p $OUT
+# ncu runs every kernel to completion inside its launch call: a pre-launched round (common.cuh, GkrMailbox) would wait for a
+# challenge the blocked host cannot send until its watchdog fires.  The library notices and stops pre-launching after the first
+# such stall; switching it off up front avoids even that one.
+export GKR_PRELAUNCH=0
 NCU=/usr/local/cuda/bin/ncu
 M=gpu__time_duration.sum
 # 1. launch lists (kernel share of the step; -c bounds the capture)
