@@ -19,7 +19,8 @@ $NCU --metrics $M --clock-control none -c 8000 --csv --log-file $OUT/r02_launche
     python tools/bench_pippenger.py --x-logsize 20 --d-logsize 10 --reps 1 --precompute-c 0 > $OUT/r02_prof_x20.log 2>&1
 # 2. full capture of the two large dense kernels of the headline workload: round-0 eval (register kernel) and the first fused
 #    fold+eval round (cp.async-staged kernel); the first launches of each name are the 2^24-sized ones
-$NCU --set full --clock-control none --import-source on -k regex:dense_round_kernel -c 1 -f -o $OUT/r02_dense_eval \
+# (-s 1: the first launch of that name is the MODE-2 gate sum that computes the claim when the job is set up)
+$NCU --set full --clock-control none --import-source on -k regex:dense_round_kernel -s 1 -c 1 -f -o $OUT/r02_dense_eval \
     python bench.py --steps 1 --warmup 3 --no-pippenger --no-cpu-baseline --e2e-steps 1 > /dev/null 2>&1
 $NCU --set full --clock-control none --import-source on -k regex:dense_round_staged_kernel -c 1 -f -o $OUT/r02_dense_fused \
     python bench.py --steps 1 --warmup 3 --no-pippenger --no-cpu-baseline --e2e-steps 1 > /dev/null 2>&1
