@@ -173,6 +173,14 @@ class Context:
     def set_fast_fold(self, on: bool = True):
         self.check(self.lib.gkr_ctx_set_fast_fold(self.h, 1 if on else 0))
 
+    def peer_pool(self, n_devices: int = 0):
+        """gkr_ctx_peer_pool: lend this context the HBM of devices [0, n_devices); returns (bytes on peers now, their peak)"""
+        self.lib.gkr_ctx_peer_pool.restype = C.c_int
+        self.lib.gkr_ctx_peer_pool.argtypes = [_vp, C.c_int, _vp]
+        st = np.zeros(2, np.uint64)
+        self.check(self.lib.gkr_ctx_peer_pool(self.h, int(n_devices), _ptr(st)))
+        return int(st[0]), int(st[1])
+
     def set_tuning(self, key: str, value: int):
         """kernel-selection knob by name (gkr_ctx_set_tuning): every setting is bit-exact"""
         self.check(self.lib.gkr_ctx_set_tuning(self.h, key.encode(), int(value)))

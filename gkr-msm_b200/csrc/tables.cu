@@ -52,6 +52,57 @@ inline void big_account(int64_t delta) {
     g_big_live = (uint64_t)((int64_t)g_big_live + delta);
     if (g_big_live > g_big_peak) g_big_peak = g_big_live;
 }
+// Peer pool (gkr_ctx_peer_pool): when the home GPU is full, large blocks are placed in the HBM of the other GPUs of the box and
+// the kernels -- which all run on the home GPU -- reach them through NVLink peer access.  Nothing else changes: same kernels,
+// same pointers, same proof; tables that spill over run at NVLink instead of HBM speed.  This is what lets one prover hold
+// the ~430 GiB of BASELINE config[3] at x = 24; it is memory pooling, not compute scaling.
+struct PeerPool {
+    int home = -1;
+    std::vector<int> peers;
+    std::unordered_map<void*, int> owner;  // blocks that live on a peer
+    void* ballast = nullptr;               // 1 GiB held back on the home GPU for the small allocations of the stream-ordered pool
+    uint64_t remote_live = 0, remote_peak = 0;
+};
+PeerPool g_peer;  // guarded by g_big_mutex
+
+cudaError_t peer_malloc(void** p, size_t n) {
+    int best = -1;
+    size_t best_free = 0;
+    for (int d : g_peer.peers) {
+        size_t f = 0, t = 0;
+        if (cudaSetDevice(d) == cudaSuccess && cudaMemGetInfo(&f, &t) == cudaSuccess && f > best_free) {
+            best_free = f;
+            best = d;
+        }
+    }
+    cudaError_t e = cudaErrorMemoryAllocation;
+    if (best >= 0 && best_free > n + ((size_t)1 << 28)) {
+        cudaSetDevice(best);
+        e = cudaMalloc(p, n);
+        if (e == cudaSuccess) {
+            g_peer.owner[*p] = best;
+            g_peer.remote_live += n;
+            if (g_peer.remote_live > g_peer.remote_peak) g_peer.remote_peak = g_peer.remote_live;
+        }
+    }
+    cudaSetDevice(g_peer.home);
+    if (e != cudaSuccess) (void)cudaGetLastError();
+    return e;
+}
+// give a block back to whoever owns it: the stream-ordered pool of the home GPU, or the peer it was placed on
+void release_block(void* p, size_t n, cudaStream_t s) {
+    auto it = g_peer.owner.find(p);
+    if (it == g_peer.owner.end()) {
+        cudaFreeAsync(p, s);
+        return;
+    }
+    cudaStreamSynchronize(s);  // kernels of the home GPU may still be reading it
+    cudaSetDevice(it->second);
+    cudaFree(p);
+    cudaSetDevice(g_peer.home);
+    g_peer.remote_live -= n;
+    g_peer.owner.erase(it);
+}
 }  // namespace
 
 // out[0] = live bytes in large blocks, out[1] = their peak since the last reset
@@ -74,12 +125,25 @@ cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
         c.free_blocks.erase(it);
         return cudaSuccess;
     }
-    cudaError_t e = cudaMallocAsync(p, n, s);
-    if (e != cudaSuccess) {  // out of memory: give the cached blocks back and retry once
-        for (auto& kv : c.free_blocks) cudaFreeAsync(kv.second, s);
+    // test hook (GKR_PEER_POOL_LOCAL_LIMIT_MIB): pretend the home GPU is full beyond this many MiB of live tables, so that the
+    // peer placement is exercised by instances of any size
+    static const long long local_limit = getenv("GKR_PEER_POOL_LOCAL_LIMIT_MIB") ? atoll(getenv("GKR_PEER_POOL_LOCAL_LIMIT_MIB")) : -1;
+    cudaError_t e = cudaErrorMemoryAllocation;
+    const bool force_peer = local_limit >= 0 && !g_peer.peers.empty() && g_big_live - g_peer.remote_live + n > ((uint64_t)local_limit << 20);
+    if (!force_peer) e = cudaMallocAsync(p, n, s);
+    if (e != cudaSuccess && !force_peer) {  // out of memory: give the cached blocks back and retry once
+        for (auto& kv : c.free_blocks) release_block(kv.second, kv.first, s);
         c.free_blocks.clear();
         (void)cudaGetLastError();
         e = cudaMallocAsync(p, n, s);
+    }
+    if (e != cudaSuccess && !g_peer.peers.empty()) {  // the home GPU is full: place the block on a peer (NVLink peer access)
+        (void)cudaGetLastError();
+        if (g_peer.ballast) {  // first time: hand the reserve to the stream-ordered pool for the small allocations to come
+            cudaFree(g_peer.ballast);
+            g_peer.ballast = nullptr;
+        }
+        e = peer_malloc(p, n);
     }
     if (e == cudaSuccess) {
         c.live[*p] = n;
@@ -110,8 +174,41 @@ void gkr_big_cache_release(cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_big_mutex);
     auto ci = g_big.find(s);
     if (ci == g_big.end()) return;
-    for (auto& kv : ci->second.free_blocks) cudaFreeAsync(kv.second, s);
+    for (auto& kv : ci->second.free_blocks) release_block(kv.second, kv.first, s);
     g_big.erase(ci);
+}
+
+// Lend this context the memory of the other GPUs of the box: devices [0, n_devices) except its own become the peer pool.
+// out_stats (optional, 2 x u64): bytes currently placed on peers and their peak.  n_devices <= 1 only reads the statistics.
+extern "C" int gkr_ctx_peer_pool(gkr_ctx* ctx, int n_devices, uint64_t* out_stats) {
+    if (!ctx) return GKR_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g_big_mutex);
+    if (n_devices > 1 && g_peer.peers.empty()) {
+        int count = 0;
+        GKR_CUDA_OK(ctx, cudaGetDeviceCount(&count));
+        if (n_devices > count) return ctx->fail(GKR_ERR_ARG, "gkr_ctx_peer_pool: fewer devices than requested");
+        GKR_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+        for (int d = 0; d < n_devices; d++) {
+            if (d == ctx->device) continue;
+            int can = 0;
+            GKR_CUDA_OK(ctx, cudaDeviceCanAccessPeer(&can, ctx->device, d));
+            if (!can) return ctx->fail(GKR_ERR_UNSUPPORTED, "gkr_ctx_peer_pool: no peer access between the GPUs");
+            cudaError_t e = cudaDeviceEnablePeerAccess(d, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return ctx->fail(GKR_ERR_CUDA, cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            g_peer.peers.push_back(d);
+        }
+        g_peer.home = ctx->device;
+        if (cudaMalloc(&g_peer.ballast, (size_t)1 << 30) != cudaSuccess) {
+            g_peer.ballast = nullptr;
+            (void)cudaGetLastError();
+        }
+    }
+    if (out_stats) {
+        out_stats[0] = g_peer.remote_live;
+        out_stats[1] = g_peer.remote_peak;
+    }
+    return GKR_OK;
 }
 
 int gkr_slot_wait_seq(gkr_ctx* ctx, int slot, uint32_t seq, uint32_t n_blocks, int n_acc, gkr::FrH* out) {

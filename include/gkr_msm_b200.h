@@ -83,6 +83,12 @@ int gkr_ctx_set_tuning(gkr_ctx* ctx, const char* key, long long value);
 /* host-side latency accounting: out = {ns spent inside kernel-launch calls of the round kernels, ns spent waiting for
  * round results, number of waits, kernels launched}; reset != 0 clears the first three. */
 int gkr_ctx_host_stats(gkr_ctx* ctx, uint64_t out[4], int reset);
+/* Memory pooling over the GPUs of one box: devices [0, n_devices) other than the context's own lend their HBM -- when the home
+ * GPU is full, tables of >= 4 MiB are placed on the peer with the most free memory and the kernels (which all run on the home
+ * GPU) reach them through NVLink peer access.  Same kernels, same proofs; what spills over runs at NVLink speed.  This is how
+ * one prover holds instances beyond 180 GB (BASELINE config[3] at x = 23 / 24).  out_stats (may be NULL): {bytes on peers now,
+ * their peak}.  n_devices <= 1 only reads the statistics. */
+int gkr_ctx_peer_pool(gkr_ctx* ctx, int n_devices, uint64_t* out_stats);
 int gkr_ctx_timing_read(gkr_ctx* ctx, int* kernel_id, uint64_t* n_items, float* ms, int max_n);
 
 /* ---- dense tables: `Vec<Fr>` resident in HBM ---------------------------------------------------

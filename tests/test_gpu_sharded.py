@@ -304,3 +304,31 @@ def test_vecvec_sumcheck_sharded_by_rows_equals_single_gpu(ctx, world, colv, nro
         assert (proof, c, pt, fe) == want, f"rank {rk}"
         for j in range(len(full_l1)):
             assert rows[j] == full_l1[j][rk * per:(rk + 1) * per]
+
+
+def test_peer_pool_places_tables_on_other_gpus_same_proof(tmp_path):
+    """gkr_ctx_peer_pool: with the home GPU declared full beyond 64 MiB of tables (test hook), the prover places its tables on
+    GPU 1 and reaches them through NVLink peer access -- the proof, outputs and pairing pair are the ones of the ordinary run.
+    Needs two GPUs (gpurun --gpus 2); the single-GPU box of the regular suite skips it."""
+    import json
+    import subprocess
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    outs = []
+    for pool in (0, 2):
+        dump = str(tmp_path / f"p{pool}.npz")
+        env = dict(os.environ)
+        if pool:
+            env["GKR_PEER_POOL_LOCAL_LIMIT_MIB"] = "64"
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "bench_pippenger.py"), "--x-logsize", "14", "--d-logsize", "7", "--nbits", "128", "--reps", "1",
+               "--dump", dump] + (["--peer-pool", "2"] if pool else [])
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        outs.append((np.load(dump), json.loads(res.stdout.strip().splitlines()[-1])))
+    a, b = outs[0][0], outs[1][0]
+    for k in ("proof", "dense", "evs", "pair"):
+        assert np.array_equal(a[k], b[k]), k
+    assert outs[1][1]["peer_pool_peak_gib"] > 0.05, "nothing was placed on the peer"

@@ -26,6 +26,29 @@ def srs_tau(seed: int) -> int:
     return int.from_bytes(np.random.default_rng(seed ^ 0x7A5).bytes(32), "little") % R_MOD
 
 
+def _points_chunk(job):
+    """(k_start, step, count) -> Montgomery limbs of the x and y coordinates of (k_start + i step) G, i < count"""
+    from gkr_msm_b200 import hostmath as H
+    from gkr_msm_b200.fieldutil import to_limbs
+    k_start, step, count = job
+    pts = H.te_points_arithmetic_progression(k_start, step, count)
+    return to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])
+
+
+def gen_points(k0: int, step: int, n: int, procs: int):
+    """the synthetic points (k0 + i step) G as a (2, n, 4) limb array; `procs` > 1 splits the progression over worker processes
+    (pure-python big-integer arithmetic: 9 us per point and core)"""
+    if procs <= 1 or n < (1 << 14):
+        x, y = _points_chunk((k0, step, n))
+        return np.stack([x, y])
+    import multiprocessing as mp
+    chunk = max(1 << 12, n // (procs * 4))
+    jobs = [(k0 + i * step, step, min(chunk, n - i)) for i in range(0, n, chunk)]
+    with mp.get_context("fork").Pool(procs) as pool:
+        parts = pool.map(_points_chunk, jobs)
+    return np.stack([np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])])
+
+
 def team_worker(args, ctx=None):
     """rank > 0 of `--gpus N`: same SRS on cuda:rank, then serve slices of the leader's commitment MSMs (csrc/msm_team.cu)"""
     import gkr_msm_b200 as g
@@ -56,8 +79,7 @@ def run(args, ctx=None, team_name=None):
     cfg = DPP.pippenger_config(dl, xl, nbits, clm)
     n = 1 << xl
     t0 = time.perf_counter()
-    pts = H.te_points_arithmetic_progression(0x1234567 + args.seed, 0x9E3779B97F4A7C15, n)
-    points_xy = np.stack([to_limbs([p[0] for p in pts]), to_limbs([p[1] for p in pts])])
+    points_xy = gen_points(0x1234567 + args.seed, 0x9E3779B97F4A7C15, n, getattr(args, "gen_procs", 1))
     raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
     nbytes = nbits // 8  # from_le_bytes_mod_order(&bytes[..num_bits / 8]), pippenger.rs:465-467
     coefs = np.zeros((n, 4), np.uint64)
@@ -68,6 +90,8 @@ def run(args, ctx=None, team_name=None):
     t_inputs = time.perf_counter() - t0
 
     ctx = ctx or g.Context(0)
+    if getattr(args, "peer_pool", 0) > 1:  # the other GPUs of the box lend their HBM (gkr_ctx_peer_pool): instances beyond 180 GB
+        ctx.peer_pool(args.peer_pool)
     t0 = time.perf_counter()
     nv = xl + clm
     tau = srs_tau(args.seed)
@@ -116,7 +140,11 @@ def run(args, ctx=None, team_name=None):
         if args.python_host:
             dense_output, claims, pair = DPP.run_pippenger(ctx, tr, points_xy, coefs, cfg, r, key)
         else:
-            g.run_pippenger_native(ctx, tr, kzg.srs, kzg.g0, key.dev, points_xy, coefs, dl, xl, nbits, clm, to_limbs(r))
+            native_out = g.run_pippenger_native(ctx, tr, kzg.srs, kzg.g0, key.dev, points_xy, coefs, dl, xl, nbits, clm, to_limbs(r))
+            if getattr(args, "dump", "") and rep == args.reps - 1:  # everything tests/verify_dumped_proof.py needs besides the seed
+                np.savez(args.dump, proof=np.frombuffer(tr.proof(), dtype=np.uint8), dense=np.ascontiguousarray(native_out[0]),
+                         evs=np.ascontiguousarray(native_out[1]), pair=np.ascontiguousarray(native_out[2]), r=to_limbs(r),
+                         meta=np.array([xl, dl, nbits, clm, args.seed], dtype=np.int64), tau=to_limbs([tau]))
         ctx.sync()
         times.append(time.perf_counter() - t0)
         launches = ctx.launches - l0
@@ -153,7 +181,8 @@ def run(args, ctx=None, team_name=None):
         "proof_bytes": proof_len, "gpu_launches": launches, "input_generation_s": t_inputs, "srs_setup_s": t_setup,
         "srs_points": 2 * (1 << nv) - 1, "srs_fixed_base_window": pre_c, "n_gpus": getattr(args, "gpus", 1),
         "multi_gpu": "commitment MSMs of >= 2^18 points split by point range over the GPUs (csrc/msm_team.cu); everything else on GPU 0" if getattr(args, "gpus", 1) > 1 else None,
-        "round_waits": hs[2], "round_wait_ms": hs[1] / 1e6, "round_launch_call_ms": hs[0] / 1e6})
+        "round_waits": hs[2], "round_wait_ms": hs[1] / 1e6, "round_launch_call_ms": hs[0] / 1e6,
+        "peer_pool_gpus": getattr(args, "peer_pool", 0), "peer_pool_peak_gib": (ctx.peer_pool(0)[1] / 2**30) if getattr(args, "peer_pool", 0) > 1 else None})
 
 
 def main():
@@ -167,6 +196,9 @@ def main():
     ap.add_argument("--profile", action="store_true", help="print a per-phase breakdown of the last repetition (python host)")
     ap.add_argument("--python-host", action="store_true", help="time the python orchestration instead of gkr_run_pippenger (C++)")
     ap.add_argument("--precompute-c", type=int, default=-1, help="window of the fixed-base SRS table (0: none; default: 20 from x + clm >= 19)")
+    ap.add_argument("--peer-pool", type=int, default=0, help="N > 1: GPUs 1..N-1 lend their HBM to the prover on GPU 0 (gkr_ctx_peer_pool)")
+    ap.add_argument("--gen-procs", type=int, default=1, help="worker processes for the synthetic points (host-side python)")
+    ap.add_argument("--dump", default="", help="write proof, outputs and pairing pair of the last repetition to this .npz (tests/verify_dumped_proof.py)")
     ap.add_argument("--mem", action="store_true", help="sample the device memory in use while proving (pynvml) and report the peak")
     ap.add_argument("--gpus", type=int, default=1, help="N > 1: spawn N - 1 worker processes (cuda:1..N-1) that share the large commitment MSMs")
     ap.add_argument("--team-worker", type=int, default=0, help=argparse.SUPPRESS)
