@@ -31,12 +31,23 @@ def main():
     raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
     b = raw.view(np.uint8).reshape(n, 32).copy()
     b[:, nbits // 8:] = 0
-    words = b.view(np.uint64).reshape(n, 4).astype(object)
+    # sum_i c_i (k0 + i step) = k0 * sum_i c_i + step * sum_i i c_i, exactly, with numpy: the scalars as 16-bit digits (16 per scalar),
+    # the index range in blocks of 2^20 so that every partial sum stays below 2^63
     k0, step = 0x1234567 + seed, 0x9E3779B97F4A7C15
-    total = 0
-    for i in range(n):
-        c = int(words[i, 0]) | (int(words[i, 1]) << 64) | (int(words[i, 2]) << 128) | (int(words[i, 3]) << 192)
-        total += c * (k0 + i * step)
+    q = b.view(np.uint16).reshape(n, 16).astype(np.uint64)
+    s0, s1 = 0, 0
+    blk = 1 << 20
+    for lo in range(0, n, blk):
+        hi = min(n, lo + blk)
+        part = q[lo:hi]
+        idx = np.arange(hi - lo, dtype=np.uint64)[:, None]
+        col = part.sum(axis=0)             # < 2^16 * 2^20
+        icol = (part * idx).sum(axis=0)    # < 2^16 * 2^20 * 2^20
+        for j in range(16):
+            cj, ij = int(col[j]) << (16 * j), int(icol[j]) << (16 * j)
+            s0 += cj
+            s1 += ij + lo * cj
+    total = k0 * s0 + step * s1
     expected = CV.te_mul(total % CV.TE_SUBGROUP_ORDER, CV.TE_GEN)
     print(f"closed-form MSM over {n} scalars: {time.time() - t0:.1f} s", flush=True)
     cfg = PP.pippenger_config(dl, x, nbits, clm)
