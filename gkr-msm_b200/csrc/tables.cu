@@ -114,7 +114,11 @@ void gkr_big_mem_stats(uint64_t out[2], bool reset_peak) {
 }
 
 cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
-    if (n < GKR_BIG_BLOCK) return cudaMallocAsync(p, n, s);
+    if (n < GKR_BIG_BLOCK) {
+        cudaError_t es = cudaMallocAsync(p, n, s);
+        if (es != cudaSuccess) fprintf(stderr, "[gkr-msm-b200] small allocation of %zu bytes failed: %s\n", n, cudaGetErrorString(es));
+        return es;
+    }
     std::lock_guard<std::mutex> lk(g_big_mutex);
     BigCache& c = g_big[s];
     auto it = c.free_blocks.lower_bound(n);
@@ -129,7 +133,13 @@ cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
     // peer placement is exercised by instances of any size
     static const long long local_limit = getenv("GKR_PEER_POOL_LOCAL_LIMIT_MIB") ? atoll(getenv("GKR_PEER_POOL_LOCAL_LIMIT_MIB")) : -1;
     cudaError_t e = cudaErrorMemoryAllocation;
-    const bool force_peer = local_limit >= 0 && !g_peer.peers.empty() && g_big_live - g_peer.remote_live + n > ((uint64_t)local_limit << 20);
+    bool force_peer = local_limit >= 0 && !g_peer.peers.empty() && g_big_live - g_peer.remote_live + n > ((uint64_t)local_limit << 20);
+    if (!force_peer && !g_peer.peers.empty()) {
+        // with a peer pool the home GPU keeps 2 GiB free for the small allocations of the stream-ordered pool (parameter arrays,
+        // result buffers): a large block that would eat into that goes to a peer
+        size_t f = 0, t = 0;
+        if (cudaMemGetInfo(&f, &t) == cudaSuccess && f < n + ((size_t)2 << 30)) force_peer = true;
+    }
     if (!force_peer) e = cudaMallocAsync(p, n, s);
     if (e != cudaSuccess && !force_peer) {  // out of memory: give the cached blocks back and retry once
         for (auto& kv : c.free_blocks) release_block(kv.second, kv.first, s);
@@ -148,6 +158,9 @@ cudaError_t gkr_malloc_async_impl(void** p, size_t n, cudaStream_t s) {
     if (e == cudaSuccess) {
         c.live[*p] = n;
         big_account((int64_t)n);
+    } else {
+        fprintf(stderr, "[gkr-msm-b200] allocation of %.1f MiB failed: %.2f GiB of tables live (%.2f GiB of them on %zu peer GPUs)\n", n / 1048576.0,
+                g_big_live / 1073741824.0, g_peer.remote_live / 1073741824.0, g_peer.peers.size());
     }
     return e;
 }

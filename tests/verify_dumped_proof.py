@@ -54,7 +54,10 @@ def main():
     r = fr_vec_from_mont_u64(d["r"])
     tau = fr_vec_from_mont_u64(d["tau"])[0]
     nv = x + clm
-    okey = PP.KnucklesKey(PP.KzgKey(tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2)
+    # the VERIFIER's key: KnucklesProvingKey::new also tabulates 2^(nv+1) inverses for compute_t (prover side only; hours of python
+    # at nv = 26), so the object is assembled without them
+    okey = PP.KnucklesKey.__new__(PP.KnucklesKey)
+    okey.kzg, okey.num_vars, okey.k, okey.inverses = PP.KzgKey(tau, CV.G1_GEN, 2 * (1 << nv) - 1), nv, 2, None
     dense_output = [fr_vec_from_mont_u64(t) for t in d["dense"]]
     evs = fr_vec_from_mont_u64(d["evs"])
     proof = d["proof"].tobytes()
