@@ -75,8 +75,10 @@ cudaError_t peer_malloc(void** p, size_t n) {
             best = d;
         }
     }
+    // what a peer keeps for itself (GKR_PEER_RESERVE_GIB, default 0.25): raise it when the peers also run MSM team workers
+    static const double reserve_gib = getenv("GKR_PEER_RESERVE_GIB") ? atof(getenv("GKR_PEER_RESERVE_GIB")) : 0.25;
     cudaError_t e = cudaErrorMemoryAllocation;
-    if (best >= 0 && best_free > n + ((size_t)1 << 28)) {
+    if (best >= 0 && (double)best_free > (double)n + reserve_gib * 1073741824.0) {
         cudaSetDevice(best);
         e = cudaMalloc(p, n);
         if (e == cudaSuccess) {
