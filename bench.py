@@ -446,6 +446,43 @@ def run_ours(args, rank, world, local_rank):
             pip20_multi = {"error": repr(e)}
         barrier()
 
+    # ---- N >= 4: BASELINE config[3] itself -- x = 24, 253-bit scalars, clm 2: 430 GiB of live tables.  Rank 0 proves with its tables
+    # pooled over the HBM of all ranks' GPUs (gkr_ctx_peer_pool, NVLink peer access); the other ranks serve their share of the G1
+    # work (msm_team.cu) from the same GPUs.  One proof is ~6 s on 8 GPUs, ~12 s on 4; inputs and SRS take another ~35 s.
+    # OPT-IN (--config3, 8 GPUs): with only 4 GPUs the team workers' own memory leaves no peer with room for the largest single
+    # slab (77 GiB) -- there the instance runs with the peer pool alone (tools/bench_pippenger.py --peer-pool 4, 11.7 s).
+    config3 = None
+    if world >= 8 and args.config3 and not args.no_pippenger:
+        import importlib.util
+        import subprocess
+        spec = importlib.util.spec_from_file_location("bench_pippenger", os.path.join(ROOT, "tools", "bench_pippenger.py"))
+        bp = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bp)
+        os.environ.setdefault("GKR_PEER_RESERVE_GIB", "20")  # what every GPU keeps for its own team worker
+        os.environ.setdefault("GKR_TEAM_TIMEOUT_S", "180")
+        tname = f"/gkr_c3_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+        pfile = f"/dev/shm/gkr_c3_points_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}.npy"
+        pa = argparse.Namespace(x_logsize=24, d_logsize=8, nbits=253, clm=2, reps=2, seed=7, profile=False, python_host=False, gpus=world,
+                                team_worker=rank, team_name=tname, team_tau="%x" % bp.srs_tau(7), peer_pool=world, precompute_c=0,
+                                points_file=pfile, dump="", mem=False, gen_procs=1)
+        try:
+            if rank == 0:
+                subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "bench_pippenger.py"), "--x-logsize", "24", "--gen-procs", "16",
+                                       "--gen-only", pfile], timeout=600)
+                r = bp.run(pa, ctx=ctx, team_name=tname)
+                os.unlink(pfile)
+                config3 = {"prove_ms": r["prove_ms_best"], "prove_ms_all": r["prove_ms_all"], "proof_bytes": r["proof_bytes"],
+                           "config": f"BASELINE config[3]: x_logsize 24, d_logsize 8, nbits 253 (full width), commitment-log-multiplicity 2 on {world} GPUs",
+                           "incidences": r["incidences"], "peer_pool_peak_gib": r["peer_pool_peak_gib"], "gpu_launches_rank0": r["gpu_launches"],
+                           "how": "rank 0 runs gkr_run_pippenger; its tables beyond 180 GB live in the HBM of the other GPUs (NVLink peer access); the "
+                                  "commitment MSMs and the c / d bucket sums are split over all GPUs (csrc/msm_team.cu).  Verification of the same "
+                                  "proof: profiles/r02_config3_x23_x24_peer_pool.txt"}
+            else:
+                bp.team_worker(pa, ctx=ctx)
+        except Exception as e:  # pragma: no cover
+            config3 = {"error": repr(e)}
+        barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -511,7 +548,7 @@ def run_ours(args, rank, world, local_rank):
                                   "the max-over-ranks timing all-reduce; no device collective on the data path"),
                    "l2": "inputs (1.5 GiB per GPU) larger than the 126 MB L2", "transcript": "merlin on host, one challenge per round"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "pippenger_prove": pip, "pippenger_prove_2e20": pip20, "strong_scaling": strong, "vecvec_rows": vecvec_rows,
+        "pippenger_prove": pip, "pippenger_prove_2e20": pip20, "strong_scaling": strong, "vecvec_rows": vecvec_rows, "pippenger_config3_x24": config3,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -530,6 +567,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pippenger", action="store_true")
+    ap.add_argument("--config3", action="store_true", help="N >= 8: also prove BASELINE config[3] at x = 24 (about a minute of inputs / SRS, 6 s per proof)")
     ap.add_argument("--no-vecvec", action="store_true", help="skip the row-sharded ragged sumcheck leg")
     ap.add_argument("--vecvec-row-log", type=int, default=11)
     ap.add_argument("--vecvec-col-log", type=int, default=12, help="log2 of the rows per GPU of the row-sharded ragged sumcheck leg")

@@ -79,7 +79,11 @@ def run(args, ctx=None, team_name=None):
     cfg = DPP.pippenger_config(dl, xl, nbits, clm)
     n = 1 << xl
     t0 = time.perf_counter()
-    points_xy = gen_points(0x1234567 + args.seed, 0x9E3779B97F4A7C15, n, getattr(args, "gen_procs", 1))
+    if getattr(args, "points_file", ""):  # generated beforehand by `--gen-only` (bench.py: a process that holds a CUDA context does not fork)
+        points_xy = np.load(args.points_file)
+        assert points_xy.shape == (2, n, 4)
+    else:
+        points_xy = gen_points(0x1234567 + args.seed, 0x9E3779B97F4A7C15, n, getattr(args, "gen_procs", 1))
     raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
     nbytes = nbits // 8  # from_le_bytes_mod_order(&bytes[..num_bits / 8]), pippenger.rs:465-467
     coefs = np.zeros((n, 4), np.uint64)
@@ -199,6 +203,8 @@ def main():
     ap.add_argument("--peer-pool", type=int, default=0, help="N > 1: GPUs 1..N-1 lend their HBM to the prover on GPU 0 (gkr_ctx_peer_pool)")
     ap.add_argument("--gen-procs", type=int, default=1, help="worker processes for the synthetic points (host-side python)")
     ap.add_argument("--dump", default="", help="write proof, outputs and pairing pair of the last repetition to this .npz (tests/verify_dumped_proof.py)")
+    ap.add_argument("--gen-only", default="", help="only generate the synthetic points into this .npy file and exit (no GPU work)")
+    ap.add_argument("--points-file", default="", help="points generated by --gen-only")
     ap.add_argument("--mem", action="store_true", help="sample the device memory in use while proving (pynvml) and report the peak")
     ap.add_argument("--gpus", type=int, default=1, help="N > 1: spawn N - 1 worker processes (cuda:1..N-1) that share the large commitment MSMs")
     ap.add_argument("--team-worker", type=int, default=0, help=argparse.SUPPRESS)
@@ -207,6 +213,9 @@ def main():
     args = ap.parse_args()
     if args.team_worker > 0:
         team_worker(args)
+        return
+    if args.gen_only:
+        np.save(args.gen_only, gen_points(0x1234567 + args.seed, 0x9E3779B97F4A7C15, 1 << args.x_logsize, args.gen_procs))
         return
     print(json.dumps(run(args)), flush=True)
 
