@@ -415,6 +415,13 @@ class SumcheckObject:
     def round(self) -> int:
         return int(self.ctx.lib.gkr_so_round(self.h))
 
+    def set_prelaunch(self, on: bool = True):
+        """gkr_so_set_prelaunch: promise the strict unipoly -> bind alternation with no other device work in between, so that small
+        rounds are enqueued one round ahead (the challenge travels through a mailbox in mapped host memory)"""
+        self.ctx.lib.gkr_so_set_prelaunch.restype = C.c_int
+        self.ctx.lib.gkr_so_set_prelaunch.argtypes = [_vp, C.c_int]
+        self.ctx.check(self.ctx.lib.gkr_so_set_prelaunch(self.h, 1 if on else 0))
+
     def destroy(self):
         if self.h:
             self.ctx.lib.gkr_so_destroy(self.h)

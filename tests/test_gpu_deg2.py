@@ -158,3 +158,49 @@ def test_vecvec_sumcheck_prover_verifier(ctx):
     tv = ProofTranscript2.start_verifier(b"fgstglsp", proof)
     vpoint, vevs = prot.verify(tv, (point, evs))
     assert vevs == [S.evaluate_poly(d, vpoint) for d in dense]
+
+
+@pytest.mark.parametrize("colv", [0, 2])
+def test_deg2_prelaunched_rounds_release_and_cancel(ctx, colv):
+    """gkr_so_set_prelaunch on the Deg2 objects driven from here with alternating 128-bit challenges (the queued kernel is released
+    through the mailbox) and full-width ones (cancelled, ordinary launch): dense object and ragged VecVec object incl. its dense
+    tail, every round against the oracle"""
+    rng = random.Random(7700 + colv)
+    nv = 7
+    # dense Deg2
+    parts = [(g.GATE_PRJ_L1, 1)]
+    gate = oracle_stack(parts)
+    data = [[rng.randrange(P) for _ in range(1 << nv)] for _ in range(gate.n_ins)]
+    point = [rng.randrange(P) for _ in range(nv)]
+    gamma = rng.randrange(P)
+    claims = claims_of(gate, data, S.eq_poly_sequence_last(point))
+    oso = S.DenseDeg2SumcheckObjectSO.rlc(data, gate, claims, point, gamma)
+    dso = ctx.deg2_dense_so(parts, [ctx.upload(to_limbs(p)) for p in data], to_limbs(S.make_gamma_pows(gamma, gate.n_outs)), to_limb1(oso.claim), to_limbs(point))
+    dso.set_prelaunch(True)
+    for r in range(nv):
+        oso.unipoly()
+        assert from_limbs(dso.unipoly()) == oso.last_evals, f"dense round {r}"
+        t = rng.randrange(1 << 128) if r % 3 else rng.randrange(P)
+        oso.bind(t)
+        dso.bind(to_limb1(t))
+    assert from_limbs(dso.final_evals()) == oso.final_evals()
+    dso.destroy()
+    # ragged VecVec
+    rowv = nv - colv
+    gid, vgate = g.GATE_PRJ_L1, BASE[g.GATE_PRJ_L1]()
+    pads = [(0, 0), (1, 1), (1, 1)] * 2
+    vdata, opolys, lens = make_vecvec(rng, 2, rowv, colv, vgate.n_ins, pads)
+    vclaims = claims_of(vgate, [p.vec() for p in opolys], S.eq_poly_sequence_last(point))
+    voso = S.VecVecDeg2SumcheckObjectSO.rlc(opolys, vgate, vclaims, point, colv, gamma)
+    dpolys = [ctx.upload_vecvec([to_limbs(r) if len(r) else np.zeros((0, 4), np.uint64) for r in vdata[j]], to_limb1(pads[j][0]),
+                                to_limb1(pads[j][1]), rowv, colv) for j in range(vgate.n_ins)]
+    vdso = ctx.deg2_vecvec_so(gid, dpolys, to_limbs(S.make_gamma_pows(gamma, max(vgate.n_outs, 2))), to_limb1(voso.claim), to_limbs(point), colv)
+    vdso.set_prelaunch(True)
+    for r in range(nv):
+        voso.unipoly()
+        assert from_limbs(vdso.unipoly()) == voso.last_evals, f"vecvec round {r}"
+        t = rng.randrange(1 << 128) if r % 3 else rng.randrange(P)
+        voso.bind(t)
+        vdso.bind(to_limb1(t))
+    assert from_limbs(vdso.final_evals()) == voso.final_evals()
+    vdso.destroy()

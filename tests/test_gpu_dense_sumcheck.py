@@ -17,10 +17,12 @@ from tests.util import from_limbs, rand_chal128, to_limb1, to_limbs
 pytestmark = pytest.mark.gpu
 
 
-def _run_rounds(ctx, so_kind, gate_id, oracle_gate, polys, nv, claim, rng, gate_param=0, consts=None, check_tables=False):
+def _run_rounds(ctx, so_kind, gate_id, oracle_gate, polys, nv, claim, rng, gate_param=0, consts=None, check_tables=False, prelaunch=False):
     tables = [ctx.upload(to_limbs(p)) for p in polys]
     dso = ctx.dense_so(so_kind, gate_id, tables, nv, to_limb1(claim), gate_param=gate_param,
                        consts=None if consts is None else to_limbs(consts))
+    if prelaunch:  # small rounds enqueued one round ahead: 128-bit challenges release the waiting kernel, full-width ones cancel it
+        dso.set_prelaunch(True)
     oso = S.DenseSumcheckObjectSO(polys, oracle_gate, nv, claim)
     assert dso.degree == oracle_gate.deg and dso.num_polys == oracle_gate.n_ins
     for r in range(nv):
@@ -256,3 +258,24 @@ def test_c_oracle_parity_across_kernel_switch(ctx, so_kind, gate, ntab):
         assert np.array_equal(evs[r], oev[r]), f"round {r}"
     assert np.array_equal(so.final_evals(), ofe)
 
+
+
+@pytest.mark.parametrize("nv", [3, 7, 10, 13])
+def test_prelaunched_rounds_release_and_cancel(ctx, nv):
+    """gkr_so_set_prelaunch on a dense object driven from here: the loop alternates 128-bit challenges (the pre-launched kernel is
+    released through the mailbox) and full-width ones (it is cancelled and the round is launched the ordinary way) -- every round
+    polynomial, claim and final evaluation against the big-int oracle; then the same for an EqWrapper(GammaWrapper(..)) object"""
+    rng = random.Random(4100 + nv)
+    polys = [[rng.randrange(P) for _ in range(1 << nv)] for _ in range(3)]
+    f = G.Prod3()
+    claim = sum(f.exec([p[i] for p in polys]) for i in range(1 << nv)) % P
+    _run_rounds(ctx, g.SO_PLAIN, g.GATE_PROD3, f, polys, nv, claim, rng, check_tables=True, prelaunch=True)
+    gid, cls = EQ_GAMMA_GATES[3]
+    gate = cls()
+    gamma = rng.randrange(P)
+    w = G.EqWrapper(G.GammaWrapper(gate, gamma))
+    point = [rng.randrange(P) for _ in range(nv)]
+    data = [[rng.randrange(P) for _ in range(1 << nv)] for _ in range(gate.n_ins)]
+    data.append(S.eq_poly_sequence_last(point))
+    claim = sum(w.exec([p[i] for p in data]) for i in range(1 << nv)) % P
+    _run_rounds(ctx, g.SO_EQ_GAMMA, gid, w, data, nv, claim, rng, consts=S.make_gamma_pows(gamma, max(gate.n_outs, 2)), prelaunch=True)
