@@ -20,10 +20,23 @@ impl GpuCtx {
         Rc::new(Self { raw })
     }
 
-    /// thread-local default context on device `GKR_DEVICE` (default 0)
+    /// thread-local default context on device `GKR_DEVICE` (default 0); `GKR_PEER_POOL=N` lends it the HBM of GPUs 0..N
+    /// (instances beyond one GPU's memory: `examples/pippenger --x-logsize 24` with full-width scalars needs 430 GiB)
     pub fn current() -> Rc<Self> {
-        thread_local! { static CTX: Rc<GpuCtx> = GpuCtx::new(std::env::var("GKR_DEVICE").ok().and_then(|v| v.parse().ok()).unwrap_or(0)); }
+        thread_local! { static CTX: Rc<GpuCtx> = {
+            let c = GpuCtx::new(std::env::var("GKR_DEVICE").ok().and_then(|v| v.parse().ok()).unwrap_or(0));
+            if let Some(n) = std::env::var("GKR_PEER_POOL").ok().and_then(|v| v.parse::<i32>().ok()) { c.peer_pool(n); }
+            c
+        }; }
         CTX.with(|c| c.clone())
+    }
+
+    /// `gkr_ctx_peer_pool`: tables that do not fit the home GPU are placed on the other GPUs of the box (NVLink peer access);
+    /// returns (bytes on peers now, their peak)
+    pub fn peer_pool(&self, n_devices: i32) -> (u64, u64) {
+        let mut st = [0u64; 2];
+        self.check(unsafe { gkr_ctx_peer_pool(self.raw, n_devices, st.as_mut_ptr()) });
+        (st[0], st[1])
     }
 
     #[track_caller]

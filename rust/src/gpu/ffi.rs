@@ -29,6 +29,7 @@ pub const GATE_AFF_L1_BITCHECK2: c_int = 13;
 extern "C" {
     pub fn gkr_ctx_create(device: c_int, out: *mut *mut gkr_ctx) -> c_int;
     pub fn gkr_ctx_destroy(ctx: *mut gkr_ctx);
+    pub fn gkr_ctx_peer_pool(ctx: *mut gkr_ctx, n_devices: c_int, out_stats: *mut u64) -> c_int;
     pub fn gkr_last_error(ctx: *const gkr_ctx) -> *const c_char;
     pub fn gkr_ctx_sync(ctx: *mut gkr_ctx) -> c_int;
 
