@@ -2,6 +2,7 @@
 // block / grid reduction of per-thread field accumulators (warp shuffles -> shared memory -> last block).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <ctime>
@@ -48,13 +49,16 @@ struct RoundOut {  // kernel-side view of a slot
 // publishing a result and says so in `timed_out` (the host relaunches the round the ordinary way): a pre-launched kernel can
 // never hang the device.  The challenge travels as the plain 128-bit integer of transcript.challenge(128).
 struct __attribute__((aligned(64))) GkrMailbox {
-    volatile uint32_t seq;        // host -> device, written last
+    volatile uint32_t seq;        // host -> device, written after cmd / t
     volatile uint32_t cmd;        // 1: go, the challenge is in t; 2: cancelled
     volatile uint32_t t[4];       // the 128-bit challenge as a plain integer
-    uint32_t pad_[2];
+    uint32_t pad_;
+    volatile uint32_t seq2;       // the same sequence number at the END of the 32-byte sector: should the 256-bit poll ever be served as
+                                  // two 16-byte reads, a torn snapshot shows two different numbers and the poll is simply repeated
     uint32_t pad2_[7];
     volatile uint32_t timed_out;  // device -> host: seq of a launch that gave up
 };
+static_assert(offsetof(GkrMailbox, seq2) == 28 && sizeof(GkrMailbox) == 64, "mailbox layout: one 32-byte sector + the reply word");
 #define GKR_MAILBOX_TIMEOUT_NS 2000000000ull
 struct MailboxRef {  // kernel-side view; box == nullptr: the challenge travels in the kernel arguments
     GkrMailbox* box = nullptr;
@@ -102,6 +106,7 @@ struct gkr_ctx {
         for (int k = 0; k < 4; k++) m->t[k] = t4 ? t4[k] : 0u;
         m->cmd = cmd;
         __atomic_store_n((uint32_t*)&m->seq, seq, __ATOMIC_RELEASE);
+        __atomic_store_n((uint32_t*)&m->seq2, seq, __ATOMIC_RELEASE);
     }
     bool mailbox_timed_out(int slot, uint32_t seq) const { return mbox_host[slot].timed_out == seq; }
     RoundOut round_out(int slot) {  // next launch on this slot
@@ -292,7 +297,7 @@ __device__ __forceinline__ bool gkr_mailbox_wait(const MailboxRef& m, uint32_t* 
                              : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
                              : "l"(m.box)
                              : "memory");
-                if (w[0] == m.seq) break;
+                if (w[0] == m.seq && w[7] == m.seq) break;
                 if ((++polls & 15u) == 0) {
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
                     if (t1 - t0 > GKR_MAILBOX_TIMEOUT_NS) {
